@@ -1,0 +1,269 @@
+// rz_ref_tool — drives the REFERENCE'S OWN CPU implementation (compiled in place from
+// /root/reference/RayZath by oracle/Makefile) for parity vectors and the CPU baseline.
+//
+// TEST INFRASTRUCTURE ONLY: nothing in the product path links or executes this. It is used by
+// tests/, scripts/make_golden.py and bench.py's reference arm / cpu_baseline leg.
+//
+// commands
+//   dumpscene <scene.json> <out.rzs>            flattened world (C-ABI arrays) + camera 0 + reference pixel-centre rays
+//   trace     <scene.json> <rays.rzs> <out.rzs> closest hit per ray through CPU::Kernel (cpu_engine_kernel.cpp:254-352)
+//   traceany  <scene.json> <rays.rzs> <out.rzs> shadow mask per ray through CPU::Kernel::anyIntersection (:398-481)
+//   render    <scene.json> <passes> <out.rzs|-> [max_depth] [spot_samples] [direct_samples]
+//                                               N x Engine::renderWorld(CPU) ; dumps float accumulator, RGBA8, depth ; prints timing JSON
+//   headless  <tasks.json> [report_dir] [-r]    the reference's own Application/headless.cpp entry
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <filesystem>
+#include <iostream>
+#include <string>
+#include <thread>
+
+// reach the CPU kernel's private traversal entry points and the accumulator (test tool only)
+#define private public
+#define protected public
+#include "rayzath.hpp"
+#include "cpu_engine.hpp"
+#include "cpu_engine_core.hpp"
+#include "cpu_engine_renderer.hpp"
+#include "cpu_engine_kernel.hpp"
+#include "cpu_render_utils.hpp"
+#undef private
+#undef protected
+
+#include "../rayzath_b200/host/world_flatten.hpp"
+#include "rzs_io.hpp"
+
+#ifdef RZ_WITH_HEADLESS
+#include "headless.hpp"
+#endif
+
+namespace RZ = RayZath::Engine;
+
+static RZ::World& loadWorld(const std::string& scene_path)
+{
+	auto& engine = RZ::Engine::instance();
+	auto& world = engine.world();
+	world.loader().loadScene(scene_path);
+	auto& cameras = world.container<RZ::ObjectType::Camera>();
+	for (uint32_t i = 0; i < cameras.count(); ++i)
+		if (cameras[i]) cameras[i]->update();
+	world.update();
+	return world;
+}
+
+static void writeScene(rzs::Writer& w, const rzb_host::FlatScene& s)
+{
+	w.add("mesh_nodes", s.mesh_nodes);
+	w.add("triangles", s.triangles);
+	w.add("tri_host_index", s.tri_host_index);
+	w.add("meshes", s.meshes);
+	w.add("instance_nodes", s.instance_nodes);
+	w.add("instances", s.instances);
+	w.add("instance_materials", s.instance_materials);
+	w.add("materials", s.materials);
+	std::vector<rzb_map> maps = s.maps;
+	for (size_t i = 0; i < maps.size(); ++i)
+	{
+		const size_t texel = maps[i].format == RZB_MAP_R8 ? 1 : 4;
+		w.add("map_pixels_" + std::to_string(i), maps[i].pixels, uint32_t(texel), uint64_t(maps[i].width) * maps[i].height);
+		maps[i].pixels = nullptr;
+	}
+	w.add("maps", maps);
+	w.add("direct_lights", s.direct_lights);
+	w.add("spot_lights", s.spot_lights);
+	w.addValue("world_material", s.world_material);
+	w.addValue("default_material", s.default_material);
+}
+
+static int cmdDumpScene(const std::string& scene, const std::string& out_path)
+{
+	auto& world = loadWorld(scene);
+	rzb_host::FlatScene flat;
+	rzb_host::WorldFlattener(world, flat).run();
+	rzs::Writer w;
+	writeScene(w, flat);
+
+	auto& cameras = world.container<RZ::ObjectType::Camera>();
+	if (cameras.count() != 0 && cameras[0])
+	{
+		auto& cam = *cameras[0];
+		w.addValue("camera", rzb_host::flattenCamera(cam));
+		// the fixed primary-ray set: the reference's own pixel-centre rays (cpu_engine_kernel.cpp:180-204)
+		RZ::CPU::Kernel kernel;
+		kernel.setWorld(world);
+		const uint32_t W = cam.width(), H = cam.height();
+		std::vector<float> o(size_t(W) * H * 3), d(size_t(W) * H * 3), nf(size_t(W) * H * 2);
+		for (uint32_t y = 0; y < H; ++y)
+			for (uint32_t x = 0; x < W; ++x)
+			{
+				RZ::CPU::RangedRay ray;
+				kernel.generateSimpleRay(cam, ray, Math::vec2ui32(x, y));
+				const size_t i = size_t(y) * W + x;
+				o[3 * i] = ray.origin.x; o[3 * i + 1] = ray.origin.y; o[3 * i + 2] = ray.origin.z;
+				d[3 * i] = ray.direction.x; d[3 * i + 1] = ray.direction.y; d[3 * i + 2] = ray.direction.z;
+				nf[2 * i] = ray.near_far.x; nf[2 * i + 1] = ray.near_far.y;
+			}
+		w.add("ray_origins", o.data(), 12, size_t(W) * H);
+		w.add("ray_directions", d.data(), 12, size_t(W) * H);
+		w.add("ray_near_far", nf.data(), 8, size_t(W) * H);
+	}
+	w.write(out_path);
+	std::printf("{\"meshes\": %zu, \"triangles\": %zu, \"mesh_nodes\": %zu, \"instances\": %zu, \"instance_nodes\": %zu}\n",
+		flat.meshes.size(), flat.triangles.size(), flat.mesh_nodes.size(), flat.instances.size(), flat.instance_nodes.size());
+	return 0;
+}
+
+struct RaySet
+{
+	size_t n = 0;
+	const float* o = nullptr;
+	const float* d = nullptr;
+	const float* nf = nullptr;
+};
+static RaySet raysOf(const std::map<std::string, rzs::Array>& arrays)
+{
+	RaySet r;
+	const auto& o = arrays.at("ray_origins");
+	r.n = o.count;
+	r.o = o.as<float>();
+	r.d = arrays.at("ray_directions").as<float>();
+	r.nf = arrays.at("ray_near_far").as<float>();
+	return r;
+}
+
+static int cmdTrace(const std::string& scene, const std::string& rays_path, const std::string& out_path, bool any)
+{
+	auto& world = loadWorld(scene);
+	const auto arrays = rzs::read(rays_path);
+	const RaySet rays = raysOf(arrays);
+	RZ::CPU::Kernel kernel;
+	kernel.setWorld(world);
+	const auto& instances = world.container<RZ::ObjectType::Instance>();
+
+	std::vector<rzb_hit> hits;
+	std::vector<float> masks;
+	if (any) masks.resize(rays.n * 4);
+	else hits.resize(rays.n);
+
+	const unsigned n_threads = std::max(1u, std::thread::hardware_concurrency());
+	std::vector<std::thread> threads;
+	const auto t0 = std::chrono::steady_clock::now();
+	for (unsigned t = 0; t < n_threads; ++t)
+		threads.emplace_back([&, t]() {
+			for (size_t i = t; i < rays.n; i += n_threads)
+			{
+				RZ::CPU::RangedRay ray;
+				ray.origin = Math::vec3f32(rays.o[3 * i], rays.o[3 * i + 1], rays.o[3 * i + 2]);
+				ray.direction = Math::vec3f32(rays.d[3 * i], rays.d[3 * i + 1], rays.d[3 * i + 2]);
+				ray.near_far = Math::vec2f32(rays.nf[2 * i], rays.nf[2 * i + 1]);
+				if (any)
+				{
+					const Graphics::ColorF m = kernel.anyIntersection(ray);
+					masks[4 * i] = m.red; masks[4 * i + 1] = m.green; masks[4 * i + 2] = m.blue; masks[4 * i + 3] = m.alpha;
+					continue;
+				}
+				rzb_hit h{};
+				h.instance = RZB_NO_INDEX; h.triangle = RZB_NO_INDEX;
+				// Kernel::closestIntersection(RangedRay&, SurfaceProperties&) without the surface analysis
+				// (cpu_engine_kernel.cpp:279-289)
+				RZ::CPU::TraversalResult traversal;
+				if (!instances.empty() && instances.root().boundingBox().rayIntersection(ray))
+					kernel.traverseWorld(instances.root(), ray, traversal);
+				if (traversal.closest_instance)
+				{
+					h.instance = traversal.instance_idx;
+					const auto& mesh = *traversal.closest_instance->mesh();
+					h.triangle = uint32_t(traversal.closest_triangle - &mesh.triangles()[0]);
+					h.b1 = traversal.barycenter.x; h.b2 = traversal.barycenter.y;
+					h.external = traversal.external ? 1u : 0u;
+				}
+				h.t = ray.near_far.y;
+				hits[i] = h;
+			}
+		});
+	for (auto& th : threads) th.join();
+	const double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+
+	rzs::Writer w;
+	if (any) w.add("masks", masks.data(), 16, rays.n);
+	else w.add("hits", hits);
+	w.write(out_path);
+	std::printf("{\"rays\": %zu, \"seconds\": %.6f, \"threads\": %u}\n", rays.n, secs, n_threads);
+	return 0;
+}
+
+static int cmdRender(int argc, char** argv)
+{
+	const std::string scene = argv[2];
+	const uint32_t passes = uint32_t(std::atoi(argv[3]));
+	const std::string out_path = argv[4];
+	auto& engine = RZ::Engine::instance();
+	auto& world = engine.world();
+	const auto t_load0 = std::chrono::steady_clock::now();
+	world.loader().loadScene(scene);
+	if (argc > 5) engine.renderConfig().tracing().maxDepth(uint8_t(std::atoi(argv[5])));
+	if (argc > 6) engine.renderConfig().lightSampling().spotLight(uint8_t(std::atoi(argv[6])));
+	if (argc > 7) engine.renderConfig().lightSampling().directLight(uint8_t(std::atoi(argv[7])));
+	engine.renderEngine(RZ::Engine::RenderEngine::CPU);
+
+	// first call: world.update() (BVH build) + first pass; timed separately as in headless.cpp:209
+	engine.renderWorld(RZ::Engine::RenderEngine::CPU, true, true);
+	const double load_secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_load0).count();
+	const auto t0 = std::chrono::steady_clock::now();
+	for (uint32_t p = 1; p < passes; ++p)
+		engine.renderWorld(RZ::Engine::RenderEngine::CPU, true, true);
+	const double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+
+	auto& cameras = world.container<RZ::ObjectType::Camera>();
+	uint64_t rays = 0;
+	rzs::Writer w;
+	for (uint32_t i = 0; i < cameras.count(); ++i)
+	{
+		if (!cameras[i]) continue;
+		rays += cameras[i]->rayCount();
+		if (i != 0) continue;
+		auto& cam = *cameras[i];
+		auto& ctx = engine.m_cpu_engine->m_engine_core.m_renderer.m_contexts[cameras[i]];
+		w.add("accum", ctx.m_image.GetMapAddress(), 16, uint64_t(cam.width()) * cam.height());
+		w.add("rgba8", cam.imageBuffer().GetMapAddress(), 4, uint64_t(cam.width()) * cam.height());
+		w.add("depth", cam.depthBuffer().GetMapAddress(), 4, uint64_t(cam.width()) * cam.height());
+		const uint32_t res[2] = {cam.width(), cam.height()};
+		w.add("resolution", res, 4, 2);
+	}
+	if (out_path != "-") w.write(out_path);
+	const uint64_t timed_rays = passes > 1 ? rays / passes * (passes - 1) : 0;
+	std::printf("{\"passes\": %u, \"rays\": %llu, \"timed_passes\": %u, \"timed_rays\": %llu, \"seconds\": %.6f, "
+		"\"first_call_seconds\": %.6f, \"threads\": %u}\n",
+		passes, (unsigned long long)rays, passes > 1 ? passes - 1 : 0, (unsigned long long)timed_rays, secs, load_secs,
+		std::thread::hardware_concurrency());
+	return 0;
+}
+
+int main(int argc, char** argv)
+{
+	try
+	{
+		const std::string cmd = argc > 1 ? argv[1] : "";
+		if (cmd == "dumpscene" && argc == 4) return cmdDumpScene(argv[2], argv[3]);
+		if (cmd == "trace" && argc == 5) return cmdTrace(argv[2], argv[3], argv[4], false);
+		if (cmd == "traceany" && argc == 5) return cmdTrace(argv[2], argv[3], argv[4], true);
+		if (cmd == "render" && argc >= 5) return cmdRender(argc, argv);
+#ifdef RZ_WITH_HEADLESS
+		if (cmd == "headless" && argc >= 3)
+		{
+			std::filesystem::path report = argc > 3 && std::string(argv[3]) != "-r" ? argv[3] : "";
+			bool save = false;
+			for (int i = 3; i < argc; ++i) save |= std::string(argv[i]) == "-r";
+			return RayZath::Headless::Headless::instance().run(argv[2], report, save);
+		}
+#endif
+		std::fprintf(stderr, "usage: rz_ref_tool dumpscene|trace|traceany|render|headless ... (see oracle/ref_tool.cpp)\n");
+		return 2;
+	}
+	catch (const std::exception& e)
+	{
+		std::fprintf(stderr, "rz_ref_tool: %s\n", e.what());
+		return 1;
+	}
+}

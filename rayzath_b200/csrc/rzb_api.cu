@@ -1,0 +1,867 @@
+// C ABI of the B200 render path (include/rzb200.h): context, world mirror, frame loop, read-back.
+// Replaces the host half of the reference's CUDA engine:
+//   EngineCore::renderWorld      /root/reference/RayZath/cuda_engine_core.cu:32-128   (mirror + copy-back)
+//   Renderer::renderFunction     /root/reference/RayZath/cuda_engine_renderer.cu:73-262 (kernel sequence)
+//   World/Mesh/Instance/...::reconstruct  (chunked pinned-memory mirroring -> one flattened upload here)
+#include "rzb_kernels.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+using namespace rzb;
+
+static_assert(sizeof(rzb_node) == 32, "rzb_node");
+static_assert(sizeof(rzb_triangle) == 112, "rzb_triangle");
+static_assert(sizeof(rzb_mesh) == 16, "rzb_mesh");
+static_assert(sizeof(rzb_instance) == 100, "rzb_instance");
+static_assert(sizeof(rzb_material) == 64, "rzb_material");
+static_assert(sizeof(rzb_map) == 56, "rzb_map");
+static_assert(sizeof(rzb_direct_light) == 32, "rzb_direct_light");
+static_assert(sizeof(rzb_spot_light) == 48, "rzb_spot_light");
+static_assert(sizeof(rzb_camera) == 92, "rzb_camera");
+static_assert(sizeof(rzb_config) == 24, "rzb_config");
+static_assert(sizeof(rzb_hit) == 24, "rzb_hit");
+
+namespace
+{
+	thread_local std::string g_create_error;
+
+	struct DeviceBuffer
+	{
+		void* ptr = nullptr;
+		size_t bytes = 0;
+	};
+}
+
+struct rzb_ctx
+{
+	int device = 0;
+	int sm_count = 0;
+	cudaStream_t stream = nullptr;
+	cudaEvent_t ev_begin = nullptr, ev_end = nullptr, ev_stage[4] = {nullptr, nullptr, nullptr, nullptr};
+	std::string error;
+
+	std::vector<void*> scene_allocs;
+	DScene sc{};
+	bool has_scene = false, has_camera = false, frame_ready = false;
+	rzb_camera cam{};
+	rzb_config cfg{1u, 1u, 16u, 0u, 0u};
+
+	std::vector<void*> frame_allocs;
+	DFrame frame{};
+	uchar4* d_rgba = nullptr;
+	uint32_t* d_counters = nullptr;          // [0..2] work counters, [4..5] 64-bit shadow total
+	uint32_t shadow_capacity_alloc = 0;
+	void* d_shadow[3] = {nullptr, nullptr, nullptr};
+
+	// scratch for ray-set calls
+	DeviceBuffer scratch[4];
+
+	uint64_t passes = 0, launches = 0;
+	float last_render_ms = 0.0f, last_trace_ms = 0.0f, last_shade_ms = 0.0f, last_shadow_ms = 0.0f;
+	int trace_grid = 0, shadow_grid = 0, rays_grid = 0, any_grid = 0;
+};
+
+namespace
+{
+	int fail(rzb_ctx* ctx, int code, const std::string& msg)
+	{
+		if (ctx) ctx->error = msg;
+		else g_create_error = msg;
+		return code;
+	}
+	int cudaFail(rzb_ctx* ctx, cudaError_t e, const char* what)
+	{
+		return fail(ctx, RZB_ERR_CUDA, std::string(what) + ": " + cudaGetErrorName(e) + " (" + cudaGetErrorString(e) + ")");
+	}
+#define RZB_CUDA(ctx, call)                                     \
+	do                                                          \
+	{                                                           \
+		const cudaError_t rzb_e_ = (call);                      \
+		if (rzb_e_ != cudaSuccess) return cudaFail(ctx, rzb_e_, #call); \
+	} while (0)
+
+	struct DeviceGuard
+	{
+		int prev = -1;
+		explicit DeviceGuard(int dev)
+		{
+			cudaGetDevice(&prev);
+			if (prev != dev) cudaSetDevice(dev);
+			else prev = -1;
+		}
+		~DeviceGuard()
+		{
+			if (prev >= 0) cudaSetDevice(prev);
+		}
+	};
+
+	void freeAll(std::vector<void*>& v)
+	{
+		for (void* p : v) cudaFree(p);
+		v.clear();
+	}
+
+	template <typename T>
+	int upload(rzb_ctx* ctx, std::vector<void*>& owner, const T* host, size_t count, const T** out)
+	{
+		*out = nullptr;
+		void* d = nullptr;
+		const size_t bytes = std::max<size_t>(count, 1) * sizeof(T);
+		RZB_CUDA(ctx, cudaMalloc(&d, bytes));
+		owner.push_back(d);
+		if (count) RZB_CUDA(ctx, cudaMemcpyAsync(d, host, count * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
+		*out = static_cast<const T*>(d);
+		return RZB_OK;
+	}
+
+	int ensureScratch(rzb_ctx* ctx, int slot, size_t bytes)
+	{
+		DeviceBuffer& b = ctx->scratch[slot];
+		if (b.bytes >= bytes) return RZB_OK;
+		if (b.ptr) cudaFree(b.ptr);
+		b.ptr = nullptr;
+		b.bytes = 0;
+		RZB_CUDA(ctx, cudaMalloc(&b.ptr, bytes));
+		b.bytes = bytes;
+		return RZB_OK;
+	}
+
+	DCamera makeDeviceCamera(const rzb_camera& c)
+	{
+		DCamera d{};
+		d.width = c.width; d.height = c.height;
+		d.px = c.position[0]; d.py = c.position[1]; d.pz = c.position[2];
+		d.xx = c.axis_x[0]; d.xy = c.axis_x[1]; d.xz = c.axis_x[2];
+		d.yx = c.axis_y[0]; d.yy = c.axis_y[1]; d.yz = c.axis_y[2];
+		d.zx = c.axis_z[0]; d.zy = c.axis_z[1]; d.zz = c.axis_z[2];
+		d.tana = tanf(c.fov * 0.5f); // host libm, as cpu_engine_kernel.cpp:186
+		d.aspect = float(c.width) / float(c.height);
+		d.near_ = c.near_far[0]; d.far_ = c.near_far[1];
+		d.focal_distance = c.focal_distance;
+		d.aperture = c.aperture;
+		return d;
+	}
+
+	int gridFor(rzb_ctx* ctx, const void* kernel, int block)
+	{
+		int per_sm = 0;
+		if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, block, 0) != cudaSuccess || per_sm < 1) per_sm = 1;
+		return ctx->sm_count * per_sm;
+	}
+
+	int prepareFrame(rzb_ctx* ctx)
+	{
+		// (re)allocate per-camera buffers
+		freeAll(ctx->frame_allocs);
+		ctx->d_rgba = nullptr;
+		DFrame& f = ctx->frame;
+		f = DFrame{};
+		f.cam = makeDeviceCamera(ctx->cam);
+		f.tiles_x = (ctx->cam.width + 7u) / 8u;
+		f.tiles_y = (ctx->cam.height + 3u) / 4u;
+		f.n_slots = f.tiles_x * f.tiles_y * 32u;
+		const size_t n_pixels = size_t(ctx->cam.width) * ctx->cam.height;
+		auto alloc = [&](void** p, size_t bytes) -> int {
+			RZB_CUDA(ctx, cudaMalloc(p, bytes));
+			ctx->frame_allocs.push_back(*p);
+			return RZB_OK;
+		};
+		int rc;
+		if ((rc = alloc(reinterpret_cast<void**>(&f.st_o), size_t(f.n_slots) * 16))) return rc;
+		if ((rc = alloc(reinterpret_cast<void**>(&f.st_d), size_t(f.n_slots) * 16))) return rc;
+		if ((rc = alloc(reinterpret_cast<void**>(&f.st_c), size_t(f.n_slots) * 8))) return rc;
+		if ((rc = alloc(reinterpret_cast<void**>(&f.hit_a), size_t(f.n_slots) * 16))) return rc;
+		if ((rc = alloc(reinterpret_cast<void**>(&f.hit_inst), size_t(f.n_slots) * 4))) return rc;
+		if ((rc = alloc(reinterpret_cast<void**>(&f.accum), n_pixels * 16))) return rc;
+		if ((rc = alloc(reinterpret_cast<void**>(&f.depth), n_pixels * 4))) return rc;
+		if ((rc = alloc(reinterpret_cast<void**>(&ctx->d_rgba), n_pixels * 4))) return rc;
+		RZB_CUDA(ctx, cudaMemsetAsync(f.accum, 0, n_pixels * 16, ctx->stream));
+		RZB_CUDA(ctx, cudaMemsetAsync(f.depth, 0, n_pixels * 4, ctx->stream));
+		ctx->frame_ready = false;
+		return RZB_OK;
+	}
+
+	int ensureShadowQueue(rzb_ctx* ctx)
+	{
+		const uint32_t per_pixel =
+			(ctx->sc.direct_light_count ? ctx->cfg.direct_light_samples : 0u) +
+			(ctx->sc.spot_light_count ? ctx->cfg.spot_light_samples : 0u);
+		const uint32_t want = std::max<uint32_t>(ctx->frame.n_slots * std::max(per_pixel, 1u), 32u);
+		if (want > ctx->shadow_capacity_alloc)
+		{
+			for (void*& p : ctx->d_shadow)
+			{
+				if (p) cudaFree(p);
+				p = nullptr;
+			}
+			for (void*& p : ctx->d_shadow) RZB_CUDA(ctx, cudaMalloc(&p, size_t(want) * 16));
+			ctx->shadow_capacity_alloc = want;
+		}
+		ctx->frame.sh_o = static_cast<float4*>(ctx->d_shadow[0]);
+		ctx->frame.sh_d = static_cast<float4*>(ctx->d_shadow[1]);
+		ctx->frame.sh_c = static_cast<float4*>(ctx->d_shadow[2]);
+		ctx->frame.shadow_capacity = want;
+		return RZB_OK;
+	}
+}
+
+extern "C" int rzb_abi_version(void) { return int(RZB_ABI_VERSION); }
+
+extern "C" const char* rzb_last_error(const rzb_ctx* ctx)
+{
+	return ctx ? ctx->error.c_str() : g_create_error.c_str();
+}
+
+extern "C" int rzb_create(int device, rzb_ctx** out)
+{
+	if (!out) return fail(nullptr, RZB_ERR_INVALID, "rzb_create: out is NULL");
+	*out = nullptr;
+	int count = 0;
+	cudaError_t e = cudaGetDeviceCount(&count);
+	if (e != cudaSuccess) return cudaFail(nullptr, e, "cudaGetDeviceCount (no CUDA device: this path has no CPU fallback)");
+	if (device < 0 || device >= count) return fail(nullptr, RZB_ERR_INVALID, "rzb_create: device ordinal out of range");
+	rzb_ctx* ctx = new (std::nothrow) rzb_ctx();
+	if (!ctx) return fail(nullptr, RZB_ERR_NOMEM, "rzb_create: out of host memory");
+	ctx->device = device;
+	DeviceGuard guard(device);
+	cudaDeviceProp prop{};
+	if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) { delete ctx; return cudaFail(nullptr, e, "cudaGetDeviceProperties"); }
+	ctx->sm_count = prop.multiProcessorCount;
+	if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) { delete ctx; return cudaFail(nullptr, e, "cudaStreamCreate"); }
+	cudaEventCreate(&ctx->ev_begin);
+	cudaEventCreate(&ctx->ev_end);
+	for (auto& ev : ctx->ev_stage) cudaEventCreate(&ev);
+	if ((e = cudaMalloc(reinterpret_cast<void**>(&ctx->d_counters), 256)) != cudaSuccess) { delete ctx; return cudaFail(nullptr, e, "cudaMalloc(counters)"); }
+	cudaMemsetAsync(ctx->d_counters, 0, 256, ctx->stream);
+	ctx->trace_grid = gridFor(ctx, reinterpret_cast<const void*>(&k_trace_paths), kTraceBlock);
+	ctx->shadow_grid = gridFor(ctx, reinterpret_cast<const void*>(&k_trace_shadow), kTraceBlock);
+	ctx->rays_grid = gridFor(ctx, reinterpret_cast<const void*>(&k_trace_rays<false>), kTraceBlock);
+	ctx->any_grid = gridFor(ctx, reinterpret_cast<const void*>(&k_trace_any_rays), kTraceBlock);
+	*out = ctx;
+	return RZB_OK;
+}
+
+extern "C" void rzb_destroy(rzb_ctx* ctx)
+{
+	if (!ctx) return;
+	DeviceGuard guard(ctx->device);
+	cudaStreamSynchronize(ctx->stream);
+	freeAll(ctx->scene_allocs);
+	freeAll(ctx->frame_allocs);
+	for (void* p : ctx->d_shadow) if (p) cudaFree(p);
+	for (auto& b : ctx->scratch) if (b.ptr) cudaFree(b.ptr);
+	if (ctx->d_counters) cudaFree(ctx->d_counters);
+	cudaEventDestroy(ctx->ev_begin);
+	cudaEventDestroy(ctx->ev_end);
+	for (auto& ev : ctx->ev_stage) cudaEventDestroy(ev);
+	cudaStreamDestroy(ctx->stream);
+	delete ctx;
+}
+
+extern "C" int rzb_set_scene(rzb_ctx* ctx, const rzb_scene* s)
+{
+	if (!ctx || !s) return fail(ctx, RZB_ERR_INVALID, "rzb_set_scene: NULL argument");
+	DeviceGuard guard(ctx->device);
+	RZB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	freeAll(ctx->scene_allocs);
+	ctx->has_scene = false;
+	ctx->frame_ready = false;
+
+	// ---- validate
+	for (uint32_t m = 0; m < s->mesh_count; ++m)
+	{
+		const rzb_mesh& mesh = s->meshes[m];
+		if (uint64_t(mesh.node_offset) + mesh.node_count > s->mesh_node_count ||
+			uint64_t(mesh.tri_offset) + mesh.tri_count > s->triangle_count)
+			return fail(ctx, RZB_ERR_INVALID, "rzb_set_scene: mesh range outside node/triangle arrays");
+	}
+	if (s->triangle_count > kHitTriMask - 1u) return fail(ctx, RZB_ERR_INVALID, "rzb_set_scene: too many triangles");
+	if (s->default_material >= s->material_count) return fail(ctx, RZB_ERR_INVALID, "rzb_set_scene: default material out of range");
+	for (uint32_t i = 0; i < s->instance_material_count; ++i)
+		if (s->instance_materials[i] >= s->material_count)
+			return fail(ctx, RZB_ERR_INVALID, "rzb_set_scene: instance material id out of range");
+	if (s->instance_count != 0 && s->instance_node_count == 0)
+		return fail(ctx, RZB_ERR_INVALID, "rzb_set_scene: instances without an instance tree");
+
+	// ---- nodes: every tree is placed so that its root sits at an odd global index; sibling pairs (odd local
+	// index, next even) then start at even global indices = 64-byte aligned
+	std::vector<uint32_t> mesh_base(s->mesh_count, kNoIndex);
+	size_t cursor = 1;
+	for (uint32_t m = 0; m < s->mesh_count; ++m)
+	{
+		if (s->meshes[m].node_count == 0) continue;
+		if ((cursor & 1u) == 0) ++cursor;
+		mesh_base[m] = uint32_t(cursor);
+		cursor += s->meshes[m].node_count;
+	}
+	if ((cursor & 1u) == 0) ++cursor;
+	const uint32_t top_base = uint32_t(cursor);
+	cursor += s->instance_node_count;
+	if (cursor >= (1u << 30)) return fail(ctx, RZB_ERR_INVALID, "rzb_set_scene: too many nodes");
+	std::vector<rzb_node> nodes(cursor + 1);
+	std::memset(nodes.data(), 0, nodes.size() * sizeof(rzb_node));
+	for (uint32_t m = 0; m < s->mesh_count; ++m)
+	{
+		const rzb_mesh& mesh = s->meshes[m];
+		for (uint32_t i = 0; i < mesh.node_count; ++i)
+		{
+			rzb_node n = s->mesh_nodes[mesh.node_offset + i];
+			const uint32_t count = n.type_count & 0x3FFFFFFFu;
+			if (count != 0)
+			{
+				if (uint64_t(n.begin) + count > mesh.tri_count) return fail(ctx, RZB_ERR_INVALID, "rzb_set_scene: leaf outside mesh triangles");
+				n.begin += mesh.tri_offset;
+			}
+			else
+			{
+				if (uint64_t(n.begin) + 1 >= mesh.node_count || (n.begin & 1u) == 0)
+					return fail(ctx, RZB_ERR_INVALID, "rzb_set_scene: bad child index in mesh tree");
+				n.begin += mesh_base[m];
+			}
+			nodes[mesh_base[m] + i] = n;
+		}
+	}
+	for (uint32_t i = 0; i < s->instance_node_count; ++i)
+	{
+		rzb_node n = s->instance_nodes[i];
+		const uint32_t count = n.type_count & 0x3FFFFFFFu;
+		if (count != 0)
+		{
+			if (uint64_t(n.begin) + count > s->instance_count) return fail(ctx, RZB_ERR_INVALID, "rzb_set_scene: leaf outside instances");
+		}
+		else
+		{
+			if (uint64_t(n.begin) + 1 >= s->instance_node_count || (n.begin & 1u) == 0)
+				return fail(ctx, RZB_ERR_INVALID, "rzb_set_scene: bad child index in instance tree");
+			n.begin += top_base;
+		}
+		nodes[top_base + i] = n;
+	}
+
+	// ---- triangles: hot (intersection) and cold (shading) records
+	std::vector<float4> hot(size_t(s->triangle_count) * 3), cold(size_t(s->triangle_count) * 5);
+	for (uint32_t i = 0; i < s->triangle_count; ++i)
+	{
+		const rzb_triangle& t = s->triangles[i];
+		// edge vectors exactly as Triangle::closestIntersection forms them first (single fp32 subtractions)
+		volatile float e1x = t.v[1][0] - t.v[0][0], e1y = t.v[1][1] - t.v[0][1], e1z = t.v[1][2] - t.v[0][2];
+		volatile float e2x = t.v[2][0] - t.v[0][0], e2y = t.v[2][1] - t.v[0][1], e2z = t.v[2][2] - t.v[0][2];
+		uint32_t slot = t.material_slot & 0x3Fu;
+		float slot_f;
+		std::memcpy(&slot_f, &slot, 4);
+		hot[3 * size_t(i)] = make_float4(t.v[0][0], t.v[0][1], t.v[0][2], e1x);
+		hot[3 * size_t(i) + 1] = make_float4(e1y, e1z, e2x, e2y);
+		hot[3 * size_t(i) + 2] = make_float4(e2z, slot_f, 0.0f, 0.0f);
+		cold[5 * size_t(i)] = make_float4(t.n[0][0], t.n[0][1], t.n[0][2], t.uv[0][0]);
+		cold[5 * size_t(i) + 1] = make_float4(t.n[1][0], t.n[1][1], t.n[1][2], t.uv[0][1]);
+		cold[5 * size_t(i) + 2] = make_float4(t.n[2][0], t.n[2][1], t.n[2][2], t.uv[1][0]);
+		cold[5 * size_t(i) + 3] = make_float4(t.face_normal[0], t.face_normal[1], t.face_normal[2], t.uv[1][1]);
+		cold[5 * size_t(i) + 4] = make_float4(t.uv[2][0], t.uv[2][1], 0.0f, 0.0f);
+	}
+
+	// ---- instances
+	std::vector<DInstance> insts(s->instance_count);
+	std::vector<uint32_t> inst_host(s->instance_count);
+	for (uint32_t i = 0; i < s->instance_count; ++i)
+	{
+		const rzb_instance& h = s->instances[i];
+		DInstance d{};
+		d.px = h.position[0]; d.py = h.position[1]; d.pz = h.position[2];
+		d.sx = h.scale[0]; d.sy = h.scale[1]; d.sz = h.scale[2];
+		d.xx = h.axis_x[0]; d.xy = h.axis_x[1]; d.xz = h.axis_x[2];
+		d.yx = h.axis_y[0]; d.yy = h.axis_y[1]; d.yz = h.axis_y[2];
+		d.zx = h.axis_z[0]; d.zy = h.axis_z[1]; d.zz = h.axis_z[2];
+		d.bminx = h.bb_min[0]; d.bminy = h.bb_min[1]; d.bminz = h.bb_min[2];
+		d.bmaxx = h.bb_max[0]; d.bmaxy = h.bb_max[1]; d.bmaxz = h.bb_max[2];
+		d.mesh_root = kNoIndex;
+		if (h.mesh != RZB_NO_INDEX)
+		{
+			if (h.mesh >= s->mesh_count) return fail(ctx, RZB_ERR_INVALID, "rzb_set_scene: instance mesh id out of range");
+			d.mesh_root = mesh_base[h.mesh];
+		}
+		if (uint64_t(h.material_offset) + h.material_count > s->instance_material_count ||
+			h.material_count > RZB_MAX_MATERIALS_PER_INSTANCE)
+			return fail(ctx, RZB_ERR_INVALID, "rzb_set_scene: instance material slice out of range");
+		d.mat_offset = h.material_offset;
+		d.mat_count = h.material_count;
+		insts[i] = d;
+		inst_host[i] = h.host_index;
+	}
+
+	// ---- materials (+ world material appended), maps, lights
+	std::vector<rzb_material> mats(s->materials, s->materials + s->material_count);
+	mats.push_back(s->world_material);
+	for (const rzb_material& m : mats)
+	{
+		const uint32_t ids[5] = {m.texture, m.normal_map, m.metalness_map, m.roughness_map, m.emission_map};
+		for (uint32_t id : ids)
+			if (id != RZB_NO_INDEX && id >= s->map_count) return fail(ctx, RZB_ERR_INVALID, "rzb_set_scene: map id out of range");
+	}
+	std::vector<DMap> maps(s->map_count);
+	for (uint32_t i = 0; i < s->map_count; ++i)
+	{
+		const rzb_map& m = s->maps[i];
+		if (!m.pixels || m.width == 0 || m.height == 0 || m.format > RZB_MAP_R32F)
+			return fail(ctx, RZB_ERR_INVALID, "rzb_set_scene: bad map");
+		const size_t texel = m.format == RZB_MAP_R8 ? 1 : 4;
+		const uint8_t* d_pixels = nullptr;
+		int rc = upload(ctx, ctx->scene_allocs, static_cast<const uint8_t*>(m.pixels), size_t(m.width) * m.height * texel, &d_pixels);
+		if (rc) return rc;
+		DMap d{};
+		d.pixels = d_pixels;
+		d.width = m.width; d.height = m.height;
+		d.format = m.format; d.filter = m.filter; d.address = m.address;
+		d.scale_x = m.scale[0]; d.scale_y = m.scale[1];
+		d.rot_sin = sinf(m.rotation); d.rot_cos = cosf(m.rotation);
+		d.trans_x = m.translation[0]; d.trans_y = m.translation[1];
+		maps[i] = d;
+	}
+
+	DScene sc{};
+	int rc;
+	const float4* d_nodes = nullptr;
+	if ((rc = upload(ctx, ctx->scene_allocs, reinterpret_cast<const float4*>(nodes.data()), nodes.size() * 2, &d_nodes))) return rc;
+	sc.nodes = d_nodes;
+	if ((rc = upload(ctx, ctx->scene_allocs, hot.data(), hot.size(), &sc.tri_hot))) return rc;
+	if ((rc = upload(ctx, ctx->scene_allocs, cold.data(), cold.size(), &sc.tri_cold))) return rc;
+	if ((rc = upload(ctx, ctx->scene_allocs, insts.data(), insts.size(), &sc.instances))) return rc;
+	if ((rc = upload(ctx, ctx->scene_allocs, inst_host.data(), inst_host.size(), &sc.inst_host_index))) return rc;
+	std::vector<uint32_t> identity;
+	const uint32_t* tri_host = s->tri_host_index;
+	if (!tri_host)
+	{
+		identity.resize(s->triangle_count);
+		for (uint32_t i = 0; i < s->triangle_count; ++i) identity[i] = i;
+		tri_host = identity.data();
+	}
+	if ((rc = upload(ctx, ctx->scene_allocs, tri_host, s->triangle_count, &sc.tri_host_index))) return rc;
+	if ((rc = upload(ctx, ctx->scene_allocs, s->instance_materials, s->instance_material_count, &sc.inst_materials))) return rc;
+	if ((rc = upload(ctx, ctx->scene_allocs, mats.data(), mats.size(), &sc.materials))) return rc;
+	if ((rc = upload(ctx, ctx->scene_allocs, maps.data(), maps.size(), &sc.maps))) return rc;
+	if ((rc = upload(ctx, ctx->scene_allocs, s->direct_lights, s->direct_light_count, &sc.direct_lights))) return rc;
+	if ((rc = upload(ctx, ctx->scene_allocs, s->spot_lights, s->spot_light_count, &sc.spot_lights))) return rc;
+	sc.top_root = top_base;
+	sc.instance_count = s->instance_count;
+	sc.material_count = s->material_count;
+	sc.world_material = s->material_count;
+	sc.default_material = s->default_material;
+	sc.direct_light_count = s->direct_light_count;
+	sc.spot_light_count = s->spot_light_count;
+	sc.flags = ctx->cfg.flags;
+	RZB_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); // host staging vectors die at return
+	ctx->sc = sc;
+	ctx->has_scene = true;
+	return RZB_OK;
+}
+
+extern "C" int rzb_set_camera(rzb_ctx* ctx, const rzb_camera* camera)
+{
+	if (!ctx || !camera) return fail(ctx, RZB_ERR_INVALID, "rzb_set_camera: NULL argument");
+	if (camera->width == 0 || camera->height == 0 || uint64_t(camera->width) * camera->height > (1ull << 28))
+		return fail(ctx, RZB_ERR_INVALID, "rzb_set_camera: bad resolution");
+	DeviceGuard guard(ctx->device);
+	RZB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	const bool resized = !ctx->has_camera || camera->width != ctx->cam.width || camera->height != ctx->cam.height;
+	ctx->cam = *camera;
+	ctx->has_camera = true;
+	if (resized)
+	{
+		const int rc = prepareFrame(ctx);
+		if (rc) return rc;
+	}
+	else ctx->frame.cam = makeDeviceCamera(ctx->cam);
+	ctx->frame_ready = false;
+	return RZB_OK;
+}
+
+extern "C" int rzb_set_config(rzb_ctx* ctx, const rzb_config* config)
+{
+	if (!ctx || !config) return fail(ctx, RZB_ERR_INVALID, "rzb_set_config: NULL argument");
+	if (config->max_depth == 0 || config->max_depth > 255) return fail(ctx, RZB_ERR_INVALID, "rzb_set_config: max_depth must be 1..255");
+	ctx->cfg = *config;
+	ctx->sc.flags = config->flags;
+	return RZB_OK;
+}
+
+extern "C" int rzb_reset(rzb_ctx* ctx)
+{
+	if (!ctx) return RZB_ERR_INVALID;
+	if (!ctx->has_scene || !ctx->has_camera) return fail(ctx, RZB_ERR_STATE, "rzb_reset: scene and camera must be set first");
+	DeviceGuard guard(ctx->device);
+	DFrame& f = ctx->frame;
+	f.cam = makeDeviceCamera(ctx->cam);
+	k_reset<<<(f.n_slots + 255) / 256, 256, 0, ctx->stream>>>(f, ctx->sc.world_material);
+	RZB_CUDA(ctx, cudaGetLastError());
+	RZB_CUDA(ctx, cudaMemsetAsync(ctx->d_counters, 0, 64, ctx->stream));
+	ctx->launches += 1;
+	ctx->passes = 0;
+	ctx->frame_ready = true;
+	return RZB_OK;
+}
+
+extern "C" int rzb_render(rzb_ctx* ctx, uint32_t passes)
+{
+	if (!ctx) return RZB_ERR_INVALID;
+	if (!ctx->has_scene || !ctx->has_camera) return fail(ctx, RZB_ERR_STATE, "rzb_render: scene and camera must be set first");
+	DeviceGuard guard(ctx->device);
+	if (!ctx->frame_ready)
+	{
+		const int rc = rzb_reset(ctx);
+		if (rc) return rc;
+	}
+	int rc = ensureShadowQueue(ctx);
+	if (rc) return rc;
+	DFrame& f = ctx->frame;
+	f.counters = ctx->d_counters;
+	f.max_depth = ctx->cfg.max_depth;
+	f.direct_samples = ctx->cfg.direct_light_samples;
+	f.spot_samples = ctx->cfg.spot_light_samples;
+	f.seed = ctx->cfg.seed;
+	const bool lights = (ctx->sc.direct_light_count && f.direct_samples) || (ctx->sc.spot_light_count && f.spot_samples);
+	RZB_CUDA(ctx, cudaEventRecord(ctx->ev_begin, ctx->stream));
+	for (uint32_t p = 0; p < passes; ++p)
+	{
+		f.pass_index = uint32_t(ctx->passes);
+		const bool timed = (p == 0);
+		RZB_CUDA(ctx, cudaMemsetAsync(ctx->d_counters, 0, 12, ctx->stream));
+		if (timed) cudaEventRecord(ctx->ev_stage[0], ctx->stream);
+		k_trace_paths<<<ctx->trace_grid, kTraceBlock, 0, ctx->stream>>>(ctx->sc, f);
+		if (timed) cudaEventRecord(ctx->ev_stage[1], ctx->stream);
+		k_shade<<<(f.n_slots + 127) / 128, 128, 0, ctx->stream>>>(ctx->sc, f);
+		if (timed) cudaEventRecord(ctx->ev_stage[2], ctx->stream);
+		ctx->launches += 2;
+		if (lights)
+		{
+			k_trace_shadow<<<ctx->shadow_grid, kTraceBlock, 0, ctx->stream>>>(ctx->sc, f);
+			ctx->launches += 1;
+		}
+		if (timed) cudaEventRecord(ctx->ev_stage[3], ctx->stream);
+		ctx->passes += 1;
+	}
+	RZB_CUDA(ctx, cudaEventRecord(ctx->ev_end, ctx->stream));
+	RZB_CUDA(ctx, cudaGetLastError());
+	return RZB_OK;
+}
+
+extern "C" int rzb_synchronize(rzb_ctx* ctx)
+{
+	if (!ctx) return RZB_ERR_INVALID;
+	DeviceGuard guard(ctx->device);
+	RZB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	return RZB_OK;
+}
+
+namespace
+{
+	int tonemapAndCopy(rzb_ctx* ctx, const PeerList& peers, uint8_t* rgba8, float* depth)
+	{
+		const uint32_t n = ctx->cam.width * ctx->cam.height;
+		if (rgba8)
+		{
+			// ComputeFinalColor multiplies by aperture area, exposure time and 1e5 one after the other
+			const float area = ctx->cam.aperture * ctx->cam.aperture * 3.14159265358979323846f;
+			k_tonemap<<<(n + 255) / 256, 256, 0, ctx->stream>>>(ctx->frame.accum, peers, ctx->d_rgba, n, area, ctx->cam.exposure_time);
+			ctx->launches += 1;
+			RZB_CUDA(ctx, cudaGetLastError());
+			RZB_CUDA(ctx, cudaMemcpyAsync(rgba8, ctx->d_rgba, size_t(n) * 4, cudaMemcpyDeviceToHost, ctx->stream));
+		}
+		if (depth) RZB_CUDA(ctx, cudaMemcpyAsync(depth, ctx->frame.depth, size_t(n) * 4, cudaMemcpyDeviceToHost, ctx->stream));
+		RZB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+		return RZB_OK;
+	}
+}
+
+extern "C" int rzb_resolve(rzb_ctx* ctx, uint8_t* rgba8, float* depth, uint64_t* ray_count)
+{
+	if (!ctx) return RZB_ERR_INVALID;
+	if (!ctx->has_camera) return fail(ctx, RZB_ERR_STATE, "rzb_resolve: no camera");
+	DeviceGuard guard(ctx->device);
+	PeerList peers{};
+	const int rc = tonemapAndCopy(ctx, peers, rgba8, depth);
+	if (rc) return rc;
+	if (ray_count) *ray_count = ctx->passes * uint64_t(ctx->cam.width) * ctx->cam.height;
+	return RZB_OK;
+}
+
+extern "C" int rzb_resolve_peers(rzb_ctx* ctx, rzb_ctx* const* peers_in, uint32_t n_peers,
+	uint8_t* rgba8, float* depth, uint64_t* ray_count)
+{
+	if (!ctx || (n_peers && !peers_in) || n_peers > 8) return fail(ctx, RZB_ERR_INVALID, "rzb_resolve_peers: bad arguments");
+	DeviceGuard guard(ctx->device);
+	PeerList peers{};
+	uint64_t rays = ctx->passes * uint64_t(ctx->cam.width) * ctx->cam.height;
+	for (uint32_t i = 0; i < n_peers; ++i)
+	{
+		rzb_ctx* p = peers_in[i];
+		if (!p || p->cam.width != ctx->cam.width || p->cam.height != ctx->cam.height)
+			return fail(ctx, RZB_ERR_INVALID, "rzb_resolve_peers: peer resolution differs");
+		if (p->device != ctx->device)
+		{
+			int can = 0;
+			RZB_CUDA(ctx, cudaDeviceCanAccessPeer(&can, ctx->device, p->device));
+			if (!can) return fail(ctx, RZB_ERR_CUDA, "rzb_resolve_peers: no peer access between devices");
+			const cudaError_t e = cudaDeviceEnablePeerAccess(p->device, 0);
+			if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) return cudaFail(ctx, e, "cudaDeviceEnablePeerAccess");
+			cudaGetLastError();
+		}
+		{
+			DeviceGuard pg(p->device);
+			RZB_CUDA(ctx, cudaStreamSynchronize(p->stream));
+		}
+		peers.accum[i] = p->frame.accum;
+		rays += p->passes * uint64_t(p->cam.width) * p->cam.height;
+	}
+	peers.count = n_peers;
+	const int rc = tonemapAndCopy(ctx, peers, rgba8, depth);
+	if (rc) return rc;
+	if (ray_count) *ray_count = rays;
+	return RZB_OK;
+}
+
+extern "C" int rzb_read_accum(rzb_ctx* ctx, float* rgba_f32)
+{
+	if (!ctx || !rgba_f32) return fail(ctx, RZB_ERR_INVALID, "rzb_read_accum: NULL argument");
+	if (!ctx->has_camera) return fail(ctx, RZB_ERR_STATE, "rzb_read_accum: no camera");
+	DeviceGuard guard(ctx->device);
+	const size_t n = size_t(ctx->cam.width) * ctx->cam.height;
+	RZB_CUDA(ctx, cudaMemcpyAsync(rgba_f32, ctx->frame.accum, n * 16, cudaMemcpyDeviceToHost, ctx->stream));
+	RZB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	return RZB_OK;
+}
+
+extern "C" int rzb_accum_device_ptr(rzb_ctx* ctx, void** device_ptr, size_t* bytes)
+{
+	if (!ctx || !device_ptr) return fail(ctx, RZB_ERR_INVALID, "rzb_accum_device_ptr: NULL argument");
+	if (!ctx->has_camera) return fail(ctx, RZB_ERR_STATE, "rzb_accum_device_ptr: no camera");
+	*device_ptr = ctx->frame.accum;
+	if (bytes) *bytes = size_t(ctx->cam.width) * ctx->cam.height * 16;
+	return RZB_OK;
+}
+
+extern "C" int rzb_accum_add_device(rzb_ctx* ctx, const void* device_rgba_f32, size_t pixel_count)
+{
+	if (!ctx || !device_rgba_f32) return fail(ctx, RZB_ERR_INVALID, "rzb_accum_add_device: NULL argument");
+	if (!ctx->has_camera || pixel_count > size_t(ctx->cam.width) * ctx->cam.height)
+		return fail(ctx, RZB_ERR_INVALID, "rzb_accum_add_device: too many pixels");
+	DeviceGuard guard(ctx->device);
+	const uint32_t n = uint32_t(pixel_count);
+	k_accum_add<<<(n + 255) / 256, 256, 0, ctx->stream>>>(ctx->frame.accum, static_cast<const float4*>(device_rgba_f32), n);
+	ctx->launches += 1;
+	RZB_CUDA(ctx, cudaGetLastError());
+	return RZB_OK;
+}
+
+extern "C" int rzb_get_render_stats(rzb_ctx* ctx, rzb_render_stats* out)
+{
+	if (!ctx || !out) return RZB_ERR_INVALID;
+	DeviceGuard guard(ctx->device);
+	RZB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	std::memset(out, 0, sizeof(*out));
+	out->passes = ctx->passes;
+	out->ray_count = ctx->passes * uint64_t(ctx->cam.width) * ctx->cam.height;
+	out->kernel_launches = ctx->launches;
+	if (ctx->passes)
+	{
+		float ms = 0.0f;
+		if (cudaEventElapsedTime(&ms, ctx->ev_begin, ctx->ev_end) == cudaSuccess) ctx->last_render_ms = ms;
+		if (cudaEventElapsedTime(&ms, ctx->ev_stage[0], ctx->ev_stage[1]) == cudaSuccess) ctx->last_trace_ms = ms;
+		if (cudaEventElapsedTime(&ms, ctx->ev_stage[1], ctx->ev_stage[2]) == cudaSuccess) ctx->last_shade_ms = ms;
+		if (cudaEventElapsedTime(&ms, ctx->ev_stage[2], ctx->ev_stage[3]) == cudaSuccess) ctx->last_shadow_ms = ms;
+		cudaGetLastError();
+	}
+	uint32_t counters[16] = {};
+	RZB_CUDA(ctx, cudaMemcpy(counters, ctx->d_counters, 64, cudaMemcpyDeviceToHost));
+	out->shadow_rays = counters[1]; // of the last pass
+	out->last_render_ms = ctx->last_render_ms;
+	out->last_trace_ms = ctx->last_trace_ms;
+	out->last_shade_ms = ctx->last_shade_ms;
+	out->last_shadow_ms = ctx->last_shadow_ms;
+	return RZB_OK;
+}
+
+extern "C" int rzb_timings(rzb_ctx* ctx, char* buf, size_t buf_size)
+{
+	if (!ctx || !buf || buf_size == 0) return RZB_ERR_INVALID;
+	rzb_render_stats st{};
+	const int rc = rzb_get_render_stats(ctx, &st);
+	if (rc) return rc;
+	std::snprintf(buf, buf_size,
+		"B200 wavefront engine (device %d, %d SMs)\n"
+		"passes: %llu  rays: %llu  kernel launches: %llu\n"
+		"last render call: %.3f ms\n"
+		"  closest-hit: %.3f ms/pass\n  shade+NEE:   %.3f ms/pass\n  shadow rays: %.3f ms/pass (%llu rays)\n",
+		ctx->device, ctx->sm_count, (unsigned long long)st.passes, (unsigned long long)st.ray_count,
+		(unsigned long long)st.kernel_launches, st.last_render_ms, st.last_trace_ms, st.last_shade_ms,
+		st.last_shadow_ms, (unsigned long long)st.shadow_rays);
+	return RZB_OK;
+}
+
+// ---------------------------------------------------------------- ray-set entry points
+namespace
+{
+	int packRays(rzb_ctx* ctx, const float* origins, const float* directions, const float* near_far, uint32_t n)
+	{
+		int rc;
+		if ((rc = ensureScratch(ctx, 0, size_t(n) * 16))) return rc;
+		if ((rc = ensureScratch(ctx, 1, size_t(n) * 16))) return rc;
+		std::vector<float4> o(n), d(n);
+		for (uint32_t i = 0; i < n; ++i)
+		{
+			o[i] = make_float4(origins[3 * size_t(i)], origins[3 * size_t(i) + 1], origins[3 * size_t(i) + 2], near_far[2 * size_t(i)]);
+			d[i] = make_float4(directions[3 * size_t(i)], directions[3 * size_t(i) + 1], directions[3 * size_t(i) + 2], near_far[2 * size_t(i) + 1]);
+		}
+		RZB_CUDA(ctx, cudaMemcpy(ctx->scratch[0].ptr, o.data(), size_t(n) * 16, cudaMemcpyHostToDevice));
+		RZB_CUDA(ctx, cudaMemcpy(ctx->scratch[1].ptr, d.data(), size_t(n) * 16, cudaMemcpyHostToDevice));
+		return RZB_OK;
+	}
+}
+
+extern "C" int rzb_trace_closest_device(rzb_ctx* ctx, const void* rays_o_near, const void* rays_d_far,
+	uint32_t n, void* hits_out_device, float* elapsed_ms)
+{
+	if (!ctx || !rays_o_near || !rays_d_far || !hits_out_device) return fail(ctx, RZB_ERR_INVALID, "rzb_trace_closest_device: NULL argument");
+	if (!ctx->has_scene) return fail(ctx, RZB_ERR_STATE, "rzb_trace_closest_device: no scene");
+	DeviceGuard guard(ctx->device);
+	RZB_CUDA(ctx, cudaMemsetAsync(ctx->d_counters + 8, 0, 4, ctx->stream));
+	if (elapsed_ms) RZB_CUDA(ctx, cudaEventRecord(ctx->ev_begin, ctx->stream));
+	k_trace_rays<false><<<ctx->rays_grid, kTraceBlock, 0, ctx->stream>>>(ctx->sc,
+		static_cast<const float4*>(rays_o_near), static_cast<const float4*>(rays_d_far), n,
+		static_cast<DHit*>(hits_out_device), ctx->d_counters + 8, nullptr);
+	ctx->launches += 1;
+	RZB_CUDA(ctx, cudaGetLastError());
+	if (elapsed_ms)
+	{
+		RZB_CUDA(ctx, cudaEventRecord(ctx->ev_end, ctx->stream));
+		RZB_CUDA(ctx, cudaEventSynchronize(ctx->ev_end));
+		RZB_CUDA(ctx, cudaEventElapsedTime(elapsed_ms, ctx->ev_begin, ctx->ev_end));
+	}
+	return RZB_OK;
+}
+
+extern "C" int rzb_trace_closest(rzb_ctx* ctx, const float* origins, const float* directions,
+	const float* near_far, uint32_t n, rzb_hit* hits_out, rzb_trace_stats* stats)
+{
+	if (!ctx || !origins || !directions || !near_far || !hits_out) return fail(ctx, RZB_ERR_INVALID, "rzb_trace_closest: NULL argument");
+	if (!ctx->has_scene) return fail(ctx, RZB_ERR_STATE, "rzb_trace_closest: no scene");
+	if (n == 0) return RZB_OK;
+	DeviceGuard guard(ctx->device);
+	int rc;
+	if ((rc = packRays(ctx, origins, directions, near_far, n))) return rc;
+	if ((rc = ensureScratch(ctx, 2, size_t(n) * sizeof(DHit)))) return rc;
+	if ((rc = ensureScratch(ctx, 3, size_t(n) * sizeof(rzb_hit) + 64))) return rc;
+	unsigned long long* d_stats = reinterpret_cast<unsigned long long*>(ctx->d_counters + 10);
+	RZB_CUDA(ctx, cudaMemsetAsync(ctx->d_counters + 8, 0, 40, ctx->stream));
+	if (stats)
+		k_trace_rays<true><<<ctx->rays_grid, kTraceBlock, 0, ctx->stream>>>(ctx->sc,
+			static_cast<const float4*>(ctx->scratch[0].ptr), static_cast<const float4*>(ctx->scratch[1].ptr), n,
+			static_cast<DHit*>(ctx->scratch[2].ptr), ctx->d_counters + 8, d_stats);
+	else
+		k_trace_rays<false><<<ctx->rays_grid, kTraceBlock, 0, ctx->stream>>>(ctx->sc,
+			static_cast<const float4*>(ctx->scratch[0].ptr), static_cast<const float4*>(ctx->scratch[1].ptr), n,
+			static_cast<DHit*>(ctx->scratch[2].ptr), ctx->d_counters + 8, nullptr);
+	k_convert_hits<<<(n + 255) / 256, 256, 0, ctx->stream>>>(ctx->sc, static_cast<const DHit*>(ctx->scratch[2].ptr),
+		static_cast<rzb_hit*>(ctx->scratch[3].ptr), n);
+	ctx->launches += 2;
+	RZB_CUDA(ctx, cudaGetLastError());
+	RZB_CUDA(ctx, cudaMemcpyAsync(hits_out, ctx->scratch[3].ptr, size_t(n) * sizeof(rzb_hit), cudaMemcpyDeviceToHost, ctx->stream));
+	RZB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	if (stats)
+	{
+		unsigned long long h[4] = {};
+		RZB_CUDA(ctx, cudaMemcpy(h, d_stats, sizeof(h), cudaMemcpyDeviceToHost));
+		stats->rays = n;
+		stats->top_nodes = h[0]; stats->instances_entered = h[1]; stats->mesh_nodes = h[2]; stats->triangles = h[3];
+	}
+	return RZB_OK;
+}
+
+extern "C" int rzb_trace_any(rzb_ctx* ctx, const float* origins, const float* directions,
+	const float* near_far, uint32_t n, float* mask_out)
+{
+	if (!ctx || !origins || !directions || !near_far || !mask_out) return fail(ctx, RZB_ERR_INVALID, "rzb_trace_any: NULL argument");
+	if (!ctx->has_scene) return fail(ctx, RZB_ERR_STATE, "rzb_trace_any: no scene");
+	if (n == 0) return RZB_OK;
+	DeviceGuard guard(ctx->device);
+	int rc;
+	if ((rc = packRays(ctx, origins, directions, near_far, n))) return rc;
+	if ((rc = ensureScratch(ctx, 2, size_t(n) * 16))) return rc;
+	RZB_CUDA(ctx, cudaMemsetAsync(ctx->d_counters + 8, 0, 4, ctx->stream));
+	k_trace_any_rays<<<ctx->any_grid, kTraceBlock, 0, ctx->stream>>>(ctx->sc,
+		static_cast<const float4*>(ctx->scratch[0].ptr), static_cast<const float4*>(ctx->scratch[1].ptr), n,
+		static_cast<float4*>(ctx->scratch[2].ptr), ctx->d_counters + 8);
+	ctx->launches += 1;
+	RZB_CUDA(ctx, cudaGetLastError());
+	RZB_CUDA(ctx, cudaMemcpyAsync(mask_out, ctx->scratch[2].ptr, size_t(n) * 16, cudaMemcpyDeviceToHost, ctx->stream));
+	RZB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	return RZB_OK;
+}
+
+extern "C" int rzb_generate_camera_rays(rzb_ctx* ctx, float* origins, float* directions, float* near_far)
+{
+	if (!ctx || !origins || !directions || !near_far) return fail(ctx, RZB_ERR_INVALID, "rzb_generate_camera_rays: NULL argument");
+	if (!ctx->has_camera) return fail(ctx, RZB_ERR_STATE, "rzb_generate_camera_rays: no camera");
+	DeviceGuard guard(ctx->device);
+	const uint32_t n = ctx->cam.width * ctx->cam.height;
+	int rc;
+	if ((rc = ensureScratch(ctx, 0, size_t(n) * 16))) return rc;
+	if ((rc = ensureScratch(ctx, 1, size_t(n) * 16))) return rc;
+	k_camera_rays<<<(n + 255) / 256, 256, 0, ctx->stream>>>(makeDeviceCamera(ctx->cam),
+		static_cast<float4*>(ctx->scratch[0].ptr), static_cast<float4*>(ctx->scratch[1].ptr));
+	ctx->launches += 1;
+	RZB_CUDA(ctx, cudaGetLastError());
+	std::vector<float4> o(n), d(n);
+	RZB_CUDA(ctx, cudaMemcpyAsync(o.data(), ctx->scratch[0].ptr, size_t(n) * 16, cudaMemcpyDeviceToHost, ctx->stream));
+	RZB_CUDA(ctx, cudaMemcpyAsync(d.data(), ctx->scratch[1].ptr, size_t(n) * 16, cudaMemcpyDeviceToHost, ctx->stream));
+	RZB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	for (uint32_t i = 0; i < n; ++i)
+	{
+		origins[3 * size_t(i)] = o[i].x; origins[3 * size_t(i) + 1] = o[i].y; origins[3 * size_t(i) + 2] = o[i].z;
+		directions[3 * size_t(i)] = d[i].x; directions[3 * size_t(i) + 1] = d[i].y; directions[3 * size_t(i) + 2] = d[i].z;
+		near_far[2 * size_t(i)] = o[i].w; near_far[2 * size_t(i) + 1] = d[i].w;
+	}
+	return RZB_OK;
+}
+
+extern "C" int rzb_raycast(rzb_ctx* ctx, uint32_t* instance, uint32_t* material_slot)
+{
+	if (!ctx || !instance || !material_slot) return fail(ctx, RZB_ERR_INVALID, "rzb_raycast: NULL argument");
+	if (!ctx->has_scene || !ctx->has_camera) return fail(ctx, RZB_ERR_STATE, "rzb_raycast: scene and camera must be set first");
+	*instance = RZB_NO_INDEX;
+	*material_slot = RZB_NO_INDEX;
+	const uint32_t px = std::min(ctx->cam.raycast_pixel[0], ctx->cam.width - 1u);
+	const uint32_t py = std::min(ctx->cam.raycast_pixel[1], ctx->cam.height - 1u);
+	DeviceGuard guard(ctx->device);
+	// depth of the pick pixel, then a pixel-centre ray with range depth * [0.99, 1.01] (cuda_render_kernel.cu:130-144)
+	float depth = 0.0f;
+	RZB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	RZB_CUDA(ctx, cudaMemcpy(&depth, ctx->frame.depth + size_t(py) * ctx->cam.width + px, 4, cudaMemcpyDeviceToHost));
+	const uint32_t n = ctx->cam.width * ctx->cam.height;
+	std::vector<float> o(size_t(n) * 3), d(size_t(n) * 3), nf(size_t(n) * 2);
+	int rc = rzb_generate_camera_rays(ctx, o.data(), d.data(), nf.data());
+	if (rc) return rc;
+	const size_t i = size_t(py) * ctx->cam.width + px;
+	const float range[2] = {depth * 0.99f, depth * 1.01f};
+	rzb_hit hit{};
+	rc = rzb_trace_closest(ctx, &o[3 * i], &d[3 * i], range, 1, &hit, nullptr);
+	if (rc) return rc;
+	if (hit.instance != RZB_NO_INDEX)
+	{
+		*instance = hit.instance;
+		// material slot of the hit triangle: read back from the hot record through the BVH-order hit
+		DHit dh{};
+		RZB_CUDA(ctx, cudaMemcpy(&dh, ctx->scratch[2].ptr, sizeof(DHit), cudaMemcpyDeviceToHost));
+		const uint32_t tri = dh.tri_bits & kHitTriMask;
+		float4 h2{};
+		RZB_CUDA(ctx, cudaMemcpy(&h2, ctx->sc.tri_hot + 3 * size_t(tri) + 2, sizeof(float4), cudaMemcpyDeviceToHost));
+		uint32_t slot;
+		std::memcpy(&slot, &h2.y, 4);
+		*material_slot = slot;
+	}
+	return RZB_OK;
+}

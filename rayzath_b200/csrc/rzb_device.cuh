@@ -1,0 +1,416 @@
+// Device-side data layout and the two traversal cores (closest-hit, any-hit) of the B200 render path.
+//
+// What is reproduced, bit for bit, from the reference (so that closest-hit IDs match):
+//   slab test        BoundingBox::rayIntersection   /root/reference/RayZath/cuda_render_parts.cuh:1178-1191
+//   triangle test    Triangle::closestIntersection  /root/reference/RayZath/cuda_render_parts.cuh:1023-1054
+//   instance entry   Instance::closestIntersection  /root/reference/RayZath/cuda_instance.cuh:186-214
+//   visiting order   Mesh::closestIntersection / ObjectContainerWithBVH::closestIntersection
+//                    /root/reference/RayZath/cuda_instance.cuh:35-91, cuda_bvh.cuh:114-171 (near child first
+//                    by ray sign on the split axis; the far child's box is tested against the range
+//                    AFTER the near subtree has been searched)
+// What is NOT taken from the reference: the control structure. The reference walks with a per-thread
+// 32-entry local-memory array and re-reads 48-byte nodes one at a time; here sibling pairs are one
+// 64-byte aligned fetch (4 x LDG.128), triangles are a 48-byte hot record (3 x LDG.128) with shading
+// data split off, the far child is deferred on a short stack in shared memory together with its slab
+// entry distance (so the late range test is a compare, not a second node fetch), and both BVH levels
+// share one flat loop. All parity-critical arithmetic uses __f*_rn intrinsics: no FMA contraction.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/rzb200.h"
+
+namespace rzb
+{
+	constexpr uint32_t kNoIndex = 0xFFFFFFFFu;
+	constexpr float kFltMax = 3.402823466e+38f;
+
+	// ---- parity-critical scalar ops: round-to-nearest, never contracted ----
+	__device__ __forceinline__ float fmul(float a, float b) { return __fmul_rn(a, b); }
+	__device__ __forceinline__ float fadd(float a, float b) { return __fadd_rn(a, b); }
+	__device__ __forceinline__ float fsub(float a, float b) { return __fsub_rn(a, b); }
+	__device__ __forceinline__ float fdiv(float a, float b) { return __fdiv_rn(a, b); }
+
+	struct V3
+	{
+		float x, y, z;
+	};
+	__device__ __forceinline__ V3 v3(float x, float y, float z) { return V3{x, y, z}; }
+	// vec3f::dotProduct / crossProduct (cuda_render_parts.cuh:46-57): left-to-right, no FMA
+	__device__ __forceinline__ float dot_rn(const V3& a, const V3& b)
+	{
+		return fadd(fadd(fmul(a.x, b.x), fmul(a.y, b.y)), fmul(a.z, b.z));
+	}
+	__device__ __forceinline__ V3 cross_rn(const V3& a, const V3& b)
+	{
+		return v3(
+			fsub(fmul(a.y, b.z), fmul(a.z, b.y)),
+			fsub(fmul(a.z, b.x), fmul(a.x, b.z)),
+			fsub(fmul(a.x, b.y), fmul(a.y, b.x)));
+	}
+	__device__ __forceinline__ V3 sub_rn(const V3& a, const V3& b) { return v3(fsub(a.x, b.x), fsub(a.y, b.y), fsub(a.z, b.z)); }
+
+	// ---- device scene ----
+	// Instance record for traversal, 96 B = 6 x float4.
+	struct __align__(16) DInstance
+	{
+		float px, py, pz, sx;
+		float sy, sz, xx, xy;
+		float xz, yx, yy, yz;
+		float zx, zy, zz, bminx;
+		float bminy, bminz, bmaxx, bmaxy;
+		float bmaxz;
+		uint32_t mesh_root; // global node index of the mesh root, kNoIndex = no mesh / empty mesh
+		uint32_t mat_offset;
+		uint32_t mat_count;
+	};
+	static_assert(sizeof(DInstance) == 96, "DInstance layout");
+
+	struct DMap
+	{
+		const void* pixels;
+		uint32_t width, height;
+		uint32_t format, filter, address;
+		float scale_x, scale_y;
+		float rot_sin, rot_cos;
+		float trans_x, trans_y;
+		uint32_t _pad;
+	};
+
+	struct DScene
+	{
+		const float4* nodes;    // 2 x float4 per node: {min.xyz, max.x}, {max.y, max.z, begin, type_count}; global indices
+		const float4* tri_hot;  // 3 x float4 per triangle: {v1.xyz, e1.x}, {e1.yz, e2.xy}, {e2.z, slot, -, -}
+		const float4* tri_cold; // 5 x float4 per triangle: n1, n2, n3, face normal, uvs
+		const DInstance* instances;
+		const uint32_t* inst_host_index;
+		const uint32_t* tri_host_index;
+		const uint32_t* inst_materials;
+		const rzb_material* materials; // [material_count] + world material at index world_material
+		const DMap* maps;
+		const rzb_direct_light* direct_lights;
+		const rzb_spot_light* spot_lights;
+		uint32_t top_root;       // global node index of the instance tree root
+		uint32_t instance_count;
+		uint32_t material_count;
+		uint32_t world_material; // index of the world material in `materials`
+		uint32_t default_material;
+		uint32_t direct_light_count, spot_light_count;
+		uint32_t flags;
+	};
+
+	struct Hit
+	{
+		float t;       // ray.near_far.y after traversal
+		float near_;   // ray.near_far.x after traversal (changes when an instance registers a hit)
+		float b1, b2;
+		uint32_t tri;  // global triangle index (BVH order), kNoIndex on miss
+		uint32_t inst; // index into the BVH-ordered instance array
+		bool external;
+	};
+
+	struct TraceCounters
+	{
+		uint32_t top_nodes, instances, mesh_nodes, triangles;
+	};
+
+	// ---- short stack: first kSmemStack entries per thread in shared memory (interleaved by thread so a
+	// warp's pushes hit 32 consecutive 8-byte words), the rest in local memory. Depth bound: two trees of
+	// depth <= 33 (max_depth 31 in both builders) plus one instance-range entry.
+	constexpr int kSmemStack = 20;
+	constexpr int kLocalStack = 52;
+	constexpr int kTraceBlock = 128;
+
+	enum : uint32_t
+	{
+		kEntryMeshNode = 0u << 30,
+		kEntryTopNode = 1u << 30,
+		kEntryInstRange = 2u << 30,
+		kEntryKindMask = 3u << 30,
+		kEntryIndexMask = ~(3u << 30)
+	};
+
+	struct Stack
+	{
+		uint2* smem; // &smem_stack[0][threadIdx.x], stride blockDim.x
+		uint2 local[kLocalStack];
+		int sp;
+		__device__ __forceinline__ void push(uint32_t a, uint32_t b)
+		{
+			if (sp < kSmemStack) smem[sp * kTraceBlock] = make_uint2(a, b);
+			else if (sp - kSmemStack < kLocalStack) local[sp - kSmemStack] = make_uint2(a, b);
+			++sp;
+		}
+		__device__ __forceinline__ uint2 pop()
+		{
+			--sp;
+			if (sp < kSmemStack) return smem[sp * kTraceBlock];
+			return local[sp - kSmemStack];
+		}
+	};
+
+	// BoundingBox::rayIntersection: six IEEE divides, fminf/fmaxf, then the three range tests.
+	// Returns the far-independent part; tmin is handed back for the (possibly deferred) `tmin > far` test.
+	__device__ __forceinline__ bool slab_rn(const float4 n0, const float4 n1, const V3& o, const V3& d,
+		const float near_, float& tmin)
+	{
+		const float t1 = fdiv(fsub(n0.x, o.x), d.x);
+		const float t2 = fdiv(fsub(n0.w, o.x), d.x);
+		const float t3 = fdiv(fsub(n0.y, o.y), d.y);
+		const float t4 = fdiv(fsub(n1.x, o.y), d.y);
+		const float t5 = fdiv(fsub(n0.z, o.z), d.z);
+		const float t6 = fdiv(fsub(n1.y, o.z), d.z);
+		tmin = fmaxf(fmaxf(fminf(t1, t2), fminf(t3, t4)), fminf(t5, t6));
+		const float tmax = fminf(fminf(fmaxf(t1, t2), fmaxf(t3, t4)), fmaxf(t5, t6));
+		return !(tmax < near_ || tmin > tmax);
+	}
+	// the reference's full predicate is  !(tmax < near || tmin > tmax || tmin > far)
+	__device__ __forceinline__ bool range_ok(const float tmin, const float far_) { return !(tmin > far_); }
+
+	// Triangle::closestIntersection on the hot record. Returns true when the hit was accepted.
+	__device__ __forceinline__ bool triangle_closest(const float4* __restrict__ tri_hot, const uint32_t tri,
+		const V3& o, const V3& d, const float near_, float& far_, float& b1_out, float& b2_out, bool& external)
+	{
+		const float4 q0 = __ldg(tri_hot + 3 * size_t(tri));
+		const float4 q1 = __ldg(tri_hot + 3 * size_t(tri) + 1);
+		const float4 q2 = __ldg(tri_hot + 3 * size_t(tri) + 2);
+		const V3 v1 = v3(q0.x, q0.y, q0.z);
+		const V3 e1 = v3(q0.w, q1.x, q1.y);
+		const V3 e2 = v3(q1.z, q1.w, q2.x);
+		const V3 pvec = cross_rn(d, e2);
+		float det = dot_rn(e1, pvec);
+		if (det > -1.0e-7f && det < 1.0e-7f) det = fadd(det, 1.0e-7f);
+		const float inv_det = fdiv(1.0f, det);
+		const V3 tvec = sub_rn(o, v1);
+		const float b1 = fmul(dot_rn(tvec, pvec), inv_det);
+		if (b1 < 0.0f || b1 > 1.0f) return false;
+		const V3 qvec = cross_rn(tvec, e1);
+		const float b2 = fmul(dot_rn(d, qvec), inv_det);
+		if (b2 < 0.0f || fadd(b1, b2) > 1.0f) return false;
+		const float t = fmul(dot_rn(e2, qvec), inv_det);
+		if (t <= near_ || t >= far_) return false;
+		far_ = t;
+		b1_out = b1;
+		b2_out = b2;
+		external = det > 0.0f;
+		return true;
+	}
+
+	// Transformation::transformG2L + length factor (cuda_instance.cuh:193-199, cuda_render_parts.cuh:1150-1158).
+	// Normalisation divides by the magnitude (the host Math library's Normalize as restated in oracle/shim/vec3.h;
+	// the reference's CUDA side uses rnorm3df — see DESIGN.md "normalisation").
+	__device__ __forceinline__ void ray_to_local(const DInstance& in, const V3& wo, const V3& wd,
+		V3& lo, V3& ld, float& len)
+	{
+		const V3 p = sub_rn(wo, v3(in.px, in.py, in.pz));
+		lo = v3(
+			fdiv(fadd(fadd(fmul(in.xx, p.x), fmul(in.xy, p.y)), fmul(in.xz, p.z)), in.sx),
+			fdiv(fadd(fadd(fmul(in.yx, p.x), fmul(in.yy, p.y)), fmul(in.yz, p.z)), in.sy),
+			fdiv(fadd(fadd(fmul(in.zx, p.x), fmul(in.zy, p.y)), fmul(in.zz, p.z)), in.sz));
+		ld = v3(
+			fdiv(fadd(fadd(fmul(in.xx, wd.x), fmul(in.xy, wd.y)), fmul(in.xz, wd.z)), in.sx),
+			fdiv(fadd(fadd(fmul(in.yx, wd.x), fmul(in.yy, wd.y)), fmul(in.yz, wd.z)), in.sy),
+			fdiv(fadd(fadd(fmul(in.zx, wd.x), fmul(in.zy, wd.y)), fmul(in.zz, wd.z)), in.sz));
+		len = __fsqrt_rn(fadd(fadd(fmul(ld.x, ld.x), fmul(ld.y, ld.y)), fmul(ld.z, ld.z)));
+		ld = v3(fdiv(ld.x, len), fdiv(ld.y, len), fdiv(ld.z, len));
+	}
+
+	__device__ __forceinline__ uint32_t sign_bits(const V3& d)
+	{
+		// bit 2 = x, bit 1 = y, bit 0 = z (cuda_instance.cuh:49-52); split types X=2, Y=1, Z=0, Size=3
+		return (uint32_t(d.x < 0.0f) << 2) | (uint32_t(d.y < 0.0f) << 1) | uint32_t(d.z < 0.0f);
+	}
+
+	__device__ __forceinline__ DInstance load_instance(const DInstance* __restrict__ instances, uint32_t i)
+	{
+		const float4* p = reinterpret_cast<const float4*>(instances + i);
+		DInstance r;
+		float4* q = reinterpret_cast<float4*>(&r);
+#pragma unroll
+		for (int k = 0; k < 6; ++k) q[k] = __ldg(p + k);
+		return r;
+	}
+
+	// Closest hit of the two-level tree. `ordered` = near-child-first (closest-hit order); the any-hit
+	// variant below uses the fixed first/second order of the reference's shadow traversal.
+	template <bool STATS>
+	__device__ __forceinline__ Hit trace_closest(const DScene& sc, const V3 wo, const V3 wd,
+		const float near_in, const float far_in, Stack& st, TraceCounters* cnt)
+	{
+		Hit hit;
+		hit.t = far_in; hit.near_ = near_in; hit.b1 = 0.0f; hit.b2 = 0.0f;
+		hit.tri = kNoIndex; hit.inst = kNoIndex; hit.external = true;
+		if (sc.instance_count == 0u) return hit;
+
+		const float4* __restrict__ nodes = sc.nodes;
+		float wnear = near_in, wfar = far_in; // world range
+		float near_ = near_in, far_ = far_in; // range of the current level
+		V3 o = wo, d = wd;
+		uint32_t sbits = sign_bits(wd);
+		const uint32_t wbits = sbits;
+		float len = 1.0f;
+		bool in_mesh = false, mesh_hit = false;
+		uint32_t cur_inst = kNoIndex;
+		uint32_t ltri = kNoIndex; float lb1 = 0.0f, lb2 = 0.0f; bool lext = true;
+		st.sp = 0;
+
+		// root of the instance tree
+		uint32_t cur_begin, cur_tc;
+		{
+			const float4 n0 = __ldg(nodes + 2 * size_t(sc.top_root));
+			const float4 n1 = __ldg(nodes + 2 * size_t(sc.top_root) + 1);
+			float tmin;
+			if (STATS) cnt->top_nodes++;
+			if (!(slab_rn(n0, n1, o, d, near_, tmin) && range_ok(tmin, far_))) return hit;
+			cur_begin = __float_as_uint(n1.z);
+			cur_tc = __float_as_uint(n1.w);
+		}
+		bool have_cur = true; // cur_* describes a node whose box has been passed
+
+		for (;;)
+		{
+			if (have_cur)
+			{
+				const uint32_t count = cur_tc & 0x3FFFFFFFu;
+				if (count != 0u)
+				{
+					// leaf
+					if (in_mesh)
+					{
+						for (uint32_t i = cur_begin; i < cur_begin + count; ++i)
+						{
+							if (STATS) cnt->triangles++;
+							if (triangle_closest(sc.tri_hot, i, o, d, near_, far_, lb1, lb2, lext))
+							{
+								ltri = i;
+								mesh_hit = true;
+							}
+						}
+					}
+					else
+					{
+						st.push(kEntryInstRange | cur_begin, cur_begin + count);
+					}
+					have_cur = false;
+					continue;
+				}
+				// inner node: fetch the sibling pair (64 B, 64-byte aligned)
+				const uint32_t flip = (sbits >> (cur_tc >> 30)) & 1u;
+				const uint32_t ia = cur_begin + flip, ib = cur_begin + (flip ^ 1u);
+				const float4 a0 = __ldg(nodes + 2 * size_t(ia));
+				const float4 a1 = __ldg(nodes + 2 * size_t(ia) + 1);
+				const float4 b0 = __ldg(nodes + 2 * size_t(ib));
+				const float4 b1 = __ldg(nodes + 2 * size_t(ib) + 1);
+				if (STATS) { if (in_mesh) cnt->mesh_nodes += 2; else cnt->top_nodes += 2; }
+				float tmin_a, tmin_b;
+				const bool hit_a = slab_rn(a0, a1, o, d, near_, tmin_a) && range_ok(tmin_a, far_);
+				const bool box_b = slab_rn(b0, b1, o, d, near_, tmin_b);
+				const uint32_t a_tc = __float_as_uint(a1.w), b_tc = __float_as_uint(b1.w);
+				const bool a_leaf = (a_tc & 0x3FFFFFFFu) != 0u;
+				const uint32_t kind = in_mesh ? kEntryMeshNode : kEntryTopNode;
+
+				if (hit_a && (!a_leaf || !in_mesh))
+				{
+					// A is searched first (its subtree, or — at the top level — its instances); B's range test is
+					// deferred: it must see the range as it is AFTER A has been searched
+					if (box_b && range_ok(tmin_b, far_)) st.push(kind | ib, __float_as_uint(tmin_b));
+					cur_begin = __float_as_uint(a1.z);
+					cur_tc = a_tc;
+					continue;
+				}
+				if (hit_a)
+				{
+					// mesh leaf A: intersect now, then B sees the updated range immediately
+					const uint32_t begin = __float_as_uint(a1.z), cnt_a = a_tc & 0x3FFFFFFFu;
+					for (uint32_t i = begin; i < begin + cnt_a; ++i)
+					{
+						if (STATS) cnt->triangles++;
+						if (triangle_closest(sc.tri_hot, i, o, d, near_, far_, lb1, lb2, lext))
+						{
+							ltri = i;
+							mesh_hit = true;
+						}
+					}
+				}
+				if (box_b && range_ok(tmin_b, far_))
+				{
+					cur_begin = __float_as_uint(b1.z);
+					cur_tc = b_tc;
+					continue;
+				}
+				have_cur = false;
+				continue;
+			}
+
+			// ---- pop ----
+			if (st.sp == 0)
+			{
+				if (!in_mesh) break;
+			}
+			uint2 e = make_uint2(kEntryTopNode, 0u);
+			bool popped = false;
+			if (st.sp != 0)
+			{
+				e = st.pop();
+				popped = true;
+			}
+			const uint32_t ekind = e.x & kEntryKindMask;
+			if (in_mesh && (!popped || ekind != kEntryMeshNode))
+			{
+				// the current mesh is exhausted: leave the instance (cuda_instance.cuh:203-213)
+				if (mesh_hit)
+				{
+					hit.inst = cur_inst;
+					hit.tri = ltri; hit.b1 = lb1; hit.b2 = lb2; hit.external = lext;
+					wnear = fdiv(near_, len);
+					wfar = fdiv(far_, len);
+				}
+				in_mesh = false;
+				o = wo; d = wd; sbits = wbits;
+				near_ = wnear; far_ = wfar;
+				if (!popped) break;
+			}
+			const uint32_t idx = e.x & kEntryIndexMask;
+			if (ekind == kEntryInstRange)
+			{
+				const uint32_t end = e.y;
+				if (idx + 1u < end) st.push(kEntryInstRange | (idx + 1u), end);
+				// Instance::closestIntersection
+				if (STATS) cnt->instances++;
+				const DInstance in = load_instance(sc.instances, idx);
+				float tmin;
+				const float4 n0 = make_float4(in.bminx, in.bminy, in.bminz, in.bmaxx);
+				const float4 n1 = make_float4(in.bmaxy, in.bmaxz, 0.0f, 0.0f);
+				if (!(slab_rn(n0, n1, o, d, near_, tmin) && range_ok(tmin, far_))) continue;
+				if (in.mesh_root == kNoIndex) continue;
+				V3 lo, ld;
+				float l;
+				ray_to_local(in, wo, wd, lo, ld, l);
+				const float lnear = fmul(near_, l), lfar = fmul(far_, l);
+				// mesh root (cuda_instance.cuh:37-38)
+				const float4 r0 = __ldg(nodes + 2 * size_t(in.mesh_root));
+				const float4 r1 = __ldg(nodes + 2 * size_t(in.mesh_root) + 1);
+				if (STATS) cnt->mesh_nodes++;
+				if (!(slab_rn(r0, r1, lo, ld, lnear, tmin) && range_ok(tmin, lfar))) continue;
+				in_mesh = true; mesh_hit = false;
+				cur_inst = idx;
+				o = lo; d = ld; len = l; sbits = sign_bits(ld);
+				near_ = lnear; far_ = lfar;
+				cur_begin = __float_as_uint(r1.z);
+				cur_tc = __float_as_uint(r1.w);
+				have_cur = true;
+				continue;
+			}
+			// deferred node: late range test, then fetch its own header
+			if (!range_ok(__uint_as_float(e.y), far_)) continue;
+			const float4 n1 = __ldg(nodes + 2 * size_t(idx) + 1);
+			cur_begin = __float_as_uint(n1.z);
+			cur_tc = __float_as_uint(n1.w);
+			have_cur = true;
+		}
+		hit.t = wfar;
+		hit.near_ = wnear;
+		return hit;
+	}
+}

@@ -1,0 +1,507 @@
+// The wavefront kernels of the B200 render path (one pass = one path segment per pixel, as in the
+// reference: cuda_render_kernel.cu:67-121, but split by stage instead of one megakernel):
+//
+//   k_reset          zero the accumulator, pixel-centre rays into the path state      (passReset + generateCameraRay)
+//   k_trace_paths    closest hit for every live path; persistent warps pull 32-ray batches with one atomic
+//   k_shade          surface analysis, emission, BSDF sampling, NEE set-up (shadow rays appended to a queue by
+//                    warp-ballot compaction), accumulation, continue-or-regenerate
+//   k_trace_shadow   any-hit over the compacted shadow queue; visible light is added to the accumulator
+//   k_tonemap        ComputeFinalColor (cuda_postprocess_kernel.cu:38-58), optionally summing peer accumulators
+//                    over NVLink loads in the same pass
+// plus the ray-set entry points used for ID parity (k_trace_rays, k_trace_any_rays, k_convert_hits,
+// k_camera_rays).
+//
+// Path state lives in HBM as three coalesced arrays indexed by slot (40 B per pixel): slots follow 8x4 pixel
+// tiles so that a warp's 32 primary rays cover a compact screen patch (better node/triangle reuse in L1/L2 than
+// the reference's 32x1 rows).
+#pragma once
+
+#include "rzb_shade.cuh"
+
+namespace rzb
+{
+	constexpr uint32_t kHitTriMask = 0x3FFFFFFFu;
+	constexpr uint32_t kHitExternalBit = 0x80000000u;
+	constexpr uint32_t kHitScatterBit = 0x40000000u;
+	constexpr uint32_t kMediumShift = 8u;
+
+	struct DFrame
+	{
+		DCamera cam;
+		uint32_t tiles_x, tiles_y, n_slots;
+		float4* st_o;   // {o.xyz, bits(depth | medium << 8)}
+		float4* st_d;   // {d.xyz, throughput.r}
+		float2* st_c;   // {throughput.g, throughput.b}
+		float4* hit_a;  // {t, b1, b2, bits(tri | flags)}
+		uint32_t* hit_inst;
+		float4* accum;  // row-major width*height: rgb sum, alpha = completed paths
+		float* depth;   // row-major, written on the first pass after a reset
+		// shadow queue
+		float4* sh_o;   // {origin.xyz, max distance}
+		float4* sh_d;   // {direction.xyz, bits(pixel index)}
+		float4* sh_c;   // {contribution.rgb, -}
+		uint32_t* counters; // [0] closest work counter, [1] shadow queue size, [2] shadow work counter
+		uint32_t shadow_capacity;
+		uint32_t pass_index;
+		uint32_t max_depth, direct_samples, spot_samples;
+		uint64_t seed;
+	};
+
+	__device__ __forceinline__ bool slot_to_pixel(const DFrame& f, uint32_t slot, uint32_t& x, uint32_t& y)
+	{
+		const uint32_t tile = slot >> 5, within = slot & 31u;
+		x = (tile % f.tiles_x) * 8u + (within & 7u);
+		y = (tile / f.tiles_x) * 4u + (within >> 3);
+		return x < f.cam.width && y < f.cam.height;
+	}
+
+	__device__ __forceinline__ Stack make_stack(uint2* smem_base)
+	{
+		Stack st;
+		st.smem = smem_base + threadIdx.x;
+		st.sp = 0;
+		return st;
+	}
+
+	// ---------------------------------------------------------------- k_reset
+	__global__ void k_reset(DFrame f, uint32_t world_material)
+	{
+		const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
+		if (slot >= f.n_slots) return;
+		uint32_t x, y;
+		if (!slot_to_pixel(f, slot, x, y)) return;
+		V3 o, d;
+		camera_simple_ray(f.cam, x, y, o, d);
+		f.st_o[slot] = make_float4(o.x, o.y, o.z, __uint_as_float(world_material << kMediumShift));
+		f.st_d[slot] = make_float4(d.x, d.y, d.z, 1.0f);
+		f.st_c[slot] = make_float2(1.0f, 1.0f);
+		const size_t p = size_t(y) * f.cam.width + x;
+		f.accum[p] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+		f.depth[p] = 0.0f;
+	}
+
+	// ---------------------------------------------------------------- k_trace_paths
+	__global__ void __launch_bounds__(kTraceBlock) k_trace_paths(DScene sc, DFrame f)
+	{
+		__shared__ uint2 smem_stack[kSmemStack * kTraceBlock];
+		Stack st = make_stack(smem_stack);
+		const uint32_t lane = threadIdx.x & 31u;
+		for (;;)
+		{
+			uint32_t base = 0;
+			if (lane == 0) base = atomicAdd(&f.counters[0], 32u);
+			base = __shfl_sync(0xFFFFFFFFu, base, 0);
+			if (base >= f.n_slots) break;
+			const uint32_t slot = base + lane;
+			uint32_t x, y;
+			if (slot >= f.n_slots || !slot_to_pixel(f, slot, x, y)) continue;
+			const float4 so = f.st_o[slot];
+			const float4 sd = f.st_d[slot];
+			const uint32_t bits = __float_as_uint(so.w);
+			const uint32_t depth = bits & 0xFFu, medium = bits >> kMediumShift;
+			float near_ = 0.0f, far_ = kFltMax;
+			if (depth == 0u) { near_ = f.cam.near_; far_ = f.cam.far_; }
+			uint32_t flags = 0u;
+			// World::closestIntersection: free flight in the current medium first (cuda_material.cuh:141-159)
+			if (!(sc.flags & RZB_FLAG_CPU_SEMANTICS))
+			{
+				const float sigma = sc.materials[medium].scattering;
+				if (sigma > 1.0e-4f)
+				{
+					Rng rng(f.seed, slot, f.pass_index);
+					const float dist = (-__logf(rng.next() + 1.0e-4f)) / sigma;
+					if (dist < far_) { far_ = dist; flags |= kHitScatterBit; }
+				}
+			}
+			const Hit h = trace_closest<false>(sc, v3(so.x, so.y, so.z), v3(sd.x, sd.y, sd.z), near_, far_, st, nullptr);
+			uint32_t tri_bits = flags | (h.external ? kHitExternalBit : 0u);
+			tri_bits |= (h.tri == kNoIndex) ? kHitTriMask : (h.tri & kHitTriMask);
+			f.hit_a[slot] = make_float4(h.t, h.b1, h.b2, __uint_as_float(tri_bits));
+			f.hit_inst[slot] = h.inst;
+		}
+	}
+
+	// ---------------------------------------------------------------- shadow queue append (warp-ballot compaction)
+	__device__ __forceinline__ void shadow_push(const DFrame& f, bool want, float3 o, float3 d, float dist,
+		uint32_t pixel, float3 contrib)
+	{
+		const uint32_t active = __activemask();
+		const uint32_t ballot = __ballot_sync(active, want);
+		if (ballot == 0u) return;
+		const uint32_t lane = threadIdx.x & 31u;
+		const uint32_t leader = __ffs(ballot) - 1u;
+		uint32_t base = 0;
+		if (lane == leader) base = atomicAdd(&f.counters[1], uint32_t(__popc(ballot)));
+		base = __shfl_sync(active, base, leader);
+		if (!want) return;
+		const uint32_t idx = base + __popc(ballot & ((1u << lane) - 1u));
+		if (idx >= f.shadow_capacity) return;
+		f.sh_o[idx] = make_float4(o.x, o.y, o.z, dist);
+		f.sh_d[idx] = make_float4(d.x, d.y, d.z, __uint_as_float(pixel));
+		f.sh_c[idx] = make_float4(contrib.x, contrib.y, contrib.z, 0.0f);
+	}
+
+	// ---------------------------------------------------------------- k_shade
+	__global__ void __launch_bounds__(128) k_shade(DScene sc, DFrame f)
+	{
+		const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
+		uint32_t x = 0, y = 0;
+		const bool valid = slot < f.n_slots && slot_to_pixel(f, slot, x, y);
+		// threads without a pixel still take part in the warp-level queue appends
+		float4 so = make_float4(0, 0, 0, 0), sd = make_float4(0, 0, 1, 0), ha = make_float4(0, 0, 0, 0);
+		float2 scol = make_float2(0, 0);
+		uint32_t hinst = kNoIndex;
+		if (valid)
+		{
+			so = f.st_o[slot]; sd = f.st_d[slot]; scol = f.st_c[slot];
+			ha = f.hit_a[slot]; hinst = f.hit_inst[slot];
+		}
+		const uint32_t bits = __float_as_uint(so.w);
+		uint32_t depth = bits & 0xFFu;
+		uint32_t medium = valid ? (bits >> kMediumShift) : sc.world_material;
+		float3 ro = f3(so.x, so.y, so.z);
+		float3 rd = f3(sd.x, sd.y, sd.z);
+		float3 thr = f3(sd.w, scol.x, scol.y);
+		const float far_ = ha.x;
+		const uint32_t tri_bits = __float_as_uint(ha.w);
+		const bool cpu_sem = (sc.flags & RZB_FLAG_CPU_SEMANTICS) != 0u;
+
+		Rng rng(f.seed, slot, f.pass_index);
+		rng.dim = 1u; // dimension 1 belongs to the free-flight draw in k_trace_paths
+
+		// ---- traceRay (cuda_render_kernel.cu:146-237)
+		Surface s;
+		s.surface_material = s.behind_material = sc.world_material;
+		s.u = s.v = 0.0f;
+		s.normal = s.mapped_normal = f3(0.0f, 0.0f, 1.0f);
+		s.metalness = s.roughness = s.emission = 0.0f;
+		s.fresnel = 1.0f; s.reflectance = 0.0f; s.tint_factor = 0.0f; s.refr_x = s.refr_y = 0.0f;
+		bool any_hit = false;
+		if (tri_bits & kHitScatterBit)
+		{
+			s.surface_material = s.behind_material = medium;
+			s.normal = s.mapped_normal = rd;
+			any_hit = true;
+		}
+		if (valid && hinst != kNoIndex)
+		{
+			analyze_intersection(sc, hinst, tri_bits & kHitTriMask, ha.y, ha.z, (tri_bits & kHitExternalBit) != 0u, s);
+			any_hit = true;
+		}
+		else
+		{
+			// sky sphere coordinates (cuda_world.cuh:121-126)
+			s.u = -(0.5f + atan2f(rd.z, rd.x) * (1.0f / 6.2831853f));
+			s.v = 0.5f + asinf(fminf(fmaxf(rd.y, -1.0f), 1.0f)) * (1.0f / 3.14159265f);
+		}
+		const rzb_material& smat = sc.materials[s.surface_material];
+		{
+			const float4 oc = material_opacity_color(sc, smat, s.u, s.v);
+			s.color = f3(oc.x, oc.y, oc.z);
+			s.color_alpha = oc.w;
+			s.emission = material_emission(sc, smat, s.u, s.v);
+		}
+		if (!cpu_sem)
+		{
+			// Beer-Lambert through the current medium (cuda_render_kernel.cu:174-176)
+			const rzb_material& mm = sc.materials[medium];
+			const float a = 1.0f - mm.color[3];
+			const float k = __powf(a, far_);
+			thr = thr * f3(mm.color[0], mm.color[1], mm.color[2]) * k;
+		}
+		float3 final_color = f3(0.0f, 0.0f, 0.0f);
+		if (s.emission > 0.0f) final_color = thr * s.color * s.emission;
+
+		bool path_continues = false;
+		float3 next_o = ro, next_d = rd;
+		if (any_hit && valid)
+		{
+			++depth;
+			s.metalness = material_metalness(sc, smat, s.u, s.v);
+			s.roughness = material_roughness(sc, smat, s.u, s.v);
+			s.fresnel = fresnel_specular_ratio(s.mapped_normal, rd, sc.materials[medium].ior,
+				sc.materials[s.behind_material].ior, s.refr_x, s.refr_y);
+			s.reflectance = lerpf(s.fresnel, 1.0f, s.metalness);
+
+			uint32_t next_medium = medium;
+			next_d = sample_direction(sc, s, rd, next_medium, rng);
+			next_o = ro + rd * far_ + s.normal * (0.0001f * far_);
+			medium = next_medium;
+
+			// ---- next event estimation with MIS (cuda_render_kernel.cu:239-355)
+			const bool do_direct = sc.direct_light_count != 0u && f.direct_samples != 0u;
+			const bool do_spot = sc.spot_light_count != 0u && f.spot_samples != 0u;
+			if (do_direct || do_spot)
+			{
+				const float scattering = smat.scattering;
+				const float vS_pdf = brdf(s, scattering, rd, next_d);
+				const float3 brdf_color = lerp3(s.color, f3(1.0f, 1.0f, 1.0f), s.reflectance);
+				const float3 carry = thr * lerp3(f3(1.0f, 1.0f, 1.0f), s.color, s.metalness);
+				const uint32_t pixel = y * f.cam.width + x;
+				if (do_direct)
+				{
+					const float inv_pdf = float(sc.direct_light_count) / float(f.direct_samples);
+					for (uint32_t i = 0; i < f.direct_samples; ++i)
+					{
+						const uint32_t li = min(uint32_t(rng.next() * float(sc.direct_light_count)), sc.direct_light_count - 1u);
+						const rzb_direct_light& L = sc.direct_lights[li];
+						const float3 ldir = f3(-L.direction[0], -L.direction[1], -L.direction[2]);
+						const float cos_size = __cosf(L.angular_size);
+						float Se = 0.0f;
+						float3 vPL;
+						if (dot(next_d, ldir) > cos_size) { Se = L.emission; vPL = next_d; }
+						else
+						{
+							const float r1 = rng.next(), r2 = rng.next();
+							vPL = sample_sphere(r1, r2 * 0.5f * (1.0f - cos_size), ldir);
+						}
+						const float3 vPLn = normalize(vPL);
+						const float b = brdf(s, scattering, rd, vPLn);
+						const float solid_angle = 6.2831853f * (1.0f - cos_size);
+						const float L_pdf = 1.0f / solid_angle;
+						const float vSw = vS_pdf / (vS_pdf + L_pdf);
+						const float Lw = 1.0f - vSw;
+						const float Le = L.emission * solid_angle * b;
+						const float radiance = Le * Lw + Se * vSw;
+						const bool want = radiance >= 1.0e-4f;
+						const float3 c = f3(L.color[0], L.color[1], L.color[2]) * brdf_color * (radiance * inv_pdf) * carry;
+						shadow_push(f, want, next_o, vPLn, kFltMax, pixel, c);
+					}
+				}
+				if (do_spot)
+				{
+					const float inv_pdf = float(sc.spot_light_count) / float(f.spot_samples);
+					const float med_scattering = sc.materials[medium].scattering;
+					for (uint32_t i = 0; i < f.spot_samples; ++i)
+					{
+						const uint32_t li = min(uint32_t(rng.next() * float(sc.spot_light_count)), sc.spot_light_count - 1u);
+						const rzb_spot_light& L = sc.spot_lights[li];
+						const float3 lpos = f3(L.position[0], L.position[1], L.position[2]);
+						// SpotLight::sampleDirection (cuda_spot_light.cuh:56-74)
+						const float3 vD = normalize(next_d);
+						float3 vPL = lpos - next_o;
+						float dPL = length(vPL);
+						const float vOP_dot_vD = dot(vPL, vD);
+						const float dPQ = sqrtf(dPL * dPL - vOP_dot_vD * vOP_dot_vD);
+						float Se = 0.0f;
+						if (dPQ < L.size && vOP_dot_vD > 0.0f)
+						{
+							Se = L.emission;
+							const float dOQ = sqrtf(dPL * dPL - dPQ * dPQ);
+							vPL = next_d * fmaxf(dOQ, 1.0e-4f);
+						}
+						else
+						{
+							vPL = sample_disk(vPL * (1.0f / dPL), L.size, rng) + lpos - next_o;
+						}
+						dPL = length(vPL);
+						const float3 vPLn = vPL * (1.0f / dPL);
+						const float b = brdf(s, scattering, rd, vPLn);
+						const float A = L.size * L.size * 3.14159265f;
+						const float d1 = dPL + 1.0f;
+						const float solid_angle = A / (d1 * d1);
+						const float sctr = __expf(-dPL * med_scattering);
+						const float beam = float(__cosf(L.beam_angle) <
+							similarity(-vPL, f3(L.direction[0], L.direction[1], L.direction[2])));
+						const float L_pdf = 1.0f / solid_angle;
+						const float vSw = vS_pdf / (vS_pdf + L_pdf);
+						const float Lw = 1.0f - vSw;
+						const float Le = L.emission * solid_angle * b;
+						const float radiance = (Le * Lw + Se * vSw) * sctr * beam;
+						const bool want = b >= 1.0e-4f && beam >= 1.0e-4f && radiance >= 1.0e-4f;
+						const float3 c = f3(L.color[0], L.color[1], L.color[2]) * brdf_color * (radiance * inv_pdf) * carry;
+						shadow_push(f, want, next_o, vPLn, dPL, pixel, c);
+					}
+				}
+			}
+			// ray.color.Blend(ray.color * surface.color, tint_factor)
+			thr = thr + (thr * s.color - thr) * s.tint_factor;
+			path_continues = depth < f.max_depth;
+		}
+		if (!valid) return;
+
+		// ---- epilogue (cuda_render_kernel.cu:98-120)
+		const size_t p = size_t(y) * f.cam.width + x;
+		float4 acc = f.accum[p];
+		acc.x += final_color.x; acc.y += final_color.y; acc.z += final_color.z;
+		acc.w += path_continues ? 0.0f : 1.0f;
+		f.accum[p] = acc;
+		if (f.pass_index == 0u) f.depth[p] = far_;
+
+		if (!path_continues)
+		{
+			camera_generate_ray(f.cam, x, y, rng, next_o, next_d);
+			medium = sc.world_material;
+			thr = f3(1.0f, 1.0f, 1.0f);
+			depth = 0u;
+		}
+		f.st_o[slot] = make_float4(next_o.x, next_o.y, next_o.z, __uint_as_float((medium << kMediumShift) | depth));
+		f.st_d[slot] = make_float4(next_d.x, next_d.y, next_d.z, thr.x);
+		f.st_c[slot] = make_float2(thr.y, thr.z);
+	}
+
+	// ---------------------------------------------------------------- k_trace_shadow
+	__global__ void __launch_bounds__(kTraceBlock) k_trace_shadow(DScene sc, DFrame f)
+	{
+		__shared__ uint2 smem_stack[kSmemStack * kTraceBlock];
+		Stack st = make_stack(smem_stack);
+		const uint32_t lane = threadIdx.x & 31u;
+		const uint32_t n = min(f.counters[1], f.shadow_capacity);
+		for (;;)
+		{
+			uint32_t base = 0;
+			if (lane == 0) base = atomicAdd(&f.counters[2], 32u);
+			base = __shfl_sync(0xFFFFFFFFu, base, 0);
+			if (base >= n) break;
+			const uint32_t i = base + lane;
+			if (i >= n) continue;
+			const float4 o = f.sh_o[i];
+			const float4 d = f.sh_d[i];
+			const float4 c = f.sh_c[i];
+			const float4 m = trace_any(sc, v3(o.x, o.y, o.z), v3(d.x, d.y, d.z), 0.0f, o.w, st);
+			const float w = m.w;
+			if (w <= 0.0f) continue;
+			float* a = reinterpret_cast<float*>(f.accum + __float_as_uint(d.w));
+			atomicAdd(a + 0, c.x * m.x * w);
+			atomicAdd(a + 1, c.y * m.y * w);
+			atomicAdd(a + 2, c.z * m.z * w);
+		}
+	}
+
+	// ---------------------------------------------------------------- k_tonemap
+	struct PeerList
+	{
+		const float4* accum[8];
+		uint32_t count;
+	};
+	__global__ void k_tonemap(const float4* __restrict__ accum, PeerList peers, uchar4* __restrict__ rgba,
+		uint32_t n_pixels, float aperture_area, float exposure_time)
+	{
+		const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+		if (i >= n_pixels) return;
+		float4 p = accum[i];
+		for (uint32_t k = 0; k < peers.count; ++k)
+		{
+			const float4 q = peers.accum[k][i]; // peer-mapped address: the load crosses NVLink
+			p.x += q.x; p.y += q.y; p.z += q.z; p.w += q.w;
+		}
+		// ComputeFinalColor: divide by the sample count, then three separate multiplications, then c/(c+1);
+		// kept in this order (no FMA possible: pure mul/div chain) so RGBA8 truncation matches the oracle bit for bit
+		const float a = p.w == 0.0f ? 1.0f : p.w;
+		float r = fdiv(p.x, a), g = fdiv(p.y, a), b = fdiv(p.z, a);
+		r = fmul(fmul(fmul(r, aperture_area), exposure_time), 1.0e5f);
+		g = fmul(fmul(fmul(g, aperture_area), exposure_time), 1.0e5f);
+		b = fmul(fmul(fmul(b, aperture_area), exposure_time), 1.0e5f);
+		r = fdiv(r, fadd(r, 1.0f)); g = fdiv(g, fadd(g, 1.0f)); b = fdiv(b, fadd(b, 1.0f));
+		rgba[i] = make_uchar4((unsigned char)(fmul(r, 255.0f)), (unsigned char)(fmul(g, 255.0f)), (unsigned char)(fmul(b, 255.0f)), 255);
+	}
+	__global__ void k_accum_add(float4* __restrict__ accum, const float4* __restrict__ other, uint32_t n)
+	{
+		const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+		if (i >= n) return;
+		float4 p = accum[i];
+		const float4 q = other[i];
+		p.x += q.x; p.y += q.y; p.z += q.z; p.w += q.w;
+		accum[i] = p;
+	}
+
+	// ---------------------------------------------------------------- ray-set entry points
+	struct DHit
+	{
+		float t, b1, b2;
+		uint32_t tri_bits;
+		uint32_t inst;
+		uint32_t _pad[3];
+	};
+	static_assert(sizeof(DHit) == 32, "DHit");
+
+	template <bool STATS>
+	__global__ void __launch_bounds__(kTraceBlock) k_trace_rays(DScene sc, const float4* __restrict__ ray_o_near,
+		const float4* __restrict__ ray_d_far, uint32_t n, DHit* __restrict__ hits, uint32_t* counter,
+		unsigned long long* stats)
+	{
+		__shared__ uint2 smem_stack[kSmemStack * kTraceBlock];
+		Stack st = make_stack(smem_stack);
+		const uint32_t lane = threadIdx.x & 31u;
+		TraceCounters cnt{0u, 0u, 0u, 0u};
+		for (;;)
+		{
+			uint32_t base = 0;
+			if (lane == 0) base = atomicAdd(counter, 32u);
+			base = __shfl_sync(0xFFFFFFFFu, base, 0);
+			if (base >= n) break;
+			const uint32_t i = base + lane;
+			if (i >= n) continue;
+			const float4 o = __ldg(ray_o_near + i);
+			const float4 d = __ldg(ray_d_far + i);
+			const Hit h = trace_closest<STATS>(sc, v3(o.x, o.y, o.z), v3(d.x, d.y, d.z), o.w, d.w, st, &cnt);
+			DHit out;
+			out.t = h.t; out.b1 = h.b1; out.b2 = h.b2;
+			out.tri_bits = (h.tri == kNoIndex ? kHitTriMask : (h.tri & kHitTriMask)) | (h.external ? kHitExternalBit : 0u);
+			out.inst = h.inst;
+			out._pad[0] = out._pad[1] = out._pad[2] = 0u;
+			float4* dst = reinterpret_cast<float4*>(hits + i);
+			dst[0] = make_float4(out.t, out.b1, out.b2, __uint_as_float(out.tri_bits));
+			dst[1] = make_float4(__uint_as_float(out.inst), 0.0f, 0.0f, 0.0f);
+		}
+		if (STATS)
+		{
+			atomicAdd(stats + 0, (unsigned long long)cnt.top_nodes);
+			atomicAdd(stats + 1, (unsigned long long)cnt.instances);
+			atomicAdd(stats + 2, (unsigned long long)cnt.mesh_nodes);
+			atomicAdd(stats + 3, (unsigned long long)cnt.triangles);
+		}
+	}
+
+	__global__ void k_convert_hits(DScene sc, const DHit* __restrict__ in, rzb_hit* __restrict__ out, uint32_t n)
+	{
+		const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+		if (i >= n) return;
+		const DHit h = in[i];
+		rzb_hit r;
+		r.t = h.t;
+		if (h.inst == kNoIndex)
+		{
+			r.instance = RZB_NO_INDEX; r.triangle = RZB_NO_INDEX; r.b1 = 0.0f; r.b2 = 0.0f; r.external = 0u;
+		}
+		else
+		{
+			const uint32_t tri = h.tri_bits & kHitTriMask;
+			r.instance = sc.inst_host_index[h.inst];
+			r.triangle = sc.tri_host_index[tri];
+			r.b1 = h.b1; r.b2 = h.b2;
+			r.external = (h.tri_bits & kHitExternalBit) ? 1u : 0u;
+		}
+		out[i] = r;
+	}
+
+	__global__ void __launch_bounds__(kTraceBlock) k_trace_any_rays(DScene sc, const float4* __restrict__ ray_o_near,
+		const float4* __restrict__ ray_d_far, uint32_t n, float4* __restrict__ masks, uint32_t* counter)
+	{
+		__shared__ uint2 smem_stack[kSmemStack * kTraceBlock];
+		Stack st = make_stack(smem_stack);
+		const uint32_t lane = threadIdx.x & 31u;
+		for (;;)
+		{
+			uint32_t base = 0;
+			if (lane == 0) base = atomicAdd(counter, 32u);
+			base = __shfl_sync(0xFFFFFFFFu, base, 0);
+			if (base >= n) break;
+			const uint32_t i = base + lane;
+			if (i >= n) continue;
+			const float4 o = __ldg(ray_o_near + i);
+			const float4 d = __ldg(ray_d_far + i);
+			masks[i] = trace_any(sc, v3(o.x, o.y, o.z), v3(d.x, d.y, d.z), o.w, d.w, st);
+		}
+	}
+
+	__global__ void k_camera_rays(DCamera cam, float4* __restrict__ ray_o_near, float4* __restrict__ ray_d_far)
+	{
+		const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+		if (i >= cam.width * cam.height) return;
+		V3 o, d;
+		camera_simple_ray(cam, i % cam.width, i / cam.width, o, d);
+		ray_o_near[i] = make_float4(o.x, o.y, o.z, cam.near_);
+		ray_d_far[i] = make_float4(d.x, d.y, d.z, cam.far_);
+	}
+}
