@@ -1,0 +1,403 @@
+#!/usr/bin/env python3
+"""bench.py -- the headline measurement of the B200 render path (BASELINE.json: Mrays/s at 1080p).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload NAME] [--impl ours|reference]
+
+A *step* is one pass of the hot path over one frame: one path segment per pixel (closest-hit trace, shade + NEE,
+shadow trace), W*H rays -- the reference's own unit (cuda_render_kernel.cu:122-129: ray_count += W*H per pass).
+One JSON line is printed by rank 0:
+  value      Mrays/s, whole job, scene and path state resident in HBM, K passes timed on the device (CUDA events on
+             the launching stream), barrier + synchronize on both sides, max over ranks
+  e2e        the same metric through the reference-facing boundary with HOST buffers: every e2e step is one
+             Engine::renderWorld-equivalent frame = rzb_set_scene (host arrays -> device) + rzb_set_camera + rzb_reset
+             + rzb_render(rpp passes) + rzb_resolve (tone map, RGBA8 + depth -> pinned host buffers)
+  roofline   HBM roofline of the dominant kernel (k_trace_paths) from ALGORITHMIC bytes
+  cpu_baseline  the reference's own CPU engine (oracle/_ref/rz_ref_tool, built from /root/reference) on this box's
+             host cores on a bounded sample of the same workload
+`--impl reference` times that CPU engine alone and prints the same line with "impl": "reference".
+N > 1 (torchrun): sample streams are sharded over the ranks (same frame, disjoint RNG streams, weak scaling), no
+collective while rendering; the accumulators are combined once, inside the timed region, by the fused
+IPC/NVLink sum + tone-map kernel on rank 0 (NCCL reduce with --reduce nccl).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # BASELINE.json configs[1]: the configuration the metric is quoted on (fits one GPU)
+    "materials_1080p": ("materials", dict(resolution=(1920, 1080), res=64)),
+    # configs[2] geometry (1M triangles, maps, DoF), kept as a secondary line in "aux"
+    "heightfield_1m_1080p": ("heightfield_1m", dict(resolution=(1920, 1080))),
+    "instancing_10m_1080p": ("instancing_10m", dict(resolution=(1920, 1080))),
+    "cornell_512": ("cornell", dict(resolution=(512, 512))),
+}
+# reference-layout byte constants for the algorithmic traffic figure (SURVEY.md 8d / DESIGN.md)
+B_NODE, B_TRI, B_STATE, B_HIT = 48, 144, 57, 24
+MAX_DEPTH = 16          # Tracing::maxDepth default, engine_parts.hpp:101
+RPP_E2E = 64            # passes per renderWorld call the headless auto-tuner converges to (headless.cpp:287-295)
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """Samples SM clock and throttle reasons during the timed region (NVML: the same counters nvidia-smi prints)."""
+
+    def __init__(self, index):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._thread = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def _run(self):
+        nv = self.nv
+        names = {
+            getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8): "hw_slowdown",
+            getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4): "sw_power_cap",
+            getattr(nv, "nvmlClocksEventReasonHwPowerBrakeSlowdown", 0x80): "hw_power_brake_slowdown",
+        }
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.01)
+
+    def start(self):
+        if self.nv:
+            self._thread = threading.Thread(target=self._run, daemon=True)
+            self._thread.start()
+
+    def stop(self):
+        self._stop.set()
+        if self._thread:
+            self._thread.join()
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(s)}
+
+
+def build_world(workload):
+    from rayzath_b200 import scenes
+    name, kw = WORKLOADS[workload]
+    return scenes.CONFIGS[name](**kw)
+
+
+# ---------------------------------------------------------------------------------------------- reference arm
+def reference_run(workload, steps, warmup, budget_s=150.0):
+    """The reference's own CPU engine (oracle/_ref/rz_ref_tool render) on this box's cores. A step = one
+    Engine::renderWorld(CPU) = one pass over the frame; the frame is a bounded sample of the workload: same scene
+    and camera at a resolution reduced until (steps + warmup) passes fit the time budget."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import rz_oracle as O
+    from rayzath_b200 import scenes
+    name, kw = WORKLOADS[workload]
+    full = kw["resolution"]
+    tmp = tempfile.mkdtemp(prefix="rzb_bench_ref_")
+
+    def run(res, passes, wu):
+        kw2 = dict(kw)
+        kw2["resolution"] = res
+        w = scenes.CONFIGS[name](**kw2)
+        path = w.save_reference(os.path.join(tmp, "%dx%d" % res))
+        return O.ref_tool("render", path, passes, "-", MAX_DEPTH, 1, 1, wu)
+
+    probe_res = (max(full[0] // 8, 16), max(full[1] // 8, 16))
+    probe = run(probe_res, 3, 1)
+    rps = probe["timed_rays"] / max(probe["seconds"], 1e-9)
+    div = 1
+    while div < 16 and (steps + warmup) * (full[0] // div) * (full[1] // div) / rps > budget_s:
+        div *= 2
+    res = (max(full[0] // div, 16), max(full[1] // div, 16))
+    info = run(res, steps + warmup, max(warmup, 1))
+    timed_passes = max(info["timed_passes"], 1)
+    value = info["timed_rays"] / info["seconds"] / 1e6
+    return {
+        "value": value, "ms_per_step": info["seconds"] / timed_passes * 1e3, "cores": info["threads"],
+        "sample": "%d passes of the %s scene at %dx%d (1/%d of the pixels of %dx%d), max depth %d, reference CPU engine"
+                  % (timed_passes, workload, res[0], res[1], div * div, full[0], full[1], MAX_DEPTH),
+        "kind": "reference",
+    }
+
+
+# ---------------------------------------------------------------------------------------------- our arm
+def pin(arrays):
+    """Page-lock the host arrays the boundary reads from (cudaHostRegister through torch)."""
+    import torch
+    rt = torch.cuda.cudart()
+    for a in arrays:
+        if a.size:
+            rt.cudaHostRegister(a.ctypes.data, a.nbytes, 0)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=512)
+    ap.add_argument("--warmup", type=int, default=16)
+    ap.add_argument("--workload", default="materials_1080p", choices=sorted(WORKLOADS))
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--reduce", default="ipc", choices=["ipc", "nccl"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-aux", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    base = {"metric": "Mrays/s at 1080p (path segments per second, passes*W*H/t)", "unit": "Mrays/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic"}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        r = reference_run(args.workload, args.steps, args.warmup)
+        line = dict(base)
+        line.update({"impl": "reference", "value": r["value"], "ms_per_step": r["ms_per_step"],
+                     "config": {"workload": args.workload, "max_depth": MAX_DEPTH, "light_samples": [1, 1]},
+                     "cpu_baseline": {"value": r["value"], "unit": "Mrays/s", "cores": r["cores"], "kind": r["kind"],
+                                      "sample": r["sample"]},
+                     "e2e": {"value": r["value"], "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                     "gpu_launches": 0})
+        print(json.dumps(line), flush=True)
+        return 0
+
+    import numpy as np
+    import torch
+    from rayzath_b200 import capi, parallel
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the render path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        dist = parallel.init_process_group("nccl")
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    world_obj = build_world(args.workload)
+    flat = world_obj.flatten()
+    cam = world_obj.camera_struct()
+    W, H = int(cam[0]["width"]), int(cam[0]["height"])
+    n_px = W * H
+    peak, peak_src = load_peaks()
+
+    ctx = capi.Context(local_rank)
+    stream = torch.cuda.current_stream()
+    ctx.set_stream(stream.cuda_stream)
+    ctx.set_scene(flat)
+    ctx.set_camera(cam)
+    seed = parallel.stream_seed(20261018, rank)
+    ctx.set_config(1, 1, MAX_DEPTH, capi.FLAG_NONE, seed)
+    ctx.reset()
+    rgba_host = torch.empty((H, W, 4), dtype=torch.uint8, pin_memory=True).numpy()
+    depth_host = torch.empty((H, W), dtype=torch.float32, pin_memory=True).numpy()
+
+    fused = parallel.FusedResolve(ctx) if (world > 1 and args.reduce == "ipc") else None
+
+    def combine():
+        """the one exchange step of the N>1 path: sum the accumulators onto rank 0 (and tone-map there)"""
+        if world == 1:
+            return
+        if fused is not None:
+            fused(want_depth=True)
+        else:
+            parallel.reduce_accum(ctx.accum_tensor().clone(), dst=0)  # a copy: rendering continues on the original
+
+    # ---- warm-up, then the timed region: K passes (+ the exchange step), device-timed on the launching stream
+    ctx.render(args.warmup)
+    combine()
+    barrier()
+    alpha0 = float(ctx.read_accum()[..., 3].mean())
+    launches0 = int(ctx.render_stats()["kernel_launches"])
+    sampler = ClockSampler(local_rank)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    sampler.start()
+    ev0.record(stream)
+    ctx.render(args.steps)
+    combine()
+    ev1.record(stream)
+    ev1.synchronize()
+    barrier()
+    clocks = sampler.stop()
+    ms = ev0.elapsed_time(ev1)
+    # per-kernel device time per launch: CUDA events recorded around each stage of (up to 256 of) the timed passes
+    st = ctx.render_stats()
+    trace_ms, shade_ms, shadow_ms = float(st["last_trace_ms"]), float(st["last_shade_ms"]), float(st["last_shadow_ms"])
+    launches = int(st["kernel_launches"]) - launches0
+    t_all = torch.tensor([ms, (float(ctx.read_accum()[..., 3].mean()) - alpha0)], dtype=torch.float64, device="cuda")
+    ms_max, spp_sum = float(t_all[0].item()), float(t_all[1].item())
+    if dist is not None:
+        t_max = t_all.clone()
+        dist.all_reduce(t_max, op=dist.ReduceOp.MAX)
+        dist.all_reduce(t_all, op=dist.ReduceOp.SUM)
+        ms_max, spp_sum = float(t_max[0].item()), float(t_all[1].item())
+    value = world * args.steps * n_px / (ms_max * 1e-3) / 1e6
+    spp_per_s = spp_sum / (ms_max * 1e-3)
+
+    # ---- algorithmic bytes of the dominant kernel: replay the same passes with the counting kernels
+    # (the RNG is counter-based on (seed, pixel, pass): after a reset the same pass indices retrace the same rays)
+    ctx.reset()
+    ctx.render(args.warmup)
+    ctx.set_config(1, 1, MAX_DEPTH, capi.FLAG_COUNT_WORK, seed)
+    ctx.render(args.steps)
+    wc = ctx.work_counters()
+    seg = max(int(wc["segments"]), 1)
+    nodes_per_seg = float(wc["closest_top_nodes"] + wc["closest_mesh_nodes"]) / seg
+    tris_per_seg = float(wc["closest_triangles"]) / seg
+    shadow_per_seg = float(wc["shadow_rays"]) / seg
+    bytes_per_seg = B_STATE + nodes_per_seg * B_NODE + tris_per_seg * B_TRI + B_HIT
+    achieved = bytes_per_seg * n_px / (trace_ms * 1e-3) / 1e9 if trace_ms > 0 else None
+    traffic = None
+    prof = os.path.join(ROOT, "profiles", "ncu_summary.json")
+    if os.path.exists(prof):
+        try:
+            traffic = json.load(open(prof)).get(args.workload, {}).get("k_trace_paths_dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+    ctx.set_config(1, 1, MAX_DEPTH, capi.FLAG_NONE, seed)
+
+    # ---- e2e through the boundary with host buffers (every step = one renderWorld-equivalent frame)
+    host_arrays = [np.ascontiguousarray(v) for v in flat.values()]
+    flat_pinned = dict(zip(flat.keys(), host_arrays))
+    try:
+        pin(host_arrays)
+    except Exception:
+        pass
+    h2d = sum(a.nbytes for a in host_arrays) + cam.nbytes + capi.config_dtype.itemsize
+    d2h = rgba_host.nbytes + depth_host.nbytes
+    e2e_frames = max(2, min(8, args.steps // RPP_E2E))
+
+    def frame():
+        ctx.set_scene(flat_pinned)
+        ctx.set_camera(cam)
+        ctx.set_config(1, 1, MAX_DEPTH, capi.FLAG_NONE, seed)
+        ctx.reset()
+        ctx.render(RPP_E2E)
+        if world > 1:
+            if fused is not None:
+                fused(want_depth=True)
+            else:
+                parallel.reduce_accum(ctx.accum_tensor(), dst=0)
+                if rank == 0:
+                    ctx.resolve(rgba_host, depth_host)
+        else:
+            ctx.resolve(rgba_host, depth_host)
+
+    frame()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_frames):
+        frame()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    e2e_t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
+    e2e_value = world * e2e_frames * RPP_E2E * n_px / float(e2e_t.item()) / 1e6
+
+    # ---- secondary workload (config 3 geometry) and the CPU baseline: rank 0, N=1 only
+    aux = None
+    cpu = None
+    if rank == 0 and world == 1:
+        if not args.no_aux and args.workload != "heightfield_1m_1080p":
+            try:
+                w2 = build_world("heightfield_1m_1080p")
+                ctx.set_scene(w2.flatten())
+                ctx.set_camera(w2.camera_struct())
+                ctx.reset()
+                ctx.render(args.warmup)
+                torch.cuda.synchronize()
+                a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                n2 = min(args.steps, 256)
+                a0.record(stream)
+                ctx.render(n2)
+                a1.record(stream)
+                a1.synchronize()
+                st2 = ctx.render_stats()
+                aux = {"workload": "heightfield_1m_1080p", "triangles": int(w2.flatten()["triangles"].shape[0]),
+                       "value": n2 * n_px / (a0.elapsed_time(a1) * 1e-3) / 1e6, "unit": "Mrays/s", "steps": n2,
+                       "trace_ms": float(st2["last_trace_ms"]), "shade_ms": float(st2["last_shade_ms"]),
+                       "shadow_ms": float(st2["last_shadow_ms"])}
+            except Exception as e:  # the headline line must still be printed
+                aux = {"workload": "heightfield_1m_1080p", "error": repr(e)}
+        if not args.no_cpu_baseline:
+            try:
+                r = reference_run(args.workload, 4, 1, budget_s=25.0)
+                cpu = {"value": r["value"], "unit": "Mrays/s", "cores": r["cores"], "kind": r["kind"], "sample": r["sample"]}
+            except Exception as e:
+                cpu = {"value": None, "unit": "Mrays/s", "cores": os.cpu_count(), "kind": "reference", "sample": "failed: %r" % e}
+
+    if rank == 0:
+        working_set = (flat["triangles"].shape[0] * 128 + flat["mesh_nodes"].shape[0] * 32 + n_px * (40 + 20 + 16 + 48)) / 1e6
+        line = dict(base)
+        line.update({
+            "value": value, "ms_per_step": ms_max / args.steps,
+            "config": {"workload": args.workload, "resolution": [W, H], "triangles": int(flat["triangles"].shape[0]),
+                       "instances": int(flat["instances"].shape[0]), "max_depth": MAX_DEPTH, "light_samples": [1, 1],
+                       "sharding": "sample streams x%d" % world if world > 1 else "single GPU",
+                       "reduce": args.reduce if world > 1 else None,
+                       "l2": "no flush: per-pass working set %.0f MB (path state + queues + accumulator + scene) > 126 MB L2"
+                             % working_set,
+                       "spp_per_s": spp_per_s},
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                    "step": "set_scene + set_camera + reset + render(%d passes) + resolve to pinned host buffers" % RPP_E2E,
+                    "frames": e2e_frames},
+            "gpu_launches": launches,
+            "stage_ms_per_pass": {"k_trace_paths": trace_ms, "k_shade": shade_ms, "k_trace_shadow": shadow_ms},
+            "roofline": {"bound": "hbm", "kernel": "k_trace_paths", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": (achieved / peak) if achieved else None, "traffic": traffic, "peak_source": peak_src,
+                         "algorithmic_bytes_per_segment": bytes_per_seg, "nodes_per_segment": nodes_per_seg,
+                         "triangles_per_segment": tris_per_seg, "shadow_rays_per_segment": shadow_per_seg,
+                         "segments_per_launch": n_px},
+            "cpu_baseline": cpu, "aux": aux,
+        })
+        print(json.dumps(line), flush=True)
+    ctx.close()
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -186,8 +186,10 @@ typedef struct rzb_config
 enum
 {
 	RZB_FLAG_NONE = 0,
-	RZB_FLAG_CPU_SEMANTICS = 1 /* follow cpu_engine_kernel.cpp where it differs from the CUDA kernel:
-	                              no medium scattering / Beer-Lambert, opaque shadows, texture replaces colour */
+	RZB_FLAG_CPU_SEMANTICS = 1, /* follow cpu_engine_kernel.cpp where it differs from the CUDA kernel:
+	                               no medium scattering / Beer-Lambert, opaque shadows, texture replaces colour */
+	RZB_FLAG_COUNT_WORK = 2     /* rzb_render counts box tests / triangle tests / shadow rays (rzb_work_counters);
+	                               measurement aid, slower kernels */
 };
 
 /* Closest-hit record (TraversalResult, cuda_render_parts.cuh:946-952), 24 B. */
@@ -211,11 +213,21 @@ typedef struct rzb_render_stats
 {
 	uint64_t passes;           /* since last reset */
 	uint64_t ray_count;        /* passes * width * height  (cuda_render_kernel.cu:122-129) */
-	uint64_t shadow_rays;      /* any-hit queries issued since last reset */
+	uint64_t shadow_rays;      /* any-hit queries issued by the last pass */
 	uint64_t kernel_launches;  /* kernels launched by this context since creation */
-	float last_render_ms;      /* device time of the last rzb_render call (CUDA events) */
-	float last_trace_ms, last_shade_ms, last_shadow_ms; /* per-stage split of the last call */
+	float last_render_ms;      /* device time of the last rzb_render call (CUDA events on the context stream) */
+	/* per-stage device time of the last rzb_render call, averaged over its sampled passes (ms per launch) */
+	float last_trace_ms, last_shade_ms, last_shadow_ms;
 } rzb_render_stats;
+
+/* Work done by rzb_render since the last rzb_reset while RZB_FLAG_COUNT_WORK was set. */
+typedef struct rzb_work_counters
+{
+	uint64_t closest_top_nodes, closest_instances, closest_mesh_nodes, closest_triangles;
+	uint64_t shadow_top_nodes, shadow_instances, shadow_mesh_nodes, shadow_triangles;
+	uint64_t shadow_rays;
+	uint64_t segments; /* closest-hit queries = passes * pixels */
+} rzb_work_counters;
 
 /* ---- context ---- */
 int rzb_abi_version(void);
@@ -224,6 +236,10 @@ int rzb_create(int device, rzb_ctx** out);
 void rzb_destroy(rzb_ctx* ctx);
 /* text of the last error on this context (ctx may be NULL for creation errors) */
 const char* rzb_last_error(const rzb_ctx* ctx);
+/* Run every kernel and copy of this context on the caller's CUDA stream (a cudaStream_t, e.g. the host
+ * framework's current stream) instead of the context's own; NULL restores the private stream. Replaces the
+ * reference's fixed m_render_stream / m_mirror_stream pair (cuda_engine_core.cu:245-249). */
+int rzb_set_stream(rzb_ctx* ctx, void* cuda_stream);
 
 /* ---- world mirror: replaces World::reconstructAll (cuda_world.cu) ---- */
 int rzb_set_scene(rzb_ctx* ctx, const rzb_scene* scene);
@@ -249,10 +265,18 @@ int rzb_accum_add_device(rzb_ctx* ctx, const void* device_rgba_f32, size_t pixel
  * NVLink peer loads while tone-mapping on ctx's device; results as rzb_resolve. */
 int rzb_resolve_peers(rzb_ctx* ctx, rzb_ctx* const* peers, uint32_t n_peers,
 	uint8_t* rgba8, float* depth, uint64_t* ray_count);
+/* One-process-per-GPU variant of the fused resolve: export this context's accumulator as a CUDA IPC handle
+ * (64 bytes) ... */
+int rzb_accum_ipc_handle(rzb_ctx* ctx, void* handle_out_64_bytes);
+/* ... and, on the root rank, open the other ranks' handles and sum + tone-map over NVLink peer loads in ONE
+ * kernel. handles = n_peers * 64 bytes. The peers must have finished rendering (barrier) before the call. */
+int rzb_resolve_ipc(rzb_ctx* ctx, const void* handles, uint32_t n_peers,
+	uint8_t* rgba8, float* depth);
 /* pick ray (rayCast kernel, cuda_render_kernel.cu:130-144): instance host index + material slot. */
 int rzb_raycast(rzb_ctx* ctx, uint32_t* instance, uint32_t* material_slot);
 int rzb_synchronize(rzb_ctx* ctx);
 int rzb_get_render_stats(rzb_ctx* ctx, rzb_render_stats* out);
+int rzb_get_work_counters(rzb_ctx* ctx, rzb_work_counters* out);
 /* human-readable per-stage timings (Engine::timingsString) */
 int rzb_timings(rzb_ctx* ctx, char* buf, size_t buf_size);
 

@@ -8,8 +8,9 @@
 //   dumpscene <scene.json> <out.rzs>            flattened world (C-ABI arrays) + camera 0 + reference pixel-centre rays
 //   trace     <scene.json> <rays.rzs> <out.rzs> closest hit per ray through CPU::Kernel (cpu_engine_kernel.cpp:254-352)
 //   traceany  <scene.json> <rays.rzs> <out.rzs> shadow mask per ray through CPU::Kernel::anyIntersection (:398-481)
-//   render    <scene.json> <passes> <out.rzs|-> [max_depth] [spot_samples] [direct_samples]
-//                                               N x Engine::renderWorld(CPU) ; dumps float accumulator, RGBA8, depth ; prints timing JSON
+//   render    <scene.json> <passes> <out.rzs|-> [max_depth] [spot_samples] [direct_samples] [warmup=1]
+//                                               <passes> x Engine::renderWorld(CPU), the first <warmup> of them untimed (the first call
+//                                               also builds the BVHs) ; dumps float accumulator, RGBA8, depth ; prints timing JSON
 //   headless  <tasks.json> [report_dir] [-r]    the reference's own Application/headless.cpp entry
 #include <chrono>
 #include <cstdio>
@@ -205,13 +206,15 @@ static int cmdRender(int argc, char** argv)
 	if (argc > 5) engine.renderConfig().tracing().maxDepth(uint8_t(std::atoi(argv[5])));
 	if (argc > 6) engine.renderConfig().lightSampling().spotLight(uint8_t(std::atoi(argv[6])));
 	if (argc > 7) engine.renderConfig().lightSampling().directLight(uint8_t(std::atoi(argv[7])));
+	const uint32_t warmup = std::min(passes, argc > 8 ? uint32_t(std::atoi(argv[8])) : 1u);
 	engine.renderEngine(RZ::Engine::RenderEngine::CPU);
 
 	// first call: world.update() (BVH build) + first pass; timed separately as in headless.cpp:209
-	engine.renderWorld(RZ::Engine::RenderEngine::CPU, true, true);
+	for (uint32_t p = 0; p < warmup; ++p)
+		engine.renderWorld(RZ::Engine::RenderEngine::CPU, true, true);
 	const double load_secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_load0).count();
 	const auto t0 = std::chrono::steady_clock::now();
-	for (uint32_t p = 1; p < passes; ++p)
+	for (uint32_t p = warmup; p < passes; ++p)
 		engine.renderWorld(RZ::Engine::RenderEngine::CPU, true, true);
 	const double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
 
@@ -232,10 +235,10 @@ static int cmdRender(int argc, char** argv)
 		w.add("resolution", res, 4, 2);
 	}
 	if (out_path != "-") w.write(out_path);
-	const uint64_t timed_rays = passes > 1 ? rays / passes * (passes - 1) : 0;
+	const uint64_t timed_rays = passes ? rays / passes * (passes - warmup) : 0;
 	std::printf("{\"passes\": %u, \"rays\": %llu, \"timed_passes\": %u, \"timed_rays\": %llu, \"seconds\": %.6f, "
 		"\"first_call_seconds\": %.6f, \"threads\": %u}\n",
-		passes, (unsigned long long)rays, passes > 1 ? passes - 1 : 0, (unsigned long long)timed_rays, secs, load_secs,
+		passes, (unsigned long long)rays, passes - warmup, (unsigned long long)timed_rays, secs, load_secs,
 		std::thread::hardware_concurrency());
 	return 0;
 }

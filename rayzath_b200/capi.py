@@ -20,6 +20,7 @@ LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "librzb200.s
 NO_INDEX = 0xFFFFFFFF
 FLAG_NONE = 0
 FLAG_CPU_SEMANTICS = 1
+FLAG_COUNT_WORK = 2
 MAP_RGBA8, MAP_R8, MAP_R32F = 0, 1, 2
 FILTER_POINT, FILTER_LINEAR = 0, 1
 ADDRESS_WRAP, ADDRESS_CLAMP, ADDRESS_MIRROR, ADDRESS_BORDER = 0, 1, 2, 3
@@ -53,6 +54,10 @@ trace_stats_dtype = np.dtype([("rays", u8), ("top_nodes", u8), ("instances_enter
 render_stats_dtype = np.dtype([("passes", u8), ("ray_count", u8), ("shadow_rays", u8), ("kernel_launches", u8),
                                ("last_render_ms", f4), ("last_trace_ms", f4), ("last_shade_ms", f4),
                                ("last_shadow_ms", f4)])
+
+work_counters_dtype = np.dtype([(n, u8) for n in (
+    "closest_top_nodes", "closest_instances", "closest_mesh_nodes", "closest_triangles",
+    "shadow_top_nodes", "shadow_instances", "shadow_mesh_nodes", "shadow_triangles", "shadow_rays", "segments")])
 
 EXPECTED_SIZES = {
     "rzb_node": (node_dtype, 32), "rzb_triangle": (triangle_dtype, 112), "rzb_mesh": (mesh_dtype, 16),
@@ -89,6 +94,7 @@ SYMBOLS = {
     "rzb_create": (C.c_int, [C.c_int, C.POINTER(_P)]),
     "rzb_destroy": (None, [_P]),
     "rzb_last_error": (C.c_char_p, [_P]),
+    "rzb_set_stream": (C.c_int, [_P, _P]),
     "rzb_set_scene": (C.c_int, [_P, C.POINTER(SceneStruct)]),
     "rzb_set_camera": (C.c_int, [_P, _P]),
     "rzb_set_config": (C.c_int, [_P, _P]),
@@ -99,6 +105,9 @@ SYMBOLS = {
     "rzb_accum_device_ptr": (C.c_int, [_P, C.POINTER(_P), C.POINTER(C.c_size_t)]),
     "rzb_accum_add_device": (C.c_int, [_P, _P, C.c_size_t]),
     "rzb_resolve_peers": (C.c_int, [_P, C.POINTER(_P), C.c_uint32, _P, _P, C.POINTER(C.c_uint64)]),
+    "rzb_accum_ipc_handle": (C.c_int, [_P, _P]),
+    "rzb_resolve_ipc": (C.c_int, [_P, _P, C.c_uint32, _P, _P]),
+    "rzb_get_work_counters": (C.c_int, [_P, _P]),
     "rzb_raycast": (C.c_int, [_P, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),
     "rzb_synchronize": (C.c_int, [_P]),
     "rzb_get_render_stats": (C.c_int, [_P, _P]),
@@ -243,6 +252,10 @@ class Context:
         if rc:
             raise RzbError(rc, (self._l.rzb_last_error(self._h) or b"").decode())
 
+    def set_stream(self, cuda_stream: Optional[int]):
+        """Run on the caller's CUDA stream (e.g. torch.cuda.current_stream().cuda_stream); None = private stream."""
+        self._check(self._l.rzb_set_stream(self._h, cuda_stream))
+
     # -- world mirror
     def set_scene(self, scene: Dict[str, np.ndarray]):
         """scene: dict of arrays as produced by rayzath_b200.scenes.FlatScene.arrays() / rzs.read()."""
@@ -345,6 +358,34 @@ class Context:
 
     def accum_add_device(self, device_ptr: int, pixel_count: int):
         self._check(self._l.rzb_accum_add_device(self._h, device_ptr, pixel_count))
+
+    def accum_ipc_handle(self) -> bytes:
+        buf = C.create_string_buffer(64)
+        self._check(self._l.rzb_accum_ipc_handle(self._h, buf))
+        return buf.raw
+
+    def resolve_ipc(self, handles, want_depth=False):
+        """Fused sum-over-NVLink + tone map of this context's and the peers' accumulators (peers = 64-byte IPC handles)."""
+        rgba8 = np.empty((self.height, self.width, 4), dtype=np.uint8)
+        depth = np.empty((self.height, self.width), dtype=f4) if want_depth else None
+        blob = b"".join(handles)
+        self._check(self._l.rzb_resolve_ipc(self._h, blob if blob else None, len(handles), rgba8.ctypes.data, _ptr(depth)))
+        return rgba8, depth
+
+    def accum_tensor(self):
+        """The device accumulator as a torch tensor [h, w, 4] float32 sharing memory (for NCCL collectives)."""
+        import torch
+        ptr, nbytes = self.accum_device_ptr()
+
+        class _Wrap:
+            __cuda_array_interface__ = {"shape": (self.height, self.width, 4), "typestr": "<f4", "data": (ptr, False),
+                                        "version": 3, "strides": None}
+        return torch.as_tensor(_Wrap(), device="cuda:%d" % self.device)
+
+    def work_counters(self) -> np.ndarray:
+        w = np.zeros(1, dtype=work_counters_dtype)
+        self._check(self._l.rzb_get_work_counters(self._h, w.ctypes.data))
+        return w[0]
 
     def raycast(self):
         inst, slot = C.c_uint32(0), C.c_uint32(0)

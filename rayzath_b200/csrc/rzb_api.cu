@@ -26,6 +26,7 @@ static_assert(sizeof(rzb_spot_light) == 48, "rzb_spot_light");
 static_assert(sizeof(rzb_camera) == 92, "rzb_camera");
 static_assert(sizeof(rzb_config) == 24, "rzb_config");
 static_assert(sizeof(rzb_hit) == 24, "rzb_hit");
+static_assert(sizeof(rzb_scene) == 240, "rzb_scene");
 
 namespace
 {
@@ -42,8 +43,15 @@ struct rzb_ctx
 {
 	int device = 0;
 	int sm_count = 0;
-	cudaStream_t stream = nullptr;
-	cudaEvent_t ev_begin = nullptr, ev_end = nullptr, ev_stage[4] = {nullptr, nullptr, nullptr, nullptr};
+	cudaStream_t stream = nullptr;     // the stream everything runs on (own_stream unless rzb_set_stream gave another)
+	cudaStream_t own_stream = nullptr;
+	cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
+	std::vector<cudaEvent_t> ev_stage; // 4 per sampled pass of the last rzb_render call
+	uint32_t sampled_passes = 0;
+	bool last_had_shadow = false;
+	unsigned long long* d_work = nullptr; // RZB_FLAG_COUNT_WORK counters (16 x u64)
+	uint64_t counted_segments = 0;
+	std::vector<std::pair<std::string, void*>> ipc_open; // opened peer accumulators (handle bytes -> mapped pointer)
 	std::string error;
 
 	std::vector<void*> scene_allocs;
@@ -233,14 +241,16 @@ extern "C" int rzb_create(int device, rzb_ctx** out)
 	cudaDeviceProp prop{};
 	if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) { delete ctx; return cudaFail(nullptr, e, "cudaGetDeviceProperties"); }
 	ctx->sm_count = prop.multiProcessorCount;
-	if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) { delete ctx; return cudaFail(nullptr, e, "cudaStreamCreate"); }
+	if ((e = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking)) != cudaSuccess) { delete ctx; return cudaFail(nullptr, e, "cudaStreamCreate"); }
+	ctx->stream = ctx->own_stream;
 	cudaEventCreate(&ctx->ev_begin);
 	cudaEventCreate(&ctx->ev_end);
-	for (auto& ev : ctx->ev_stage) cudaEventCreate(&ev);
+	if ((e = cudaMalloc(reinterpret_cast<void**>(&ctx->d_work), 128)) != cudaSuccess) { delete ctx; return cudaFail(nullptr, e, "cudaMalloc(work)"); }
+	cudaMemsetAsync(ctx->d_work, 0, 128, ctx->stream);
 	if ((e = cudaMalloc(reinterpret_cast<void**>(&ctx->d_counters), 256)) != cudaSuccess) { delete ctx; return cudaFail(nullptr, e, "cudaMalloc(counters)"); }
 	cudaMemsetAsync(ctx->d_counters, 0, 256, ctx->stream);
-	ctx->trace_grid = gridFor(ctx, reinterpret_cast<const void*>(&k_trace_paths), kTraceBlock);
-	ctx->shadow_grid = gridFor(ctx, reinterpret_cast<const void*>(&k_trace_shadow), kTraceBlock);
+	ctx->trace_grid = gridFor(ctx, reinterpret_cast<const void*>(&k_trace_paths<false>), kTraceBlock);
+	ctx->shadow_grid = gridFor(ctx, reinterpret_cast<const void*>(&k_trace_shadow<false>), kTraceBlock);
 	ctx->rays_grid = gridFor(ctx, reinterpret_cast<const void*>(&k_trace_rays<false>), kTraceBlock);
 	ctx->any_grid = gridFor(ctx, reinterpret_cast<const void*>(&k_trace_any_rays), kTraceBlock);
 	*out = ctx;
@@ -257,11 +267,22 @@ extern "C" void rzb_destroy(rzb_ctx* ctx)
 	for (void* p : ctx->d_shadow) if (p) cudaFree(p);
 	for (auto& b : ctx->scratch) if (b.ptr) cudaFree(b.ptr);
 	if (ctx->d_counters) cudaFree(ctx->d_counters);
+	if (ctx->d_work) cudaFree(ctx->d_work);
+	for (auto& h : ctx->ipc_open) cudaIpcCloseMemHandle(h.second);
 	cudaEventDestroy(ctx->ev_begin);
 	cudaEventDestroy(ctx->ev_end);
 	for (auto& ev : ctx->ev_stage) cudaEventDestroy(ev);
-	cudaStreamDestroy(ctx->stream);
+	cudaStreamDestroy(ctx->own_stream);
 	delete ctx;
+}
+
+extern "C" int rzb_set_stream(rzb_ctx* ctx, void* cuda_stream)
+{
+	if (!ctx) return RZB_ERR_INVALID;
+	DeviceGuard guard(ctx->device);
+	RZB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	ctx->stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : ctx->own_stream;
+	return RZB_OK;
 }
 
 extern "C" int rzb_set_scene(rzb_ctx* ctx, const rzb_scene* s)
@@ -499,6 +520,8 @@ extern "C" int rzb_reset(rzb_ctx* ctx)
 	k_reset<<<(f.n_slots + 255) / 256, 256, 0, ctx->stream>>>(f, ctx->sc.world_material);
 	RZB_CUDA(ctx, cudaGetLastError());
 	RZB_CUDA(ctx, cudaMemsetAsync(ctx->d_counters, 0, 64, ctx->stream));
+	RZB_CUDA(ctx, cudaMemsetAsync(ctx->d_work, 0, 128, ctx->stream));
+	ctx->counted_segments = 0;
 	ctx->launches += 1;
 	ctx->passes = 0;
 	ctx->frame_ready = true;
@@ -524,25 +547,46 @@ extern "C" int rzb_render(rzb_ctx* ctx, uint32_t passes)
 	f.spot_samples = ctx->cfg.spot_light_samples;
 	f.seed = ctx->cfg.seed;
 	const bool lights = (ctx->sc.direct_light_count && f.direct_samples) || (ctx->sc.spot_light_count && f.spot_samples);
+	const bool count = (ctx->cfg.flags & RZB_FLAG_COUNT_WORK) != 0u;
+	f.work = ctx->d_work;
+	// per-stage device timing: up to 256 passes of this call are bracketed by events (4 per sampled pass)
+	const uint32_t stride = (passes + 255u) / 256u;
+	const uint32_t n_sampled = passes ? (passes + stride - 1u) / stride : 0u;
+	while (ctx->ev_stage.size() < size_t(n_sampled) * 4)
+	{
+		cudaEvent_t ev = nullptr;
+		RZB_CUDA(ctx, cudaEventCreate(&ev));
+		ctx->ev_stage.push_back(ev);
+	}
+	ctx->sampled_passes = 0;
+	ctx->last_had_shadow = lights;
 	RZB_CUDA(ctx, cudaEventRecord(ctx->ev_begin, ctx->stream));
 	for (uint32_t p = 0; p < passes; ++p)
 	{
 		f.pass_index = uint32_t(ctx->passes);
-		const bool timed = (p == 0);
+		const bool timed = (p % stride) == 0u;
+		cudaEvent_t* ev = timed ? &ctx->ev_stage[size_t(ctx->sampled_passes) * 4] : nullptr;
 		RZB_CUDA(ctx, cudaMemsetAsync(ctx->d_counters, 0, 12, ctx->stream));
-		if (timed) cudaEventRecord(ctx->ev_stage[0], ctx->stream);
-		k_trace_paths<<<ctx->trace_grid, kTraceBlock, 0, ctx->stream>>>(ctx->sc, f);
-		if (timed) cudaEventRecord(ctx->ev_stage[1], ctx->stream);
+		if (timed) cudaEventRecord(ev[0], ctx->stream);
+		if (count) k_trace_paths<true><<<ctx->trace_grid, kTraceBlock, 0, ctx->stream>>>(ctx->sc, f);
+		else k_trace_paths<false><<<ctx->trace_grid, kTraceBlock, 0, ctx->stream>>>(ctx->sc, f);
+		if (timed) cudaEventRecord(ev[1], ctx->stream);
 		k_shade<<<(f.n_slots + 127) / 128, 128, 0, ctx->stream>>>(ctx->sc, f);
-		if (timed) cudaEventRecord(ctx->ev_stage[2], ctx->stream);
+		if (timed) cudaEventRecord(ev[2], ctx->stream);
 		ctx->launches += 2;
 		if (lights)
 		{
-			k_trace_shadow<<<ctx->shadow_grid, kTraceBlock, 0, ctx->stream>>>(ctx->sc, f);
+			if (count) k_trace_shadow<true><<<ctx->shadow_grid, kTraceBlock, 0, ctx->stream>>>(ctx->sc, f);
+			else k_trace_shadow<false><<<ctx->shadow_grid, kTraceBlock, 0, ctx->stream>>>(ctx->sc, f);
 			ctx->launches += 1;
 		}
-		if (timed) cudaEventRecord(ctx->ev_stage[3], ctx->stream);
+		if (timed)
+		{
+			cudaEventRecord(ev[3], ctx->stream);
+			ctx->sampled_passes += 1;
+		}
 		ctx->passes += 1;
+		if (count) ctx->counted_segments += uint64_t(ctx->cam.width) * ctx->cam.height;
 	}
 	RZB_CUDA(ctx, cudaEventRecord(ctx->ev_end, ctx->stream));
 	RZB_CUDA(ctx, cudaGetLastError());
@@ -670,9 +714,20 @@ extern "C" int rzb_get_render_stats(rzb_ctx* ctx, rzb_render_stats* out)
 	{
 		float ms = 0.0f;
 		if (cudaEventElapsedTime(&ms, ctx->ev_begin, ctx->ev_end) == cudaSuccess) ctx->last_render_ms = ms;
-		if (cudaEventElapsedTime(&ms, ctx->ev_stage[0], ctx->ev_stage[1]) == cudaSuccess) ctx->last_trace_ms = ms;
-		if (cudaEventElapsedTime(&ms, ctx->ev_stage[1], ctx->ev_stage[2]) == cudaSuccess) ctx->last_shade_ms = ms;
-		if (cudaEventElapsedTime(&ms, ctx->ev_stage[2], ctx->ev_stage[3]) == cudaSuccess) ctx->last_shadow_ms = ms;
+		double t = 0.0, sh = 0.0, sd = 0.0;
+		for (uint32_t i = 0; i < ctx->sampled_passes; ++i)
+		{
+			const cudaEvent_t* ev = &ctx->ev_stage[size_t(i) * 4];
+			if (cudaEventElapsedTime(&ms, ev[0], ev[1]) == cudaSuccess) t += ms;
+			if (cudaEventElapsedTime(&ms, ev[1], ev[2]) == cudaSuccess) sh += ms;
+			if (ctx->last_had_shadow && cudaEventElapsedTime(&ms, ev[2], ev[3]) == cudaSuccess) sd += ms;
+		}
+		if (ctx->sampled_passes)
+		{
+			ctx->last_trace_ms = float(t / ctx->sampled_passes);
+			ctx->last_shade_ms = float(sh / ctx->sampled_passes);
+			ctx->last_shadow_ms = float(sd / ctx->sampled_passes);
+		}
 		cudaGetLastError();
 	}
 	uint32_t counters[16] = {};
@@ -683,6 +738,56 @@ extern "C" int rzb_get_render_stats(rzb_ctx* ctx, rzb_render_stats* out)
 	out->last_shade_ms = ctx->last_shade_ms;
 	out->last_shadow_ms = ctx->last_shadow_ms;
 	return RZB_OK;
+}
+
+extern "C" int rzb_get_work_counters(rzb_ctx* ctx, rzb_work_counters* out)
+{
+	if (!ctx || !out) return RZB_ERR_INVALID;
+	DeviceGuard guard(ctx->device);
+	RZB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	unsigned long long h[16] = {};
+	RZB_CUDA(ctx, cudaMemcpy(h, ctx->d_work, sizeof(h), cudaMemcpyDeviceToHost));
+	out->closest_top_nodes = h[0]; out->closest_instances = h[1]; out->closest_mesh_nodes = h[2]; out->closest_triangles = h[3];
+	out->shadow_top_nodes = h[4]; out->shadow_instances = h[5]; out->shadow_mesh_nodes = h[6]; out->shadow_triangles = h[7];
+	out->shadow_rays = h[8];
+	out->segments = ctx->counted_segments;
+	return RZB_OK;
+}
+
+extern "C" int rzb_accum_ipc_handle(rzb_ctx* ctx, void* handle_out)
+{
+	if (!ctx || !handle_out) return fail(ctx, RZB_ERR_INVALID, "rzb_accum_ipc_handle: NULL argument");
+	if (!ctx->has_camera) return fail(ctx, RZB_ERR_STATE, "rzb_accum_ipc_handle: no camera");
+	static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+	DeviceGuard guard(ctx->device);
+	cudaIpcMemHandle_t h;
+	RZB_CUDA(ctx, cudaIpcGetMemHandle(&h, ctx->frame.accum));
+	std::memcpy(handle_out, &h, 64);
+	return RZB_OK;
+}
+
+extern "C" int rzb_resolve_ipc(rzb_ctx* ctx, const void* handles, uint32_t n_peers, uint8_t* rgba8, float* depth)
+{
+	if (!ctx || (n_peers && !handles) || n_peers > 8) return fail(ctx, RZB_ERR_INVALID, "rzb_resolve_ipc: bad arguments");
+	if (!ctx->has_camera) return fail(ctx, RZB_ERR_STATE, "rzb_resolve_ipc: no camera");
+	DeviceGuard guard(ctx->device);
+	PeerList peers{};
+	for (uint32_t i = 0; i < n_peers; ++i)
+	{
+		const std::string key(static_cast<const char*>(handles) + size_t(i) * 64, 64);
+		void* mapped = nullptr;
+		for (auto& h : ctx->ipc_open) if (h.first == key) mapped = h.second;
+		if (!mapped)
+		{
+			cudaIpcMemHandle_t h;
+			std::memcpy(&h, key.data(), 64);
+			RZB_CUDA(ctx, cudaIpcOpenMemHandle(&mapped, h, cudaIpcMemLazyEnablePeerAccess));
+			ctx->ipc_open.emplace_back(key, mapped);
+		}
+		peers.accum[i] = static_cast<const float4*>(mapped);
+	}
+	peers.count = n_peers;
+	return tonemapAndCopy(ctx, peers, rgba8, depth);
 }
 
 extern "C" int rzb_timings(rzb_ctx* ctx, char* buf, size_t buf_size)

@@ -41,6 +41,7 @@ namespace rzb
 		float4* sh_d;   // {direction.xyz, bits(pixel index)}
 		float4* sh_c;   // {contribution.rgb, -}
 		uint32_t* counters; // [0] closest work counter, [1] shadow queue size, [2] shadow work counter
+		unsigned long long* work; // RZB_FLAG_COUNT_WORK: [0..3] closest top/inst/mesh/tri, [4..7] shadow, [8] shadow rays
 		uint32_t shadow_capacity;
 		uint32_t pass_index;
 		uint32_t max_depth, direct_samples, spot_samples;
@@ -81,11 +82,26 @@ namespace rzb
 	}
 
 	// ---------------------------------------------------------------- k_trace_paths
+	__device__ __forceinline__ void flush_counters(const TraceCounters& cnt, unsigned long long* dst)
+	{
+		// one atomic per warp and counter
+		unsigned long long v[4] = {cnt.top_nodes, cnt.instances, cnt.mesh_nodes, cnt.triangles};
+#pragma unroll
+		for (int k = 0; k < 4; ++k)
+		{
+			unsigned long long x = v[k];
+			for (int off = 16; off > 0; off >>= 1) x += __shfl_down_sync(0xFFFFFFFFu, x, off);
+			if ((threadIdx.x & 31u) == 0u && x) atomicAdd(dst + k, x);
+		}
+	}
+
+	template <bool STATS>
 	__global__ void __launch_bounds__(kTraceBlock) k_trace_paths(DScene sc, DFrame f)
 	{
 		__shared__ uint2 smem_stack[kSmemStack * kTraceBlock];
 		Stack st = make_stack(smem_stack);
 		const uint32_t lane = threadIdx.x & 31u;
+		TraceCounters cnt{0u, 0u, 0u, 0u};
 		for (;;)
 		{
 			uint32_t base = 0;
@@ -113,12 +129,13 @@ namespace rzb
 					if (dist < far_) { far_ = dist; flags |= kHitScatterBit; }
 				}
 			}
-			const Hit h = trace_closest<false>(sc, v3(so.x, so.y, so.z), v3(sd.x, sd.y, sd.z), near_, far_, st, nullptr);
+			const Hit h = trace_closest<STATS>(sc, v3(so.x, so.y, so.z), v3(sd.x, sd.y, sd.z), near_, far_, st, &cnt);
 			uint32_t tri_bits = flags | (h.external ? kHitExternalBit : 0u);
 			tri_bits |= (h.tri == kNoIndex) ? kHitTriMask : (h.tri & kHitTriMask);
 			f.hit_a[slot] = make_float4(h.t, h.b1, h.b2, __uint_as_float(tri_bits));
 			f.hit_inst[slot] = h.inst;
 		}
+		if (STATS) flush_counters(cnt, f.work);
 	}
 
 	// ---------------------------------------------------------------- shadow queue append (warp-ballot compaction)
@@ -341,12 +358,15 @@ namespace rzb
 	}
 
 	// ---------------------------------------------------------------- k_trace_shadow
+	template <bool STATS>
 	__global__ void __launch_bounds__(kTraceBlock) k_trace_shadow(DScene sc, DFrame f)
 	{
 		__shared__ uint2 smem_stack[kSmemStack * kTraceBlock];
 		Stack st = make_stack(smem_stack);
 		const uint32_t lane = threadIdx.x & 31u;
 		const uint32_t n = min(f.counters[1], f.shadow_capacity);
+		TraceCounters cnt{0u, 0u, 0u, 0u};
+		if (STATS && blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(f.work + 8, (unsigned long long)n);
 		for (;;)
 		{
 			uint32_t base = 0;
@@ -358,7 +378,7 @@ namespace rzb
 			const float4 o = f.sh_o[i];
 			const float4 d = f.sh_d[i];
 			const float4 c = f.sh_c[i];
-			const float4 m = trace_any(sc, v3(o.x, o.y, o.z), v3(d.x, d.y, d.z), 0.0f, o.w, st);
+			const float4 m = trace_any<STATS>(sc, v3(o.x, o.y, o.z), v3(d.x, d.y, d.z), 0.0f, o.w, st, &cnt);
 			const float w = m.w;
 			if (w <= 0.0f) continue;
 			float* a = reinterpret_cast<float*>(f.accum + __float_as_uint(d.w));
@@ -366,6 +386,7 @@ namespace rzb
 			atomicAdd(a + 1, c.y * m.y * w);
 			atomicAdd(a + 2, c.z * m.z * w);
 		}
+		if (STATS) flush_counters(cnt, f.work + 4);
 	}
 
 	// ---------------------------------------------------------------- k_tonemap
@@ -491,7 +512,7 @@ namespace rzb
 			if (i >= n) continue;
 			const float4 o = __ldg(ray_o_near + i);
 			const float4 d = __ldg(ray_d_far + i);
-			masks[i] = trace_any(sc, v3(o.x, o.y, o.z), v3(d.x, d.y, d.z), o.w, d.w, st);
+			masks[i] = trace_any<false>(sc, v3(o.x, o.y, o.z), v3(d.x, d.y, d.z), o.w, d.w, st, nullptr);
 		}
 	}
 

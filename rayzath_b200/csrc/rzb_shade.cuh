@@ -417,8 +417,9 @@ namespace rzb
 	// ------------------------------------------------------------------ any-hit (cuda_bvh.cuh:172-232, cuda_instance.cuh:92-164, 215-229)
 	// Returns the RGBA shadow mask. Child order is the fixed first/second order of the reference; the mask is a
 	// product, so order only matters for the early-out.
+	template <bool STATS>
 	__device__ __forceinline__ float4 trace_any(const DScene& sc, const V3 wo, const V3 wd,
-		const float near_in, const float far_in, Stack& st)
+		const float near_in, const float far_in, Stack& st, TraceCounters* cnt)
 	{
 		float4 mask = make_float4(1.0f, 1.0f, 1.0f, 1.0f);
 		if (sc.instance_count == 0u) return mask;
@@ -433,6 +434,7 @@ namespace rzb
 			const float4 n0 = __ldg(nodes + 2 * size_t(sc.top_root));
 			const float4 n1 = __ldg(nodes + 2 * size_t(sc.top_root) + 1);
 			float tmin;
+			if (STATS) cnt->top_nodes++;
 			if (!(slab_rn(n0, n1, o, d, near_, tmin) && range_ok(tmin, far_))) return mask;
 			cur_begin = __float_as_uint(n1.z);
 			cur_tc = __float_as_uint(n1.w);
@@ -451,6 +453,7 @@ namespace rzb
 						{
 							float tf = far_, b1, b2;
 							bool ext;
+							if (STATS) cnt->triangles++;
 							if (!triangle_closest(sc.tri_hot, i, o, d, near_, tf, b1, b2, ext)) continue;
 							if (sc.flags & RZB_FLAG_CPU_SEMANTICS) return make_float4(0.0f, 0.0f, 0.0f, 0.0f);
 							const float4 c0 = __ldg(sc.tri_cold + 5 * size_t(i));
@@ -476,6 +479,7 @@ namespace rzb
 				const float4 a1 = __ldg(nodes + 2 * size_t(cur_begin) + 1);
 				const float4 b0 = __ldg(nodes + 2 * size_t(cur_begin) + 2);
 				const float4 b1 = __ldg(nodes + 2 * size_t(cur_begin) + 3);
+				if (STATS) { if (in_mesh) cnt->mesh_nodes += 2; else cnt->top_nodes += 2; }
 				float ta, tb;
 				const bool hit_a = slab_rn(a0, a1, o, d, near_, ta) && range_ok(ta, far_);
 				const bool hit_b = slab_rn(b0, b1, o, d, near_, tb) && range_ok(tb, far_);
@@ -507,6 +511,7 @@ namespace rzb
 			if (ekind == kEntryInstRange)
 			{
 				if (idx + 1u < e.y) st.push(kEntryInstRange | (idx + 1u), e.y);
+				if (STATS) cnt->instances++;
 				const DInstance in = load_instance(sc.instances, idx);
 				float tmin;
 				const float4 n0 = make_float4(in.bminx, in.bminy, in.bminz, in.bmaxx);
@@ -519,6 +524,7 @@ namespace rzb
 				const float lnear = fmul(near_, l), lfar = fmul(far_, l);
 				const float4 r0 = __ldg(nodes + 2 * size_t(in.mesh_root));
 				const float4 r1 = __ldg(nodes + 2 * size_t(in.mesh_root) + 1);
+				if (STATS) cnt->mesh_nodes++;
 				if (!(slab_rn(r0, r1, lo, ld, lnear, tmin) && range_ok(tmin, lfar))) continue;
 				in_mesh = true;
 				mat_offset = in.mat_offset; mat_count = in.mat_count;

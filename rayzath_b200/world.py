@@ -4,7 +4,7 @@ semantics, which
 
   * flattens itself into the C-ABI arrays of include/rzb200.h exactly like the C++ drop-in does from the
     reference's own World (rayzath_b200/host/world_flatten.hpp) -- tests/test_flatten.py checks the two
-    byte for byte through oracle/_ref/rz_ref_tool dumpscene;
+    byte for byte against a dump of the reference World;
   * saves itself in the reference's scene format (`scene.json` + `.obj` + `.png`; json_loader.cpp:1064-1097,
     loader.cpp:735-1030) so the reference's CPU engine renders the identical scene.
 

@@ -1,0 +1,341 @@
+"""Parity tests proper (run with -m gpu on a B200): the CUDA path, called through the C ABI, against
+  * the committed golden vectors produced by the reference's own CPU engine (tests/golden/),
+  * the oracle restatement (oracle/rz_oracle.c) on seeded inputs, up to BASELINE.json's full sizes,
+  * size-independent properties of the estimator (sample counting, linearity of accumulation, tone map).
+Integer / index / byte results are bit-exact; floating-point images use the tolerance stated in each test."""
+import numpy as np
+import pytest
+
+import rz_oracle as O
+from rayzath_b200 import capi, scenes
+from rayzath_b200.world import World
+from tests.golden_scenes import GOLDEN_SCENES, RENDER_SETTINGS, shadow_rays
+
+pytestmark = pytest.mark.gpu
+NAMES = list(GOLDEN_SCENES)
+
+
+@pytest.fixture(scope="module")
+def contexts(flats, worlds):
+    ctxs = {}
+    for name in NAMES:
+        c = capi.Context(0)
+        c.set_scene(flats[name])
+        c.set_camera(worlds[name].camera_struct())
+        ctxs[name] = c
+    yield ctxs
+    for c in ctxs.values():
+        c.close()
+
+
+def _ids_equal(a, b):
+    return (a["instance"] == b["instance"]) & (a["triangle"] == b["triangle"])
+
+
+# ------------------------------------------------------------------ rays and closest hit
+@pytest.mark.parametrize("name", NAMES)
+def test_camera_rays_bit_exact(name, contexts, golden):
+    o, d, nf = contexts[name].generate_camera_rays()
+    g = golden[name]
+    assert np.array_equal(o.view(np.uint32), g["ray_origins"].view(np.uint32))
+    assert np.array_equal(d.view(np.uint32), g["ray_directions"].view(np.uint32))
+    assert np.array_equal(nf.view(np.uint32), g["ray_near_far"].view(np.uint32))
+
+
+@pytest.mark.parametrize("name", NAMES)
+def test_closest_hit_ids_vs_reference_cpu_engine(name, contexts, golden):
+    """Fixed primary-ray set: instance and triangle ids equal to the reference CPU traversal for every ray,
+    except exact-t ties (the CUDA order visits the near child first); t, b1, b2, external bit-equal where ids agree."""
+    g = golden[name]
+    hits = contexts[name].trace_closest(g["ray_origins"], g["ray_directions"], g["ray_near_far"])
+    same = _ids_equal(hits, g["hits"])
+    ties = np.flatnonzero(~same)
+    assert np.array_equal(hits["t"][ties].view(np.uint32), g["hits"]["t"][ties].view(np.uint32)), \
+        "id mismatches that are not exact-t ties: %s" % ties[:10]
+    assert ties.size <= 0.001 * hits.shape[0] + 1, "listed ties: %s" % ties.tolist()
+    assert np.array_equal(hits[same].view(np.uint8), g["hits"][same].view(np.uint8))
+
+
+@pytest.mark.parametrize("name", NAMES)
+def test_closest_hit_records_vs_oracle_cuda_order(name, contexts, golden, flats):
+    """Against the restatement run in the CUDA engine's visiting order the whole record is byte-equal, ties included;
+    the work counters (box tests, triangle tests) equal the reference algorithm's too."""
+    g = golden[name]
+    hits, st = contexts[name].trace_closest(g["ray_origins"], g["ray_directions"], g["ray_near_far"], stats=True)
+    ref, rst = O.trace_closest(O.Scene(flats[name]), g["ray_origins"], g["ray_directions"], g["ray_near_far"],
+                               order=O.ORDER_CUDA, minmax=O.MINMAX_FMINF, stats=True)
+    assert np.array_equal(hits.view(np.uint8), ref.view(np.uint8))
+    assert int(st["triangles"]) == int(rst["triangles"])
+    assert int(st["mesh_nodes"]) == int(rst["mesh_nodes"])
+    assert int(st["top_nodes"]) == int(rst["top_nodes"])
+
+
+@pytest.mark.parametrize("name", NAMES)
+def test_closest_hit_secondary_like_rays(name, contexts, worlds, flats):
+    """Seeded incoherent rays from inside the scene with clipped ranges (what bounces look like)."""
+    rng = np.random.default_rng(11)
+    n = 20000
+    o = rng.uniform(-3, 3, (n, 3)).astype(np.float32)
+    o[:, 1] = rng.uniform(0.05, 3.0, n).astype(np.float32)
+    d = rng.normal(0, 1, (n, 3)).astype(np.float32)
+    d = (d / np.sqrt((d * d).sum(1, keepdims=True, dtype=np.float32))).astype(np.float32)
+    nf = np.zeros((n, 2), np.float32)
+    nf[:, 1] = 3.0e38
+    nf[::4, 1] = rng.uniform(0.5, 5.0, n)[::4].astype(np.float32)
+    nf[1::7, 0] = 0.7
+    hits = contexts[name].trace_closest(o, d, nf)
+    ref = O.trace_closest(O.Scene(flats[name]), o, d, nf, order=O.ORDER_CUDA, minmax=O.MINMAX_FMINF)
+    assert np.array_equal(hits.view(np.uint8), ref.view(np.uint8))
+    assert (ref["instance"] != capi.NO_INDEX).mean() > 0.05
+
+
+def test_closest_hit_axis_aligned_and_degenerate_rays(contexts, flats):
+    """Zero direction components (0/0 and x/0 in the slab test) and rays starting on box planes: same NaN/inf
+    handling as the CUDA reference (fminf/fmaxf)."""
+    o = np.array([[0, 1, -4.4], [0, 1, 0], [-1, 0, -1], [0.3, 2.5, 0.1], [0, 1, 0], [1, 1, 1]], np.float32)
+    d = np.array([[0, 0, 1], [0, -1, 0], [1, 0, 0], [0, -1, 0], [0, 0, -1], [-1, 0, 0]], np.float32)
+    nf = np.tile(np.array([0.0, 1.0e30], np.float32), (o.shape[0], 1))
+    hits = contexts["cornell"].trace_closest(o, d, nf)
+    ref = O.trace_closest(O.Scene(flats["cornell"]), o, d, nf, order=O.ORDER_CUDA, minmax=O.MINMAX_FMINF)
+    assert np.array_equal(hits.view(np.uint8), ref.view(np.uint8))
+
+
+def test_closest_hit_empty_inputs(contexts):
+    z3, z2 = np.zeros((0, 3), np.float32), np.zeros((0, 2), np.float32)
+    assert contexts["cornell"].trace_closest(z3, z3, z2).shape == (0,)
+    w = World()
+    w.create_camera(resolution=(5, 3))
+    with capi.Context(0) as c:
+        c.set_scene(w.flatten())
+        c.set_camera(w.camera_struct())
+        o, d, nf = c.generate_camera_rays()
+        hits = c.trace_closest(o, d, nf)
+        assert (hits["instance"] == capi.NO_INDEX).all() and np.array_equal(hits["t"], nf[:, 1])
+
+
+def test_instance_without_mesh_and_default_material(flats):
+    w = scenes.cornell(resolution=(32, 32))
+    w.create_instance("ghost", None, [w.materials[0]], position=(0, 1, 0))
+    flat = w.flatten()
+    with capi.Context(0) as c:
+        c.set_scene(flat)
+        c.set_camera(w.camera_struct())
+        o, d, nf = c.generate_camera_rays()
+        hits = c.trace_closest(o, d, nf)
+        ref = O.trace_closest(O.Scene(flat), o, d, nf)
+        assert np.array_equal(hits.view(np.uint8), ref.view(np.uint8))
+
+
+# ------------------------------------------------------------------ full BASELINE sizes
+def test_full_size_id_parity_1m_triangles():
+    """Config 3: 1,001,112 triangles, the 2,073,600 pixel-centre rays of 1920x1080: every record byte-equal."""
+    w = scenes.heightfield_scene()
+    flat = w.flatten()
+    assert flat["triangles"].shape[0] >= 1_000_000
+    cam = w.camera_struct()
+    with capi.Context(0) as c:
+        c.set_scene(flat)
+        c.set_camera(cam)
+        o, d, nf = c.generate_camera_rays()
+        ro, rd, rnf = O.camera_rays(cam)
+        assert np.array_equal(o, ro) and np.array_equal(d, rd) and np.array_equal(nf, rnf)
+        hits = c.trace_closest(o, d, nf)
+    ref = O.trace_closest(O.Scene(flat), o, d, nf, order=O.ORDER_CUDA, minmax=O.MINMAX_FMINF)
+    assert hits.shape[0] == 1920 * 1080
+    assert np.array_equal(hits.view(np.uint8), ref.view(np.uint8))
+    cpu = O.trace_closest(O.Scene(flat), o, d, nf, order=O.ORDER_CPU, minmax=O.MINMAX_SELECT)
+    diff = np.flatnonzero(~_ids_equal(hits, cpu))
+    assert np.array_equal(hits["t"][diff].view(np.uint32), cpu["t"][diff].view(np.uint32))  # exact-t ties only
+    assert diff.size < 50, "ties: %d" % diff.size
+
+
+def test_full_size_id_parity_instancing_10m():
+    """Config 4: 100 instances x 100,352 triangles (10.0M effective), 1920x1080 primary rays."""
+    w = scenes.instancing_scene()
+    flat = w.flatten()
+    assert flat["instances"].shape[0] * flat["triangles"].shape[0] >= 10_000_000
+    with capi.Context(0) as c:
+        c.set_scene(flat)
+        c.set_camera(w.camera_struct())
+        o, d, nf = c.generate_camera_rays()
+        hits = c.trace_closest(o, d, nf)
+    ref = O.trace_closest(O.Scene(flat), o, d, nf, order=O.ORDER_CUDA, minmax=O.MINMAX_FMINF)
+    assert np.array_equal(hits.view(np.uint8), ref.view(np.uint8))
+    assert (hits["instance"] != capi.NO_INDEX).mean() > 0.3
+
+
+# ------------------------------------------------------------------ any hit
+@pytest.mark.parametrize("name", NAMES)
+def test_any_hit_vs_reference_cpu_engine(name, contexts, golden):
+    g = golden[name]
+    so, sd, snf = shadow_rays(g["ray_origins"], g["ray_directions"], g["hits"])
+    c = contexts[name]
+    c.set_config(flags=capi.FLAG_CPU_SEMANTICS)
+    masks = c.trace_any(so, sd, snf)
+    c.set_config()
+    assert np.array_equal(masks, g["masks"])
+
+
+def test_any_hit_coloured_transparency():
+    """CUDA-engine semantics (cuda_instance.cuh:105-112): every crossed triangle multiplies the mask by the
+    material's opacity colour (rgb, 1 - alpha)."""
+    w = World()
+    red = w.create_material("red glass", color=(255, 0, 0, 64))     # opacity colour (1, 0, 0, 1 - 64/255)
+    grey = w.create_material("grey glass", color=(128, 128, 128, 0))
+    for i, (y, m) in enumerate(((1.0, red), (2.0, grey))):
+        v, t, uv = scenes.quad_mesh((-1, y, -1), (2, 0, 0), (0, 0, 2))
+        w.create_instance("q%d" % i, w.create_mesh("q%d" % i, v, t, texcrds=uv, tri_texcrds=t), [m])
+    w.create_camera(resolution=(4, 4))
+    o = np.array([[0.1, 0, 0.2], [0.1, 1.5, 0.2], [5, 0, 5]], np.float32)
+    d = np.tile(np.array([0, 1, 0], np.float32), (3, 1))
+    nf = np.tile(np.array([0, 1e30], np.float32), (3, 1))
+    with capi.Context(0) as c:
+        c.set_scene(w.flatten())
+        masks = c.trace_any(o, d, nf)
+    a_red, g = np.float32(1) - np.float32(64) / np.float32(255), np.float32(128) / np.float32(255)
+    exp = np.array([[g, 0, 0, a_red], [g, g, g, 1], [1, 1, 1, 1]], np.float32)
+    assert np.allclose(masks, exp, rtol=1e-6, atol=0)
+
+
+# ------------------------------------------------------------------ estimator properties
+def test_sample_counting_and_ray_count():
+    """alpha counts completed paths (cuda_render_kernel.cu:45,104); with max_depth 1 every segment completes one;
+    ray count = passes * W * H (cuda_render_kernel.cu:122-129). Ragged resolution (not a multiple of the 8x4 tiles)."""
+    w = scenes.cornell(resolution=(37, 23))
+    with capi.Context(0) as c:
+        c.set_scene(w.flatten())
+        c.set_camera(w.camera_struct())
+        c.set_config(max_depth=1, seed=3)
+        c.reset()
+        c.render(5)
+        acc = c.read_accum()
+        _, _, rays = c.resolve()
+        assert acc.shape == (23, 37, 4) and (acc[..., 3] == 5.0).all() and rays == 5 * 37 * 23
+        c.set_config(max_depth=6, seed=3)
+        c.reset()
+        assert (c.read_accum() == 0).all()
+        c.render(40)
+        acc = c.read_accum()
+        assert acc[..., 3].min() >= 40 // 6 and acc[..., 3].max() <= 40
+        st = c.render_stats()
+        assert int(st["passes"]) == 40 and int(st["ray_count"]) == 40 * 37 * 23
+
+
+def test_sky_only_scene_is_analytic():
+    """No instances: every segment misses and returns throughput * sky colour * emission (cuda_render_kernel.cu:179-193)."""
+    w = World()
+    w.world_material.color = (128, 64, 255, 255)
+    w.world_material.emission = 2.5
+    w.create_camera(resolution=(16, 8))
+    with capi.Context(0) as c:
+        c.set_scene(w.flatten())
+        c.set_camera(w.camera_struct())
+        c.set_config(max_depth=4)
+        c.reset()
+        c.render(7)
+        acc = c.read_accum()
+    col = np.array([128, 64, 255], np.float32) / np.float32(255) * np.float32(2.5)
+    assert np.allclose(acc[..., :3], 7 * col, rtol=1e-6) and (acc[..., 3] == 7).all()
+
+
+def test_determinism_and_seed(flats, worlds):
+    """No lights -> no atomics: same seed gives a bit-identical accumulator, another seed a different one."""
+    def run(seed):
+        with capi.Context(0) as c:
+            c.set_scene(flats["cornell"])
+            c.set_camera(worlds["cornell"].camera_struct())
+            c.set_config(max_depth=8, seed=seed)
+            c.reset()
+            c.render(24)
+            return c.read_accum()
+    a, b, d = run(5), run(5), run(6)
+    assert np.array_equal(a, b) and not np.array_equal(a, d)
+
+
+def test_tonemap_bit_exact_and_depth(contexts, worlds, golden):
+    c, w = contexts["materials"], worlds["materials"]
+    c.set_config(max_depth=8, seed=9)
+    c.reset()
+    c.render(16)
+    acc = c.read_accum()
+    rgba, depth, _ = c.resolve(want_depth=True)
+    cam = w.camera_struct()[0]
+    assert np.array_equal(rgba, O.tonemap(acc, float(cam["aperture"]), float(cam["exposure_time"])))
+    # first-pass depth = closest-hit distance of the pixel-centre ray (cpu_engine_kernel.cpp:33)
+    assert np.array_equal(depth.reshape(-1), golden["materials"]["depth"].reshape(-1))
+
+
+def test_peer_resolve_sums_accumulators(flats, worlds):
+    """Two contexts = two sample streams (seeds differ); the fused peer resolve tone-maps the SUM bit-exactly."""
+    cam = worlds["materials"].camera_struct()
+    ctxs = []
+    for seed in (1, 2):
+        c = capi.Context(0)
+        c.set_scene(flats["materials"])
+        c.set_camera(cam)
+        c.set_config(max_depth=6, seed=seed)
+        c.reset()
+        c.render(12)
+        ctxs.append(c)
+    a0, a1 = ctxs[0].read_accum(), ctxs[1].read_accum()
+    assert not np.array_equal(a0, a1)
+    rgba, _, rays = ctxs[0].resolve_peers([ctxs[1]])
+    assert rays == 2 * 12 * cam[0]["width"] * cam[0]["height"]
+    assert np.array_equal(rgba, O.tonemap(a0 + a1, float(cam[0]["aperture"]), float(cam[0]["exposure_time"])))
+    # and the explicit add path used after an NCCL reduce
+    ptr, nbytes = ctxs[1].accum_device_ptr()
+    ctxs[0].accum_add_device(ptr, nbytes // 16)
+    assert np.array_equal(ctxs[0].read_accum(), a0 + a1)
+    for c in ctxs:
+        c.close()
+
+
+def test_raycast_pick(contexts, worlds, golden):
+    c = contexts["cornell"]
+    c.set_config(max_depth=4)
+    c.reset()
+    c.render(1)
+    inst, slot = c.raycast()
+    cam = worlds["cornell"].camera_struct()[0]
+    px = int(cam["raycast_pixel"][1]) * int(cam["width"]) + int(cam["raycast_pixel"][0])
+    assert inst == golden["cornell"]["hits"]["instance"][px] and slot == 0
+
+
+# ------------------------------------------------------------------ converged image vs the reference CPU engine
+def _radiance(acc):
+    return acc[..., :3] / np.maximum(acc[..., 3:4], 1.0)
+
+
+def _rel_rmse(a, b):
+    return float(np.sqrt(np.mean((a - b) ** 2)) / np.mean(b))
+
+
+def _block_mean(img, h, w, k):
+    img = img.reshape(h, w, 3)[: h // k * k, : w // k * k]
+    return img.reshape(h // k, k, w // k, k, 3).mean(axis=(1, 3))
+
+
+@pytest.mark.parametrize("name", list(RENDER_SETTINGS))
+def test_image_vs_reference_cpu_engine(name, contexts, golden, worlds):
+    """Equal passes, CPU semantics. Two independent reference renders A, B give the Monte-Carlo noise floor
+    sigma_MC = relRMSE(A, B); tolerance (stated): relRMSE(GPU, A) <= 1.25 * sigma_MC + 0.01, and -- noise averaged
+    out over 8x8 pixel blocks -- relRMSE of block means <= 1.25 * block sigma_MC + 0.02, and the image mean within 3 %."""
+    g = golden[name]
+    passes, depth = RENDER_SETTINGS[name]
+    c = contexts[name]
+    c.set_config(spot_light_samples=1, direct_light_samples=1, max_depth=depth, flags=capi.FLAG_CPU_SEMANTICS, seed=2024)
+    c.reset()
+    c.render(passes)
+    acc = c.read_accum()
+    c.set_config()
+    cam = worlds[name].camera_struct()[0]
+    h, w = int(cam["height"]), int(cam["width"])
+    A, B, G = _radiance(g["accum_a"].reshape(h, w, 4)), _radiance(g["accum_b"].reshape(h, w, 4)), _radiance(acc)
+    spp_ref, spp_gpu = g["accum_a"][:, 3].mean(), acc[..., 3].mean()
+    assert abs(spp_gpu - spp_ref) / spp_ref < 0.02, (spp_gpu, spp_ref)
+    sigma = _rel_rmse(A, B)
+    assert _rel_rmse(G, A) <= 1.25 * sigma + 0.01, (_rel_rmse(G, A), sigma)
+    bs = _rel_rmse(_block_mean(A, h, w, 8), _block_mean(B, h, w, 8))
+    bg = _rel_rmse(_block_mean(G, h, w, 8), _block_mean(0.5 * (A + B), h, w, 8))
+    assert bg <= 1.25 * bs + 0.02, (bg, bs)
+    assert abs(G.mean() - 0.5 * (A.mean() + B.mean())) / A.mean() < 0.03, (G.mean(), A.mean(), B.mean())
