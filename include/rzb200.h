@@ -237,9 +237,10 @@ void rzb_destroy(rzb_ctx* ctx);
 /* text of the last error on this context (ctx may be NULL for creation errors) */
 const char* rzb_last_error(const rzb_ctx* ctx);
 /* Run every kernel and copy of this context on the caller's CUDA stream (a cudaStream_t, e.g. the host
- * framework's current stream) instead of the context's own; NULL restores the private stream. Replaces the
- * reference's fixed m_render_stream / m_mirror_stream pair (cuda_engine_core.cu:245-249). */
-int rzb_set_stream(rzb_ctx* ctx, void* cuda_stream);
+ * framework's current stream; NULL is the legacy default stream, as everywhere in CUDA) when use_caller_stream
+ * is non-zero; zero restores the context's private non-blocking stream. Replaces the reference's fixed
+ * m_render_stream / m_mirror_stream pair (cuda_engine_core.cu:245-249). */
+int rzb_set_stream(rzb_ctx* ctx, void* cuda_stream, int use_caller_stream);
 
 /* ---- world mirror: replaces World::reconstructAll (cuda_world.cu) ---- */
 int rzb_set_scene(rzb_ctx* ctx, const rzb_scene* scene);

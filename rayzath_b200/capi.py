@@ -94,7 +94,7 @@ SYMBOLS = {
     "rzb_create": (C.c_int, [C.c_int, C.POINTER(_P)]),
     "rzb_destroy": (None, [_P]),
     "rzb_last_error": (C.c_char_p, [_P]),
-    "rzb_set_stream": (C.c_int, [_P, _P]),
+    "rzb_set_stream": (C.c_int, [_P, _P, C.c_int]),
     "rzb_set_scene": (C.c_int, [_P, C.POINTER(SceneStruct)]),
     "rzb_set_camera": (C.c_int, [_P, _P]),
     "rzb_set_config": (C.c_int, [_P, _P]),
@@ -253,8 +253,12 @@ class Context:
             raise RzbError(rc, (self._l.rzb_last_error(self._h) or b"").decode())
 
     def set_stream(self, cuda_stream: Optional[int]):
-        """Run on the caller's CUDA stream (e.g. torch.cuda.current_stream().cuda_stream); None = private stream."""
-        self._check(self._l.rzb_set_stream(self._h, cuda_stream))
+        """Run on the caller's CUDA stream (e.g. torch.cuda.current_stream().cuda_stream, 0 = legacy default stream);
+        None = back to the context's private stream."""
+        if cuda_stream is None:
+            self._check(self._l.rzb_set_stream(self._h, None, 0))
+        else:
+            self._check(self._l.rzb_set_stream(self._h, cuda_stream if cuda_stream else None, 1))
 
     # -- world mirror
     def set_scene(self, scene: Dict[str, np.ndarray]):

@@ -54,7 +54,12 @@ struct rzb_ctx
 	std::vector<std::pair<std::string, void*>> ipc_open; // opened peer accumulators (handle bytes -> mapped pointer)
 	std::string error;
 
-	std::vector<void*> scene_allocs;
+	// scene mirror: grow-only device buffers, reused across rzb_set_scene calls (no cudaMalloc/cudaFree when the
+	// world keeps its size, which is the per-frame case of a host that re-sends a dirty world)
+	enum { kBufNodes, kBufTriRaw, kBufHot, kBufCold, kBufMeshNodesRaw, kBufMeshTable, kBufInstances, kBufInstHost,
+		kBufTriHost, kBufInstMats, kBufMaterials, kBufMaps, kBufDirect, kBufSpot, kBufCount };
+	DeviceBuffer scene_buf[kBufCount];
+	std::vector<DeviceBuffer> map_pixel_buf;
 	DScene sc{};
 	bool has_scene = false, has_camera = false, frame_ready = false;
 	rzb_camera cam{};
@@ -113,19 +118,6 @@ namespace
 	{
 		for (void* p : v) cudaFree(p);
 		v.clear();
-	}
-
-	template <typename T>
-	int upload(rzb_ctx* ctx, std::vector<void*>& owner, const T* host, size_t count, const T** out)
-	{
-		*out = nullptr;
-		void* d = nullptr;
-		const size_t bytes = std::max<size_t>(count, 1) * sizeof(T);
-		RZB_CUDA(ctx, cudaMalloc(&d, bytes));
-		owner.push_back(d);
-		if (count) RZB_CUDA(ctx, cudaMemcpyAsync(d, host, count * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
-		*out = static_cast<const T*>(d);
-		return RZB_OK;
 	}
 
 	int ensureScratch(rzb_ctx* ctx, int slot, size_t bytes)
@@ -262,7 +254,8 @@ extern "C" void rzb_destroy(rzb_ctx* ctx)
 	if (!ctx) return;
 	DeviceGuard guard(ctx->device);
 	cudaStreamSynchronize(ctx->stream);
-	freeAll(ctx->scene_allocs);
+	for (auto& b : ctx->scene_buf) if (b.ptr) cudaFree(b.ptr);
+	for (auto& b : ctx->map_pixel_buf) if (b.ptr) cudaFree(b.ptr);
 	freeAll(ctx->frame_allocs);
 	for (void* p : ctx->d_shadow) if (p) cudaFree(p);
 	for (auto& b : ctx->scratch) if (b.ptr) cudaFree(b.ptr);
@@ -276,13 +269,39 @@ extern "C" void rzb_destroy(rzb_ctx* ctx)
 	delete ctx;
 }
 
-extern "C" int rzb_set_stream(rzb_ctx* ctx, void* cuda_stream)
+extern "C" int rzb_set_stream(rzb_ctx* ctx, void* cuda_stream, int use_caller_stream)
 {
 	if (!ctx) return RZB_ERR_INVALID;
 	DeviceGuard guard(ctx->device);
 	RZB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-	ctx->stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : ctx->own_stream;
+	ctx->stream = use_caller_stream ? static_cast<cudaStream_t>(cuda_stream) : ctx->own_stream;
 	return RZB_OK;
+}
+
+namespace
+{
+	// grow-only buffer: reallocates only when the requested size exceeds the capacity
+	int ensureBuf(rzb_ctx* ctx, DeviceBuffer& b, size_t bytes)
+	{
+		bytes = std::max<size_t>(bytes, 16);
+		if (b.bytes >= bytes) return RZB_OK;
+		if (b.ptr) cudaFree(b.ptr);
+		b.ptr = nullptr;
+		b.bytes = 0;
+		const size_t cap = bytes + bytes / 8; // a little slack so that small growth does not reallocate
+		RZB_CUDA(ctx, cudaMalloc(&b.ptr, cap));
+		b.bytes = cap;
+		return RZB_OK;
+	}
+	template <typename T>
+	int uploadTo(rzb_ctx* ctx, DeviceBuffer& b, const T* host, size_t count, const T** out)
+	{
+		const int rc = ensureBuf(ctx, b, count * sizeof(T));
+		if (rc) return rc;
+		if (count) RZB_CUDA(ctx, cudaMemcpyAsync(b.ptr, host, count * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
+		if (out) *out = static_cast<const T*>(b.ptr);
+		return RZB_OK;
+	}
 }
 
 extern "C" int rzb_set_scene(rzb_ctx* ctx, const rzb_scene* s)
@@ -290,18 +309,10 @@ extern "C" int rzb_set_scene(rzb_ctx* ctx, const rzb_scene* s)
 	if (!ctx || !s) return fail(ctx, RZB_ERR_INVALID, "rzb_set_scene: NULL argument");
 	DeviceGuard guard(ctx->device);
 	RZB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-	freeAll(ctx->scene_allocs);
 	ctx->has_scene = false;
 	ctx->frame_ready = false;
 
-	// ---- validate
-	for (uint32_t m = 0; m < s->mesh_count; ++m)
-	{
-		const rzb_mesh& mesh = s->meshes[m];
-		if (uint64_t(mesh.node_offset) + mesh.node_count > s->mesh_node_count ||
-			uint64_t(mesh.tri_offset) + mesh.tri_count > s->triangle_count)
-			return fail(ctx, RZB_ERR_INVALID, "rzb_set_scene: mesh range outside node/triangle arrays");
-	}
+	// ---- validate (host reads of the caller's arrays; everything heavy happens on the device below)
 	if (s->triangle_count > kHitTriMask - 1u) return fail(ctx, RZB_ERR_INVALID, "rzb_set_scene: too many triangles");
 	if (s->default_material >= s->material_count) return fail(ctx, RZB_ERR_INVALID, "rzb_set_scene: default material out of range");
 	for (uint32_t i = 0; i < s->instance_material_count; ++i)
@@ -310,44 +321,52 @@ extern "C" int rzb_set_scene(rzb_ctx* ctx, const rzb_scene* s)
 	if (s->instance_count != 0 && s->instance_node_count == 0)
 		return fail(ctx, RZB_ERR_INVALID, "rzb_set_scene: instances without an instance tree");
 
-	// ---- nodes: every tree is placed so that its root sits at an odd global index; sibling pairs (odd local
-	// index, next even) then start at even global indices = 64-byte aligned
+	// ---- node placement: every tree is placed so that its root sits at an odd global index; sibling pairs (odd
+	// local index, next even) then start at even global indices = 64-byte aligned
+	std::vector<MeshEntry> table; // non-empty meshes only, ascending node_offset
+	table.reserve(s->mesh_count);
 	std::vector<uint32_t> mesh_base(s->mesh_count, kNoIndex);
 	size_t cursor = 1;
+	uint64_t expect_node = 0;
 	for (uint32_t m = 0; m < s->mesh_count; ++m)
 	{
-		if (s->meshes[m].node_count == 0) continue;
-		if ((cursor & 1u) == 0) ++cursor;
-		mesh_base[m] = uint32_t(cursor);
-		cursor += s->meshes[m].node_count;
+		const rzb_mesh& mesh = s->meshes[m];
+		if (uint64_t(mesh.node_offset) + mesh.node_count > s->mesh_node_count ||
+			uint64_t(mesh.tri_offset) + mesh.tri_count > s->triangle_count)
+			return fail(ctx, RZB_ERR_INVALID, "rzb_set_scene: mesh range outside node/triangle arrays");
+		if (mesh.node_count != 0 && mesh.node_offset < expect_node)
+			return fail(ctx, RZB_ERR_INVALID, "rzb_set_scene: mesh node ranges must be disjoint and ascending");
+		if (mesh.node_count != 0)
+		{
+			expect_node = uint64_t(mesh.node_offset) + mesh.node_count;
+			if ((cursor & 1u) == 0) ++cursor;
+			mesh_base[m] = uint32_t(cursor);
+			cursor += mesh.node_count;
+			table.push_back(MeshEntry{mesh.node_offset, mesh.node_count, mesh.tri_offset, mesh_base[m]});
+		}
 	}
 	if ((cursor & 1u) == 0) ++cursor;
 	const uint32_t top_base = uint32_t(cursor);
 	cursor += s->instance_node_count;
 	if (cursor >= (1u << 30)) return fail(ctx, RZB_ERR_INVALID, "rzb_set_scene: too many nodes");
-	std::vector<rzb_node> nodes(cursor + 1);
-	std::memset(nodes.data(), 0, nodes.size() * sizeof(rzb_node));
+	const size_t total_nodes = cursor + 1;
 	for (uint32_t m = 0; m < s->mesh_count; ++m)
 	{
 		const rzb_mesh& mesh = s->meshes[m];
 		for (uint32_t i = 0; i < mesh.node_count; ++i)
 		{
-			rzb_node n = s->mesh_nodes[mesh.node_offset + i];
+			const rzb_node& n = s->mesh_nodes[mesh.node_offset + i];
 			const uint32_t count = n.type_count & 0x3FFFFFFFu;
 			if (count != 0)
 			{
 				if (uint64_t(n.begin) + count > mesh.tri_count) return fail(ctx, RZB_ERR_INVALID, "rzb_set_scene: leaf outside mesh triangles");
-				n.begin += mesh.tri_offset;
 			}
-			else
-			{
-				if (uint64_t(n.begin) + 1 >= mesh.node_count || (n.begin & 1u) == 0)
-					return fail(ctx, RZB_ERR_INVALID, "rzb_set_scene: bad child index in mesh tree");
-				n.begin += mesh_base[m];
-			}
-			nodes[mesh_base[m] + i] = n;
+			else if (uint64_t(n.begin) + 1 >= mesh.node_count || (n.begin & 1u) == 0)
+				return fail(ctx, RZB_ERR_INVALID, "rzb_set_scene: bad child index in mesh tree");
 		}
 	}
+	// instance tree (small): fixed up on the host
+	std::vector<rzb_node> top_nodes(s->instance_node_count);
 	for (uint32_t i = 0; i < s->instance_node_count; ++i)
 	{
 		rzb_node n = s->instance_nodes[i];
@@ -362,28 +381,7 @@ extern "C" int rzb_set_scene(rzb_ctx* ctx, const rzb_scene* s)
 				return fail(ctx, RZB_ERR_INVALID, "rzb_set_scene: bad child index in instance tree");
 			n.begin += top_base;
 		}
-		nodes[top_base + i] = n;
-	}
-
-	// ---- triangles: hot (intersection) and cold (shading) records
-	std::vector<float4> hot(size_t(s->triangle_count) * 3), cold(size_t(s->triangle_count) * 5);
-	for (uint32_t i = 0; i < s->triangle_count; ++i)
-	{
-		const rzb_triangle& t = s->triangles[i];
-		// edge vectors exactly as Triangle::closestIntersection forms them first (single fp32 subtractions)
-		volatile float e1x = t.v[1][0] - t.v[0][0], e1y = t.v[1][1] - t.v[0][1], e1z = t.v[1][2] - t.v[0][2];
-		volatile float e2x = t.v[2][0] - t.v[0][0], e2y = t.v[2][1] - t.v[0][1], e2z = t.v[2][2] - t.v[0][2];
-		uint32_t slot = t.material_slot & 0x3Fu;
-		float slot_f;
-		std::memcpy(&slot_f, &slot, 4);
-		hot[3 * size_t(i)] = make_float4(t.v[0][0], t.v[0][1], t.v[0][2], e1x);
-		hot[3 * size_t(i) + 1] = make_float4(e1y, e1z, e2x, e2y);
-		hot[3 * size_t(i) + 2] = make_float4(e2z, slot_f, 0.0f, 0.0f);
-		cold[5 * size_t(i)] = make_float4(t.n[0][0], t.n[0][1], t.n[0][2], t.uv[0][0]);
-		cold[5 * size_t(i) + 1] = make_float4(t.n[1][0], t.n[1][1], t.n[1][2], t.uv[0][1]);
-		cold[5 * size_t(i) + 2] = make_float4(t.n[2][0], t.n[2][1], t.n[2][2], t.uv[1][0]);
-		cold[5 * size_t(i) + 3] = make_float4(t.face_normal[0], t.face_normal[1], t.face_normal[2], t.uv[1][1]);
-		cold[5 * size_t(i) + 4] = make_float4(t.uv[2][0], t.uv[2][1], 0.0f, 0.0f);
+		top_nodes[i] = n;
 	}
 
 	// ---- instances
@@ -415,7 +413,7 @@ extern "C" int rzb_set_scene(rzb_ctx* ctx, const rzb_scene* s)
 		inst_host[i] = h.host_index;
 	}
 
-	// ---- materials (+ world material appended), maps, lights
+	// ---- materials (+ world material appended), maps
 	std::vector<rzb_material> mats(s->materials, s->materials + s->material_count);
 	mats.push_back(s->world_material);
 	for (const rzb_material& m : mats)
@@ -424,7 +422,9 @@ extern "C" int rzb_set_scene(rzb_ctx* ctx, const rzb_scene* s)
 		for (uint32_t id : ids)
 			if (id != RZB_NO_INDEX && id >= s->map_count) return fail(ctx, RZB_ERR_INVALID, "rzb_set_scene: map id out of range");
 	}
+	if (ctx->map_pixel_buf.size() < s->map_count) ctx->map_pixel_buf.resize(s->map_count);
 	std::vector<DMap> maps(s->map_count);
+	int rc;
 	for (uint32_t i = 0; i < s->map_count; ++i)
 	{
 		const rzb_map& m = s->maps[i];
@@ -432,8 +432,7 @@ extern "C" int rzb_set_scene(rzb_ctx* ctx, const rzb_scene* s)
 			return fail(ctx, RZB_ERR_INVALID, "rzb_set_scene: bad map");
 		const size_t texel = m.format == RZB_MAP_R8 ? 1 : 4;
 		const uint8_t* d_pixels = nullptr;
-		int rc = upload(ctx, ctx->scene_allocs, static_cast<const uint8_t*>(m.pixels), size_t(m.width) * m.height * texel, &d_pixels);
-		if (rc) return rc;
+		if ((rc = uploadTo(ctx, ctx->map_pixel_buf[i], static_cast<const uint8_t*>(m.pixels), size_t(m.width) * m.height * texel, &d_pixels))) return rc;
 		DMap d{};
 		d.pixels = d_pixels;
 		d.width = m.width; d.height = m.height;
@@ -444,29 +443,56 @@ extern "C" int rzb_set_scene(rzb_ctx* ctx, const rzb_scene* s)
 		maps[i] = d;
 	}
 
+	// ---- uploads straight from the caller's arrays, then device-side repacking into the traversal layout
 	DScene sc{};
-	int rc;
-	const float4* d_nodes = nullptr;
-	if ((rc = upload(ctx, ctx->scene_allocs, reinterpret_cast<const float4*>(nodes.data()), nodes.size() * 2, &d_nodes))) return rc;
-	sc.nodes = d_nodes;
-	if ((rc = upload(ctx, ctx->scene_allocs, hot.data(), hot.size(), &sc.tri_hot))) return rc;
-	if ((rc = upload(ctx, ctx->scene_allocs, cold.data(), cold.size(), &sc.tri_cold))) return rc;
-	if ((rc = upload(ctx, ctx->scene_allocs, insts.data(), insts.size(), &sc.instances))) return rc;
-	if ((rc = upload(ctx, ctx->scene_allocs, inst_host.data(), inst_host.size(), &sc.inst_host_index))) return rc;
-	std::vector<uint32_t> identity;
-	const uint32_t* tri_host = s->tri_host_index;
-	if (!tri_host)
+	DeviceBuffer* B = ctx->scene_buf;
+	const rzb_triangle* d_tri_raw = nullptr;
+	const rzb_node* d_mesh_nodes_raw = nullptr;
+	const MeshEntry* d_table = nullptr;
+	if ((rc = uploadTo(ctx, B[rzb_ctx::kBufTriRaw], s->triangles, s->triangle_count, &d_tri_raw))) return rc;
+	if ((rc = uploadTo(ctx, B[rzb_ctx::kBufMeshNodesRaw], s->mesh_nodes, s->mesh_node_count, &d_mesh_nodes_raw))) return rc;
+	if ((rc = uploadTo(ctx, B[rzb_ctx::kBufMeshTable], table.data(), table.size(), &d_table))) return rc;
+	if ((rc = ensureBuf(ctx, B[rzb_ctx::kBufNodes], total_nodes * 32))) return rc;
+	if ((rc = ensureBuf(ctx, B[rzb_ctx::kBufHot], size_t(s->triangle_count) * 48))) return rc;
+	if ((rc = ensureBuf(ctx, B[rzb_ctx::kBufCold], size_t(s->triangle_count) * 80))) return rc;
+	float4* d_nodes = static_cast<float4*>(B[rzb_ctx::kBufNodes].ptr);
+	RZB_CUDA(ctx, cudaMemsetAsync(d_nodes, 0, total_nodes * 32, ctx->stream));
+	if (s->instance_node_count)
+		RZB_CUDA(ctx, cudaMemcpyAsync(d_nodes + 2 * size_t(top_base), top_nodes.data(), top_nodes.size() * 32, cudaMemcpyHostToDevice, ctx->stream));
+	if (s->mesh_node_count)
 	{
-		identity.resize(s->triangle_count);
-		for (uint32_t i = 0; i < s->triangle_count; ++i) identity[i] = i;
-		tri_host = identity.data();
+		k_pack_mesh_nodes<<<(s->mesh_node_count + 255) / 256, 256, 0, ctx->stream>>>(d_mesh_nodes_raw, s->mesh_node_count,
+			d_table, uint32_t(table.size()), d_nodes);
+		ctx->launches += 1;
 	}
-	if ((rc = upload(ctx, ctx->scene_allocs, tri_host, s->triangle_count, &sc.tri_host_index))) return rc;
-	if ((rc = upload(ctx, ctx->scene_allocs, s->instance_materials, s->instance_material_count, &sc.inst_materials))) return rc;
-	if ((rc = upload(ctx, ctx->scene_allocs, mats.data(), mats.size(), &sc.materials))) return rc;
-	if ((rc = upload(ctx, ctx->scene_allocs, maps.data(), maps.size(), &sc.maps))) return rc;
-	if ((rc = upload(ctx, ctx->scene_allocs, s->direct_lights, s->direct_light_count, &sc.direct_lights))) return rc;
-	if ((rc = upload(ctx, ctx->scene_allocs, s->spot_lights, s->spot_light_count, &sc.spot_lights))) return rc;
+	if (s->triangle_count)
+	{
+		k_pack_triangles<<<(s->triangle_count + 127) / 128, 128, 0, ctx->stream>>>(d_tri_raw, s->triangle_count,
+			static_cast<float4*>(B[rzb_ctx::kBufHot].ptr), static_cast<float4*>(B[rzb_ctx::kBufCold].ptr));
+		ctx->launches += 1;
+	}
+	RZB_CUDA(ctx, cudaGetLastError());
+	sc.nodes = d_nodes;
+	sc.tri_hot = static_cast<const float4*>(B[rzb_ctx::kBufHot].ptr);
+	sc.tri_cold = static_cast<const float4*>(B[rzb_ctx::kBufCold].ptr);
+	if ((rc = uploadTo(ctx, B[rzb_ctx::kBufInstances], insts.data(), insts.size(), &sc.instances))) return rc;
+	if ((rc = uploadTo(ctx, B[rzb_ctx::kBufInstHost], inst_host.data(), inst_host.size(), &sc.inst_host_index))) return rc;
+	if (s->tri_host_index)
+	{
+		if ((rc = uploadTo(ctx, B[rzb_ctx::kBufTriHost], s->tri_host_index, s->triangle_count, &sc.tri_host_index))) return rc;
+	}
+	else
+	{
+		if ((rc = ensureBuf(ctx, B[rzb_ctx::kBufTriHost], size_t(s->triangle_count) * 4))) return rc;
+		if (s->triangle_count)
+			k_iota<<<(s->triangle_count + 255) / 256, 256, 0, ctx->stream>>>(static_cast<uint32_t*>(B[rzb_ctx::kBufTriHost].ptr), s->triangle_count);
+		sc.tri_host_index = static_cast<const uint32_t*>(B[rzb_ctx::kBufTriHost].ptr);
+	}
+	if ((rc = uploadTo(ctx, B[rzb_ctx::kBufInstMats], s->instance_materials, s->instance_material_count, &sc.inst_materials))) return rc;
+	if ((rc = uploadTo(ctx, B[rzb_ctx::kBufMaterials], mats.data(), mats.size(), &sc.materials))) return rc;
+	if ((rc = uploadTo(ctx, B[rzb_ctx::kBufMaps], maps.data(), maps.size(), &sc.maps))) return rc;
+	if ((rc = uploadTo(ctx, B[rzb_ctx::kBufDirect], s->direct_lights, s->direct_light_count, &sc.direct_lights))) return rc;
+	if ((rc = uploadTo(ctx, B[rzb_ctx::kBufSpot], s->spot_lights, s->spot_light_count, &sc.spot_lights))) return rc;
 	sc.top_root = top_base;
 	sc.instance_count = s->instance_count;
 	sc.material_count = s->material_count;
@@ -475,7 +501,7 @@ extern "C" int rzb_set_scene(rzb_ctx* ctx, const rzb_scene* s)
 	sc.direct_light_count = s->direct_light_count;
 	sc.spot_light_count = s->spot_light_count;
 	sc.flags = ctx->cfg.flags;
-	RZB_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); // host staging vectors die at return
+	RZB_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); // host staging vectors die at return; the caller may reuse its arrays
 	ctx->sc = sc;
 	ctx->has_scene = true;
 	return RZB_OK;

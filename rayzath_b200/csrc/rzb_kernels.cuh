@@ -64,6 +64,61 @@ namespace rzb
 		return st;
 	}
 
+	// ---------------------------------------------------------------- scene repacking (rzb_set_scene)
+	struct MeshEntry
+	{
+		uint32_t node_offset, node_count, tri_offset, base; // base = global index of the mesh root, kNoIndex if empty
+	};
+	// C-ABI triangle (112 B) -> hot (intersection) + cold (shading) records. The edge vectors are formed exactly as
+	// Triangle::closestIntersection forms them first (single fp32 subtractions, cuda_render_parts.cuh:1026-1027).
+	__global__ void k_pack_triangles(const rzb_triangle* __restrict__ raw, uint32_t n, float4* __restrict__ hot,
+		float4* __restrict__ cold)
+	{
+		const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+		if (i >= n) return;
+		const float* t = reinterpret_cast<const float*>(raw + i); // v[9] n[9] face[3] uv[6] slot
+		const float v0x = t[0], v0y = t[1], v0z = t[2];
+		const float e1x = fsub(t[3], v0x), e1y = fsub(t[4], v0y), e1z = fsub(t[5], v0z);
+		const float e2x = fsub(t[6], v0x), e2y = fsub(t[7], v0y), e2z = fsub(t[8], v0z);
+		const uint32_t slot = __float_as_uint(t[27]) & 0x3Fu;
+		hot[3 * size_t(i)] = make_float4(v0x, v0y, v0z, e1x);
+		hot[3 * size_t(i) + 1] = make_float4(e1y, e1z, e2x, e2y);
+		hot[3 * size_t(i) + 2] = make_float4(e2z, __uint_as_float(slot), 0.0f, 0.0f);
+		cold[5 * size_t(i)] = make_float4(t[9], t[10], t[11], t[21]);
+		cold[5 * size_t(i) + 1] = make_float4(t[12], t[13], t[14], t[22]);
+		cold[5 * size_t(i) + 2] = make_float4(t[15], t[16], t[17], t[23]);
+		cold[5 * size_t(i) + 3] = make_float4(t[18], t[19], t[20], t[24]);
+		cold[5 * size_t(i) + 4] = make_float4(t[25], t[26], 0.0f, 0.0f);
+	}
+	// per-mesh node arrays -> one global array (children / triangle ranges rebased)
+	__global__ void k_pack_mesh_nodes(const rzb_node* __restrict__ raw, uint32_t n, const MeshEntry* __restrict__ meshes,
+		uint32_t n_meshes, float4* __restrict__ nodes)
+	{
+		const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+		if (i >= n) return;
+		// the mesh whose node range holds i (ranges ascending and disjoint: binary search on node_offset)
+		uint32_t lo = 0, hi = n_meshes;
+		while (hi - lo > 1u)
+		{
+			const uint32_t mid = (lo + hi) >> 1;
+			if (meshes[mid].node_offset <= i) lo = mid; else hi = mid;
+		}
+		if (n_meshes == 0u) return;
+		const MeshEntry m = meshes[lo];
+		if (i < m.node_offset || i >= m.node_offset + m.node_count) return; // a node no mesh owns
+		rzb_node nd = raw[i];
+		const uint32_t count = nd.type_count & 0x3FFFFFFFu;
+		nd.begin += count != 0u ? m.tri_offset : m.base;
+		const size_t g = size_t(m.base) + (i - m.node_offset);
+		nodes[2 * g] = make_float4(nd.bb_min[0], nd.bb_min[1], nd.bb_min[2], nd.bb_max[0]);
+		nodes[2 * g + 1] = make_float4(nd.bb_max[1], nd.bb_max[2], __uint_as_float(nd.begin), __uint_as_float(nd.type_count));
+	}
+	__global__ void k_iota(uint32_t* __restrict__ out, uint32_t n)
+	{
+		const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+		if (i < n) out[i] = i;
+	}
+
 	// ---------------------------------------------------------------- k_reset
 	__global__ void k_reset(DFrame f, uint32_t world_material)
 	{

@@ -1,5 +1,5 @@
 // Force-included (-include) when compiling the reference's own sources on Linux for the oracle.
-// TEST INFRASTRUCTURE ONLY. The reference is written against MSVC's <cmath>, which puts the
+// LINUX PORTABILITY LAYER for building the reference host sources in place (drop-in engine, oracle). The reference is written against MSVC's <cmath>, which puts the
 // float-suffixed C functions in namespace std (std::tanf, std::sqrtf ...; e.g.
 // cpu_engine_kernel.cpp:186,214,235-238,543,640,717,837,847,864); libstdc++ 13 does not.
 #ifndef RZ_ORACLE_COMPAT_H

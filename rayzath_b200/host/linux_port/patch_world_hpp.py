@@ -1,7 +1,7 @@
 #!/usr/bin/env python3
 """Generate a g++-compatible copy of the reference's world.hpp at BUILD time (never committed).
 
-TEST INFRASTRUCTURE ONLY (oracle build). g++ 13 rejects explicit specialisations at class scope
+LINUX PORTABILITY LAYER (used by the drop-in host build and by the oracle build). g++ 13 rejects explicit specialisations at class scope
 (/root/reference/RayZath/world.hpp:143-194, `template<> struct CommonMeshParameters<...>` inside
 `class World`); MSVC accepts them. Partial specialisations ARE legal at class scope, so the
 generated header adds a defaulted dummy parameter and turns each full specialisation into a

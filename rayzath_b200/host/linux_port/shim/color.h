@@ -1,5 +1,5 @@
 // Shim for Graphics::Color / Graphics::ColorF (un-vendored `Graphics` library, no pinned version;
-// SURVEY.md §8c). TEST INFRASTRUCTURE ONLY. Semantics follow the CUDA mirror types the reference
+// SURVEY.md §8c). LINUX PORTABILITY LAYER. Semantics follow the CUDA mirror types the reference
 // keeps in-tree (cuda_render_parts.cuh:497-683 ColorF, :685-825 ColorU): ColorF(Color) = /255.0f,
 // Blend(a,b,t) = a + (b-a)*t, arithmetic is 4-channel component-wise.
 // Unknowable from the tree ("parity unpinned"): Palette byte values other than White/Black.

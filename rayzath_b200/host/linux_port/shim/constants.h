@@ -1,5 +1,5 @@
 // Shim for the un-vendored `Math` library (Greketrotny/Math, no pinned version).
-// TEST INFRASTRUCTURE ONLY: lets the reference's own CPU engine compile on Linux for the oracle.
+// LINUX PORTABILITY LAYER: lets the reference's own host sources compile on Linux (drop-in engine build, oracle build).
 // Written from the call sites in /root/reference/RayZath (e.g. world.cpp:179, camera.hpp:130);
 // "parity unpinned" at this level: the literal used upstream is unknown, (float)pi is assumed.
 #ifndef RZ_SHIM_MATH_CONSTANTS_H

@@ -221,7 +221,9 @@ def cornell(resolution=(512, 512)) -> World:
     w.create_instance("short", cube, [blue], position=(0.4, 0.3, -0.25), rotation=(0.0, -0.35, 0.0), scale=(0.6, 0.6, 0.6))
     w.create_camera(name="cam", position=(0.0, 1.0, -4.4), rotation=(0.0, 0.0, 0.0), resolution=resolution, fov=0.75,
                     near_far=(0.01, 100.0), focal_distance=4.4, aperture=0.005, exposure_time=0.05)
-    w.world_material.color = (0, 0, 0, 255)
+    # the world material is the medium camera rays start in: fully transparent (alpha 0), no sky light
+    w.world_material.color = (255, 255, 255, 0)
+    w.world_material.emission = 0.0
     return w
 
 
@@ -259,7 +261,8 @@ def materials_scene(resolution=(1920, 1080), res=64, cpu_comparable=False) -> Wo
                         size=0.5, emission=300.0, beam_angle=0.6)
     w.create_camera(name="cam", position=(0.0, 3.0, -8.5), rotation=(-0.2, 0.0, 0.0), resolution=resolution, fov=1.15,
                     near_far=(0.01, 1000.0), focal_distance=8.5, aperture=0.01, exposure_time=0.006)
-    w.world_material.color = (150, 180, 255, 255)
+    # transparent medium (alpha 0); its colour times emission is the sky radiance (cuda_render_kernel.cu:174-186)
+    w.world_material.color = (255, 255, 255, 0)
     w.world_material.emission = 1.0
     return w
 
@@ -281,7 +284,7 @@ def heightfield_scene(resolution=(1920, 1080), nx=708, nz=707, map_size=2048, wi
     w.create_direct_light("sun", direction=(-0.5, -1.0, 0.3), color=(255, 240, 220), emission=1200.0, angular_size=0.03)
     w.create_camera(name="cam", position=(0.0, 4.5, -11.0), rotation=(-0.3, 0.0, 0.0), resolution=resolution, fov=1.0,
                     near_far=(0.01, 1000.0), focal_distance=10.0, aperture=0.05, exposure_time=0.0004)
-    w.world_material.color = (140, 170, 255, 255)
+    w.world_material.color = (255, 255, 255, 0)
     w.world_material.emission = 1.5
     return w
 
@@ -309,7 +312,7 @@ def instancing_scene(resolution=(1920, 1080), n_instances=100, nx=224, nz=224, s
     w.create_camera(name="cam", position=(0.0, 9.0, -0.62 * side * 2.3 - 6.0), rotation=(-0.5, 0.0, 0.0),
                     resolution=resolution, fov=1.0, near_far=(0.01, 1000.0), focal_distance=14.0, aperture=0.001,
                     exposure_time=0.0004)
-    w.world_material.color = (140, 170, 255, 255)
+    w.world_material.color = (255, 255, 255, 0)
     w.world_material.emission = 1.5
     return w
 

@@ -143,7 +143,7 @@ class World:
         self.cameras: List[Camera] = []
         self.direct_lights: List[DirectLight] = []
         self.spot_lights: List[SpotLight] = []
-        self.world_material = Material("world", color=(0, 0, 0, 255), ior=1.0)
+        self.world_material = Material("world", color=(255, 255, 255, 0), ior=1.0)  # world.cpp:33-38
         self.default_material = Material("default", color=(192, 192, 192, 255), ior=1.0)
 
     # -- creation (names follow World::container<T>().create / Mesh::create*)

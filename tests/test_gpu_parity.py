@@ -222,9 +222,11 @@ def test_sample_counting_and_ray_count():
 
 
 def test_sky_only_scene_is_analytic():
-    """No instances: every segment misses and returns throughput * sky colour * emission (cuda_render_kernel.cu:179-193)."""
+    """No instances: every segment misses; the throughput is first tinted by the medium (world material, alpha 0 =
+    transparent: pow(1 - alpha, t) = 1) and the miss returns throughput * sky colour * emission
+    (cuda_render_kernel.cu:174-193), i.e. colour^2 * emission per pass."""
     w = World()
-    w.world_material.color = (128, 64, 255, 255)
+    w.world_material.color = (128, 64, 255, 0)
     w.world_material.emission = 2.5
     w.create_camera(resolution=(16, 8))
     with capi.Context(0) as c:
@@ -234,8 +236,8 @@ def test_sky_only_scene_is_analytic():
         c.reset()
         c.render(7)
         acc = c.read_accum()
-    col = np.array([128, 64, 255], np.float32) / np.float32(255) * np.float32(2.5)
-    assert np.allclose(acc[..., :3], 7 * col, rtol=1e-6) and (acc[..., 3] == 7).all()
+    c01 = np.array([128, 64, 255], np.float32) / np.float32(255)
+    assert np.allclose(acc[..., :3], 7 * c01 * c01 * np.float32(2.5), rtol=1e-5) and (acc[..., 3] == 7).all()
 
 
 def test_determinism_and_seed(flats, worlds):
