@@ -8,6 +8,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -78,6 +79,7 @@ struct rzb_ctx
 	uint64_t passes = 0, launches = 0;
 	float last_render_ms = 0.0f, last_trace_ms = 0.0f, last_shade_ms = 0.0f, last_shadow_ms = 0.0f;
 	int trace_grid = 0, shadow_grid = 0, rays_grid = 0, any_grid = 0;
+	uint32_t refill_threshold = 1; // RZB200_REFILL: idle lanes per warp that trigger a work fetch (tuning knob)
 };
 
 namespace
@@ -241,6 +243,7 @@ extern "C" int rzb_create(int device, rzb_ctx** out)
 	cudaMemsetAsync(ctx->d_work, 0, 128, ctx->stream);
 	if ((e = cudaMalloc(reinterpret_cast<void**>(&ctx->d_counters), 256)) != cudaSuccess) { delete ctx; return cudaFail(nullptr, e, "cudaMalloc(counters)"); }
 	cudaMemsetAsync(ctx->d_counters, 0, 256, ctx->stream);
+	if (const char* env = std::getenv("RZB200_REFILL")) ctx->refill_threshold = std::min(32u, std::max(1u, uint32_t(std::atoi(env))));
 	ctx->trace_grid = gridFor(ctx, reinterpret_cast<const void*>(&k_trace_paths<false>), kTraceBlock);
 	ctx->shadow_grid = gridFor(ctx, reinterpret_cast<const void*>(&k_trace_shadow<false>), kTraceBlock);
 	ctx->rays_grid = gridFor(ctx, reinterpret_cast<const void*>(&k_trace_rays<false>), kTraceBlock);
@@ -572,6 +575,7 @@ extern "C" int rzb_render(rzb_ctx* ctx, uint32_t passes)
 	f.direct_samples = ctx->cfg.direct_light_samples;
 	f.spot_samples = ctx->cfg.spot_light_samples;
 	f.seed = ctx->cfg.seed;
+	f.refill_threshold = ctx->refill_threshold;
 	const bool lights = (ctx->sc.direct_light_count && f.direct_samples) || (ctx->sc.spot_light_count && f.spot_samples);
 	const bool count = (ctx->cfg.flags & RZB_FLAG_COUNT_WORK) != 0u;
 	f.work = ctx->d_work;
@@ -863,7 +867,7 @@ extern "C" int rzb_trace_closest_device(rzb_ctx* ctx, const void* rays_o_near, c
 	if (elapsed_ms) RZB_CUDA(ctx, cudaEventRecord(ctx->ev_begin, ctx->stream));
 	k_trace_rays<false><<<ctx->rays_grid, kTraceBlock, 0, ctx->stream>>>(ctx->sc,
 		static_cast<const float4*>(rays_o_near), static_cast<const float4*>(rays_d_far), n,
-		static_cast<DHit*>(hits_out_device), ctx->d_counters + 8, nullptr);
+		static_cast<DHit*>(hits_out_device), ctx->d_counters + 8, nullptr, ctx->refill_threshold);
 	ctx->launches += 1;
 	RZB_CUDA(ctx, cudaGetLastError());
 	if (elapsed_ms)
@@ -891,11 +895,11 @@ extern "C" int rzb_trace_closest(rzb_ctx* ctx, const float* origins, const float
 	if (stats)
 		k_trace_rays<true><<<ctx->rays_grid, kTraceBlock, 0, ctx->stream>>>(ctx->sc,
 			static_cast<const float4*>(ctx->scratch[0].ptr), static_cast<const float4*>(ctx->scratch[1].ptr), n,
-			static_cast<DHit*>(ctx->scratch[2].ptr), ctx->d_counters + 8, d_stats);
+			static_cast<DHit*>(ctx->scratch[2].ptr), ctx->d_counters + 8, d_stats, ctx->refill_threshold);
 	else
 		k_trace_rays<false><<<ctx->rays_grid, kTraceBlock, 0, ctx->stream>>>(ctx->sc,
 			static_cast<const float4*>(ctx->scratch[0].ptr), static_cast<const float4*>(ctx->scratch[1].ptr), n,
-			static_cast<DHit*>(ctx->scratch[2].ptr), ctx->d_counters + 8, nullptr);
+			static_cast<DHit*>(ctx->scratch[2].ptr), ctx->d_counters + 8, nullptr, ctx->refill_threshold);
 	k_convert_hits<<<(n + 255) / 256, 256, 0, ctx->stream>>>(ctx->sc, static_cast<const DHit*>(ctx->scratch[2].ptr),
 		static_cast<rzb_hit*>(ctx->scratch[3].ptr), n);
 	ctx->launches += 2;
@@ -925,7 +929,7 @@ extern "C" int rzb_trace_any(rzb_ctx* ctx, const float* origins, const float* di
 	RZB_CUDA(ctx, cudaMemsetAsync(ctx->d_counters + 8, 0, 4, ctx->stream));
 	k_trace_any_rays<<<ctx->any_grid, kTraceBlock, 0, ctx->stream>>>(ctx->sc,
 		static_cast<const float4*>(ctx->scratch[0].ptr), static_cast<const float4*>(ctx->scratch[1].ptr), n,
-		static_cast<float4*>(ctx->scratch[2].ptr), ctx->d_counters + 8);
+		static_cast<float4*>(ctx->scratch[2].ptr), ctx->d_counters + 8, ctx->refill_threshold);
 	ctx->launches += 1;
 	RZB_CUDA(ctx, cudaGetLastError());
 	RZB_CUDA(ctx, cudaMemcpyAsync(mask_out, ctx->scratch[2].ptr, size_t(n) * 16, cudaMemcpyDeviceToHost, ctx->stream));

@@ -1,4 +1,5 @@
-// Device-side data layout and the two traversal cores (closest-hit, any-hit) of the B200 render path.
+// Device-side data layout and the parity-critical primitives (slab, triangle, instance transform) of the B200 render path;
+// the traversal itself is in rzb_traverse.cuh.
 //
 // What is reproduced, bit for bit, from the reference (so that closest-hit IDs match):
 //   slab test        BoundingBox::rayIntersection   /root/reference/RayZath/cuda_render_parts.cuh:1178-1191
@@ -148,6 +149,11 @@ namespace rzb
 			if (sp < kSmemStack) return smem[sp * kTraceBlock];
 			return local[sp - kSmemStack];
 		}
+		__device__ __forceinline__ uint2 peek() const
+		{
+			if (sp - 1 < kSmemStack) return smem[(sp - 1) * kTraceBlock];
+			return local[sp - 1 - kSmemStack];
+		}
 	};
 
 	// BoundingBox::rayIntersection: six IEEE divides, fminf/fmaxf, then the three range tests.
@@ -230,187 +236,5 @@ namespace rzb
 #pragma unroll
 		for (int k = 0; k < 6; ++k) q[k] = __ldg(p + k);
 		return r;
-	}
-
-	// Closest hit of the two-level tree. `ordered` = near-child-first (closest-hit order); the any-hit
-	// variant below uses the fixed first/second order of the reference's shadow traversal.
-	template <bool STATS>
-	__device__ __forceinline__ Hit trace_closest(const DScene& sc, const V3 wo, const V3 wd,
-		const float near_in, const float far_in, Stack& st, TraceCounters* cnt)
-	{
-		Hit hit;
-		hit.t = far_in; hit.near_ = near_in; hit.b1 = 0.0f; hit.b2 = 0.0f;
-		hit.tri = kNoIndex; hit.inst = kNoIndex; hit.external = true;
-		if (sc.instance_count == 0u) return hit;
-
-		const float4* __restrict__ nodes = sc.nodes;
-		float wnear = near_in, wfar = far_in; // world range
-		float near_ = near_in, far_ = far_in; // range of the current level
-		V3 o = wo, d = wd;
-		uint32_t sbits = sign_bits(wd);
-		const uint32_t wbits = sbits;
-		float len = 1.0f;
-		bool in_mesh = false, mesh_hit = false;
-		uint32_t cur_inst = kNoIndex;
-		uint32_t ltri = kNoIndex; float lb1 = 0.0f, lb2 = 0.0f; bool lext = true;
-		st.sp = 0;
-
-		// root of the instance tree
-		uint32_t cur_begin, cur_tc;
-		{
-			const float4 n0 = __ldg(nodes + 2 * size_t(sc.top_root));
-			const float4 n1 = __ldg(nodes + 2 * size_t(sc.top_root) + 1);
-			float tmin;
-			if (STATS) cnt->top_nodes++;
-			if (!(slab_rn(n0, n1, o, d, near_, tmin) && range_ok(tmin, far_))) return hit;
-			cur_begin = __float_as_uint(n1.z);
-			cur_tc = __float_as_uint(n1.w);
-		}
-		bool have_cur = true; // cur_* describes a node whose box has been passed
-
-		for (;;)
-		{
-			if (have_cur)
-			{
-				const uint32_t count = cur_tc & 0x3FFFFFFFu;
-				if (count != 0u)
-				{
-					// leaf
-					if (in_mesh)
-					{
-						for (uint32_t i = cur_begin; i < cur_begin + count; ++i)
-						{
-							if (STATS) cnt->triangles++;
-							if (triangle_closest(sc.tri_hot, i, o, d, near_, far_, lb1, lb2, lext))
-							{
-								ltri = i;
-								mesh_hit = true;
-							}
-						}
-					}
-					else
-					{
-						st.push(kEntryInstRange | cur_begin, cur_begin + count);
-					}
-					have_cur = false;
-					continue;
-				}
-				// inner node: fetch the sibling pair (64 B, 64-byte aligned)
-				const uint32_t flip = (sbits >> (cur_tc >> 30)) & 1u;
-				const uint32_t ia = cur_begin + flip, ib = cur_begin + (flip ^ 1u);
-				const float4 a0 = __ldg(nodes + 2 * size_t(ia));
-				const float4 a1 = __ldg(nodes + 2 * size_t(ia) + 1);
-				const float4 b0 = __ldg(nodes + 2 * size_t(ib));
-				const float4 b1 = __ldg(nodes + 2 * size_t(ib) + 1);
-				if (STATS) { if (in_mesh) cnt->mesh_nodes += 2; else cnt->top_nodes += 2; }
-				float tmin_a, tmin_b;
-				const bool hit_a = slab_rn(a0, a1, o, d, near_, tmin_a) && range_ok(tmin_a, far_);
-				const bool box_b = slab_rn(b0, b1, o, d, near_, tmin_b);
-				const uint32_t a_tc = __float_as_uint(a1.w), b_tc = __float_as_uint(b1.w);
-				const bool a_leaf = (a_tc & 0x3FFFFFFFu) != 0u;
-				const uint32_t kind = in_mesh ? kEntryMeshNode : kEntryTopNode;
-
-				if (hit_a && (!a_leaf || !in_mesh))
-				{
-					// A is searched first (its subtree, or — at the top level — its instances); B's range test is
-					// deferred: it must see the range as it is AFTER A has been searched
-					if (box_b && range_ok(tmin_b, far_)) st.push(kind | ib, __float_as_uint(tmin_b));
-					cur_begin = __float_as_uint(a1.z);
-					cur_tc = a_tc;
-					continue;
-				}
-				if (hit_a)
-				{
-					// mesh leaf A: intersect now, then B sees the updated range immediately
-					const uint32_t begin = __float_as_uint(a1.z), cnt_a = a_tc & 0x3FFFFFFFu;
-					for (uint32_t i = begin; i < begin + cnt_a; ++i)
-					{
-						if (STATS) cnt->triangles++;
-						if (triangle_closest(sc.tri_hot, i, o, d, near_, far_, lb1, lb2, lext))
-						{
-							ltri = i;
-							mesh_hit = true;
-						}
-					}
-				}
-				if (box_b && range_ok(tmin_b, far_))
-				{
-					cur_begin = __float_as_uint(b1.z);
-					cur_tc = b_tc;
-					continue;
-				}
-				have_cur = false;
-				continue;
-			}
-
-			// ---- pop ----
-			if (st.sp == 0)
-			{
-				if (!in_mesh) break;
-			}
-			uint2 e = make_uint2(kEntryTopNode, 0u);
-			bool popped = false;
-			if (st.sp != 0)
-			{
-				e = st.pop();
-				popped = true;
-			}
-			const uint32_t ekind = e.x & kEntryKindMask;
-			if (in_mesh && (!popped || ekind != kEntryMeshNode))
-			{
-				// the current mesh is exhausted: leave the instance (cuda_instance.cuh:203-213)
-				if (mesh_hit)
-				{
-					hit.inst = cur_inst;
-					hit.tri = ltri; hit.b1 = lb1; hit.b2 = lb2; hit.external = lext;
-					wnear = fdiv(near_, len);
-					wfar = fdiv(far_, len);
-				}
-				in_mesh = false;
-				o = wo; d = wd; sbits = wbits;
-				near_ = wnear; far_ = wfar;
-				if (!popped) break;
-			}
-			const uint32_t idx = e.x & kEntryIndexMask;
-			if (ekind == kEntryInstRange)
-			{
-				const uint32_t end = e.y;
-				if (idx + 1u < end) st.push(kEntryInstRange | (idx + 1u), end);
-				// Instance::closestIntersection
-				if (STATS) cnt->instances++;
-				const DInstance in = load_instance(sc.instances, idx);
-				float tmin;
-				const float4 n0 = make_float4(in.bminx, in.bminy, in.bminz, in.bmaxx);
-				const float4 n1 = make_float4(in.bmaxy, in.bmaxz, 0.0f, 0.0f);
-				if (!(slab_rn(n0, n1, o, d, near_, tmin) && range_ok(tmin, far_))) continue;
-				if (in.mesh_root == kNoIndex) continue;
-				V3 lo, ld;
-				float l;
-				ray_to_local(in, wo, wd, lo, ld, l);
-				const float lnear = fmul(near_, l), lfar = fmul(far_, l);
-				// mesh root (cuda_instance.cuh:37-38)
-				const float4 r0 = __ldg(nodes + 2 * size_t(in.mesh_root));
-				const float4 r1 = __ldg(nodes + 2 * size_t(in.mesh_root) + 1);
-				if (STATS) cnt->mesh_nodes++;
-				if (!(slab_rn(r0, r1, lo, ld, lnear, tmin) && range_ok(tmin, lfar))) continue;
-				in_mesh = true; mesh_hit = false;
-				cur_inst = idx;
-				o = lo; d = ld; len = l; sbits = sign_bits(ld);
-				near_ = lnear; far_ = lfar;
-				cur_begin = __float_as_uint(r1.z);
-				cur_tc = __float_as_uint(r1.w);
-				have_cur = true;
-				continue;
-			}
-			// deferred node: late range test, then fetch its own header
-			if (!range_ok(__uint_as_float(e.y), far_)) continue;
-			const float4 n1 = __ldg(nodes + 2 * size_t(idx) + 1);
-			cur_begin = __float_as_uint(n1.z);
-			cur_tc = __float_as_uint(n1.w);
-			have_cur = true;
-		}
-		hit.t = wfar;
-		hit.near_ = wnear;
-		return hit;
 	}
 }

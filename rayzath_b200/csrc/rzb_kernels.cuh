@@ -44,6 +44,7 @@ namespace rzb
 		unsigned long long* work; // RZB_FLAG_COUNT_WORK: [0..3] closest top/inst/mesh/tri, [4..7] shadow, [8] shadow rays
 		uint32_t shadow_capacity;
 		uint32_t pass_index;
+		uint32_t refill_threshold; // idle lanes per warp that trigger a work fetch
 		uint32_t max_depth, direct_samples, spot_samples;
 		uint64_t seed;
 	};
@@ -136,6 +137,26 @@ namespace rzb
 		f.depth[p] = 0.0f;
 	}
 
+	// ---------------------------------------------------------------- dynamic work fetch
+	// Lanes whose ray is finished pull the next index from a global counter: one ballot + one atomic per warp and
+	// refill. `exhausted` becomes (warp-uniformly) true once the counter has passed `n`. Returns kNoIndex for lanes
+	// that got nothing. The refill happens when at least `threshold` lanes are idle (or the warp is completely idle).
+	__device__ __forceinline__ uint32_t warp_fetch(uint32_t* counter, const uint32_t n, const bool idle, bool& exhausted,
+		const uint32_t threshold)
+	{
+		const uint32_t lane = threadIdx.x & 31u;
+		const uint32_t need = __ballot_sync(0xFFFFFFFFu, idle);
+		const uint32_t count = __popc(need);
+		if (exhausted || count == 0u || (count < threshold && count != 32u)) return kNoIndex;
+		uint32_t base = 0;
+		if (lane == 0u) base = atomicAdd(counter, count);
+		base = __shfl_sync(0xFFFFFFFFu, base, 0);
+		if (base + count >= n) exhausted = true;
+		if (!idle) return kNoIndex;
+		const uint32_t idx = base + __popc(need & ((1u << lane) - 1u));
+		return idx < n ? idx : kNoIndex;
+	}
+
 	// ---------------------------------------------------------------- k_trace_paths
 	__device__ __forceinline__ void flush_counters(const TraceCounters& cnt, unsigned long long* dst)
 	{
@@ -155,40 +176,55 @@ namespace rzb
 	{
 		__shared__ uint2 smem_stack[kSmemStack * kTraceBlock];
 		Stack st = make_stack(smem_stack);
-		const uint32_t lane = threadIdx.x & 31u;
 		TraceCounters cnt{0u, 0u, 0u, 0u};
+		Traversal<false> tv;
+		tv.state = kTravDone;
+		uint32_t slot = kNoIndex, flags = 0u;
+		bool exhausted = false;
 		for (;;)
 		{
-			uint32_t base = 0;
-			if (lane == 0) base = atomicAdd(&f.counters[0], 32u);
-			base = __shfl_sync(0xFFFFFFFFu, base, 0);
-			if (base >= f.n_slots) break;
-			const uint32_t slot = base + lane;
-			uint32_t x, y;
-			if (slot >= f.n_slots || !slot_to_pixel(f, slot, x, y)) continue;
-			const float4 so = f.st_o[slot];
-			const float4 sd = f.st_d[slot];
-			const uint32_t bits = __float_as_uint(so.w);
-			const uint32_t depth = bits & 0xFFu, medium = bits >> kMediumShift;
-			float near_ = 0.0f, far_ = kFltMax;
-			if (depth == 0u) { near_ = f.cam.near_; far_ = f.cam.far_; }
-			uint32_t flags = 0u;
-			// World::closestIntersection: free flight in the current medium first (cuda_material.cuh:141-159)
-			if (!(sc.flags & RZB_FLAG_CPU_SEMANTICS))
+			// retire finished rays
+			if (tv.done() && slot != kNoIndex)
 			{
-				const float sigma = sc.materials[medium].scattering;
-				if (sigma > 1.0e-4f)
-				{
-					Rng rng(f.seed, slot, f.pass_index);
-					const float dist = (-__logf(rng.next() + 1.0e-4f)) / sigma;
-					if (dist < far_) { far_ = dist; flags |= kHitScatterBit; }
-				}
+				uint32_t tri_bits = flags | (tv.ext ? kHitExternalBit : 0u);
+				tri_bits |= (tv.hit_tri == kNoIndex) ? kHitTriMask : (tv.hit_tri & kHitTriMask);
+				f.hit_a[slot] = make_float4(tv.wfar, tv.b1, tv.b2, __uint_as_float(tri_bits));
+				f.hit_inst[slot] = tv.hit_inst;
+				slot = kNoIndex;
 			}
-			const Hit h = trace_closest<STATS>(sc, v3(so.x, so.y, so.z), v3(sd.x, sd.y, sd.z), near_, far_, st, &cnt);
-			uint32_t tri_bits = flags | (h.external ? kHitExternalBit : 0u);
-			tri_bits |= (h.tri == kNoIndex) ? kHitTriMask : (h.tri & kHitTriMask);
-			f.hit_a[slot] = make_float4(h.t, h.b1, h.b2, __uint_as_float(tri_bits));
-			f.hit_inst[slot] = h.inst;
+			const uint32_t next = warp_fetch(&f.counters[0], f.n_slots, tv.done(), exhausted, f.refill_threshold);
+			uint32_t x, y;
+			if (next != kNoIndex && slot_to_pixel(f, next, x, y))
+			{
+				slot = next;
+				const float4 so = f.st_o[slot];
+				const float4 sd = f.st_d[slot];
+				const uint32_t bits = __float_as_uint(so.w);
+				const uint32_t depth = bits & 0xFFu, medium = bits >> kMediumShift;
+				float near_ = 0.0f, far_ = kFltMax;
+				if (depth == 0u) { near_ = f.cam.near_; far_ = f.cam.far_; }
+				flags = 0u;
+				// World::closestIntersection: free flight in the current medium first (cuda_material.cuh:141-159)
+				if (!(sc.flags & RZB_FLAG_CPU_SEMANTICS))
+				{
+					const float sigma = sc.materials[medium].scattering;
+					if (sigma > 1.0e-4f)
+					{
+						Rng rng(f.seed, slot, f.pass_index);
+						const float dist = (-__logf(rng.next() + 1.0e-4f)) / sigma;
+						if (dist < far_) { far_ = dist; flags |= kHitScatterBit; }
+					}
+				}
+				tv.begin<STATS>(sc, v3(so.x, so.y, so.z), v3(sd.x, sd.y, sd.z), near_, far_, st, cnt);
+			}
+			if (__all_sync(0xFFFFFFFFu, tv.done() && slot == kNoIndex))
+			{
+				if (exhausted) break;
+				continue;
+			}
+			tv.inner_phase<STATS>(sc, st, cnt);
+			tv.leaf_phase<STATS>(sc, st, cnt);
+			tv.transition_phase<STATS>(sc, st, cnt);
 		}
 		if (STATS) flush_counters(cnt, f.work);
 	}
@@ -418,28 +454,44 @@ namespace rzb
 	{
 		__shared__ uint2 smem_stack[kSmemStack * kTraceBlock];
 		Stack st = make_stack(smem_stack);
-		const uint32_t lane = threadIdx.x & 31u;
 		const uint32_t n = min(f.counters[1], f.shadow_capacity);
 		TraceCounters cnt{0u, 0u, 0u, 0u};
 		if (STATS && blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(f.work + 8, (unsigned long long)n);
+		Traversal<true> tv;
+		tv.state = kTravDone;
+		uint32_t item = kNoIndex;
+		bool exhausted = false;
 		for (;;)
 		{
-			uint32_t base = 0;
-			if (lane == 0) base = atomicAdd(&f.counters[2], 32u);
-			base = __shfl_sync(0xFFFFFFFFu, base, 0);
-			if (base >= n) break;
-			const uint32_t i = base + lane;
-			if (i >= n) continue;
-			const float4 o = f.sh_o[i];
-			const float4 d = f.sh_d[i];
-			const float4 c = f.sh_c[i];
-			const float4 m = trace_any<STATS>(sc, v3(o.x, o.y, o.z), v3(d.x, d.y, d.z), 0.0f, o.w, st, &cnt);
-			const float w = m.w;
-			if (w <= 0.0f) continue;
-			float* a = reinterpret_cast<float*>(f.accum + __float_as_uint(d.w));
-			atomicAdd(a + 0, c.x * m.x * w);
-			atomicAdd(a + 1, c.y * m.y * w);
-			atomicAdd(a + 2, c.z * m.z * w);
+			if (tv.done() && item != kNoIndex)
+			{
+				const float w = tv.mask.w;
+				if (w > 0.0f)
+				{
+					const float4 c = f.sh_c[item];
+					float* a = reinterpret_cast<float*>(f.accum + __float_as_uint(f.sh_d[item].w));
+					atomicAdd(a + 0, c.x * tv.mask.x * w);
+					atomicAdd(a + 1, c.y * tv.mask.y * w);
+					atomicAdd(a + 2, c.z * tv.mask.z * w);
+				}
+				item = kNoIndex;
+			}
+			const uint32_t next = warp_fetch(&f.counters[2], n, tv.done(), exhausted, f.refill_threshold);
+			if (next != kNoIndex)
+			{
+				item = next;
+				const float4 o = f.sh_o[item];
+				const float4 d = f.sh_d[item];
+				tv.begin<STATS>(sc, v3(o.x, o.y, o.z), v3(d.x, d.y, d.z), 0.0f, o.w, st, cnt);
+			}
+			if (__all_sync(0xFFFFFFFFu, tv.done() && item == kNoIndex))
+			{
+				if (exhausted) break;
+				continue;
+			}
+			tv.inner_phase<STATS>(sc, st, cnt);
+			tv.leaf_phase<STATS>(sc, st, cnt);
+			tv.transition_phase<STATS>(sc, st, cnt);
 		}
 		if (STATS) flush_counters(cnt, f.work + 4);
 	}
@@ -494,39 +546,44 @@ namespace rzb
 	template <bool STATS>
 	__global__ void __launch_bounds__(kTraceBlock) k_trace_rays(DScene sc, const float4* __restrict__ ray_o_near,
 		const float4* __restrict__ ray_d_far, uint32_t n, DHit* __restrict__ hits, uint32_t* counter,
-		unsigned long long* stats)
+		unsigned long long* stats, uint32_t refill_threshold)
 	{
 		__shared__ uint2 smem_stack[kSmemStack * kTraceBlock];
 		Stack st = make_stack(smem_stack);
-		const uint32_t lane = threadIdx.x & 31u;
 		TraceCounters cnt{0u, 0u, 0u, 0u};
+		Traversal<false> tv;
+		tv.state = kTravDone;
+		uint32_t item = kNoIndex;
+		bool exhausted = false;
 		for (;;)
 		{
-			uint32_t base = 0;
-			if (lane == 0) base = atomicAdd(counter, 32u);
-			base = __shfl_sync(0xFFFFFFFFu, base, 0);
-			if (base >= n) break;
-			const uint32_t i = base + lane;
-			if (i >= n) continue;
-			const float4 o = __ldg(ray_o_near + i);
-			const float4 d = __ldg(ray_d_far + i);
-			const Hit h = trace_closest<STATS>(sc, v3(o.x, o.y, o.z), v3(d.x, d.y, d.z), o.w, d.w, st, &cnt);
-			DHit out;
-			out.t = h.t; out.b1 = h.b1; out.b2 = h.b2;
-			out.tri_bits = (h.tri == kNoIndex ? kHitTriMask : (h.tri & kHitTriMask)) | (h.external ? kHitExternalBit : 0u);
-			out.inst = h.inst;
-			out._pad[0] = out._pad[1] = out._pad[2] = 0u;
-			float4* dst = reinterpret_cast<float4*>(hits + i);
-			dst[0] = make_float4(out.t, out.b1, out.b2, __uint_as_float(out.tri_bits));
-			dst[1] = make_float4(__uint_as_float(out.inst), 0.0f, 0.0f, 0.0f);
+			if (tv.done() && item != kNoIndex)
+			{
+				const uint32_t tri_bits = (tv.hit_tri == kNoIndex ? kHitTriMask : (tv.hit_tri & kHitTriMask)) |
+					(tv.ext ? kHitExternalBit : 0u);
+				float4* dst = reinterpret_cast<float4*>(hits + item);
+				dst[0] = make_float4(tv.wfar, tv.b1, tv.b2, __uint_as_float(tri_bits));
+				dst[1] = make_float4(__uint_as_float(tv.hit_inst), 0.0f, 0.0f, 0.0f);
+				item = kNoIndex;
+			}
+			const uint32_t next = warp_fetch(counter, n, tv.done(), exhausted, refill_threshold);
+			if (next != kNoIndex)
+			{
+				item = next;
+				const float4 o = __ldg(ray_o_near + item);
+				const float4 d = __ldg(ray_d_far + item);
+				tv.begin<STATS>(sc, v3(o.x, o.y, o.z), v3(d.x, d.y, d.z), o.w, d.w, st, cnt);
+			}
+			if (__all_sync(0xFFFFFFFFu, tv.done() && item == kNoIndex))
+			{
+				if (exhausted) break;
+				continue;
+			}
+			tv.inner_phase<STATS>(sc, st, cnt);
+			tv.leaf_phase<STATS>(sc, st, cnt);
+			tv.transition_phase<STATS>(sc, st, cnt);
 		}
-		if (STATS)
-		{
-			atomicAdd(stats + 0, (unsigned long long)cnt.top_nodes);
-			atomicAdd(stats + 1, (unsigned long long)cnt.instances);
-			atomicAdd(stats + 2, (unsigned long long)cnt.mesh_nodes);
-			atomicAdd(stats + 3, (unsigned long long)cnt.triangles);
-		}
+		if (STATS) flush_counters(cnt, stats);
 	}
 
 	__global__ void k_convert_hits(DScene sc, const DHit* __restrict__ in, rzb_hit* __restrict__ out, uint32_t n)
@@ -552,22 +609,39 @@ namespace rzb
 	}
 
 	__global__ void __launch_bounds__(kTraceBlock) k_trace_any_rays(DScene sc, const float4* __restrict__ ray_o_near,
-		const float4* __restrict__ ray_d_far, uint32_t n, float4* __restrict__ masks, uint32_t* counter)
+		const float4* __restrict__ ray_d_far, uint32_t n, float4* __restrict__ masks, uint32_t* counter,
+		uint32_t refill_threshold)
 	{
 		__shared__ uint2 smem_stack[kSmemStack * kTraceBlock];
 		Stack st = make_stack(smem_stack);
-		const uint32_t lane = threadIdx.x & 31u;
+		TraceCounters cnt{0u, 0u, 0u, 0u};
+		Traversal<true> tv;
+		tv.state = kTravDone;
+		uint32_t item = kNoIndex;
+		bool exhausted = false;
 		for (;;)
 		{
-			uint32_t base = 0;
-			if (lane == 0) base = atomicAdd(counter, 32u);
-			base = __shfl_sync(0xFFFFFFFFu, base, 0);
-			if (base >= n) break;
-			const uint32_t i = base + lane;
-			if (i >= n) continue;
-			const float4 o = __ldg(ray_o_near + i);
-			const float4 d = __ldg(ray_d_far + i);
-			masks[i] = trace_any<false>(sc, v3(o.x, o.y, o.z), v3(d.x, d.y, d.z), o.w, d.w, st, nullptr);
+			if (tv.done() && item != kNoIndex)
+			{
+				masks[item] = tv.mask;
+				item = kNoIndex;
+			}
+			const uint32_t next = warp_fetch(counter, n, tv.done(), exhausted, refill_threshold);
+			if (next != kNoIndex)
+			{
+				item = next;
+				const float4 o = __ldg(ray_o_near + item);
+				const float4 d = __ldg(ray_d_far + item);
+				tv.begin<false>(sc, v3(o.x, o.y, o.z), v3(d.x, d.y, d.z), o.w, d.w, st, cnt);
+			}
+			if (__all_sync(0xFFFFFFFFu, tv.done() && item == kNoIndex))
+			{
+				if (exhausted) break;
+				continue;
+			}
+			tv.inner_phase<false>(sc, st, cnt);
+			tv.leaf_phase<false>(sc, st, cnt);
+			tv.transition_phase<false>(sc, st, cnt);
 		}
 	}
 

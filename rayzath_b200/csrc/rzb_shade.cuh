@@ -17,7 +17,7 @@
 // renders are reproducible and sample streams of different GPUs are disjoint by construction.
 #pragma once
 
-#include "rzb_device.cuh"
+#include "rzb_traverse.cuh"
 
 namespace rzb
 {
@@ -414,131 +414,20 @@ namespace rzb
 		d = normalize(ax * ld.x + ay * ld.y + az * ld.z);
 	}
 
-	// ------------------------------------------------------------------ any-hit (cuda_bvh.cuh:172-232, cuda_instance.cuh:92-164, 215-229)
-	// Returns the RGBA shadow mask. Child order is the fixed first/second order of the reference; the mask is a
-	// product, so order only matters for the early-out.
-	template <bool STATS>
-	__device__ __forceinline__ float4 trace_any(const DScene& sc, const V3 wo, const V3 wd,
-		const float near_in, const float far_in, Stack& st, TraceCounters* cnt)
+	// ------------------------------------------------------------------ any-hit attenuation (cuda_instance.cuh:105-112)
+	template <bool ANY>
+	__device__ __forceinline__ void Traversal<ANY>::shadow_attenuate(const DScene& sc, const uint32_t i, const float tb1, const float tb2)
 	{
-		float4 mask = make_float4(1.0f, 1.0f, 1.0f, 1.0f);
-		if (sc.instance_count == 0u) return mask;
-		const float4* __restrict__ nodes = sc.nodes;
-		V3 o = wo, d = wd;
-		float near_ = near_in, far_ = far_in;
-		bool in_mesh = false;
-		uint32_t mat_offset = 0u, mat_count = 0u;
-		st.sp = 0;
-		uint32_t cur_begin, cur_tc;
-		{
-			const float4 n0 = __ldg(nodes + 2 * size_t(sc.top_root));
-			const float4 n1 = __ldg(nodes + 2 * size_t(sc.top_root) + 1);
-			float tmin;
-			if (STATS) cnt->top_nodes++;
-			if (!(slab_rn(n0, n1, o, d, near_, tmin) && range_ok(tmin, far_))) return mask;
-			cur_begin = __float_as_uint(n1.z);
-			cur_tc = __float_as_uint(n1.w);
-		}
-		bool have_cur = true;
-		for (;;)
-		{
-			if (have_cur)
-			{
-				const uint32_t count = cur_tc & 0x3FFFFFFFu;
-				if (count != 0u)
-				{
-					if (in_mesh)
-					{
-						for (uint32_t i = cur_begin; i < cur_begin + count; ++i)
-						{
-							float tf = far_, b1, b2;
-							bool ext;
-							if (STATS) cnt->triangles++;
-							if (!triangle_closest(sc.tri_hot, i, o, d, near_, tf, b1, b2, ext)) continue;
-							if (sc.flags & RZB_FLAG_CPU_SEMANTICS) return make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-							const float4 c0 = __ldg(sc.tri_cold + 5 * size_t(i));
-							const float4 c1 = __ldg(sc.tri_cold + 5 * size_t(i) + 1);
-							const float4 c2 = __ldg(sc.tri_cold + 5 * size_t(i) + 2);
-							const float4 c3 = __ldg(sc.tri_cold + 5 * size_t(i) + 3);
-							const float4 c4 = __ldg(sc.tri_cold + 5 * size_t(i) + 4);
-							const float b3 = 1.0f - b1 - b2;
-							const float u = c0.w * b3 + c2.w * b1 + c4.x * b2;
-							const float v = c1.w * b3 + c3.w * b1 + c4.y * b2;
-							const uint32_t slot = __float_as_uint(__ldg(sc.tri_hot + 3 * size_t(i) + 2).y);
-							const float4 oc = material_opacity_color(sc,
-								sc.materials[instance_material(sc, mat_offset, mat_count, slot)], u, v);
-							mask = make_float4(mask.x * oc.x, mask.y * oc.y, mask.z * oc.z, mask.w * oc.w);
-							if (mask.w < 1.0e-4f) return mask;
-						}
-					}
-					else st.push(kEntryInstRange | cur_begin, cur_begin + count);
-					have_cur = false;
-					continue;
-				}
-				const float4 a0 = __ldg(nodes + 2 * size_t(cur_begin));
-				const float4 a1 = __ldg(nodes + 2 * size_t(cur_begin) + 1);
-				const float4 b0 = __ldg(nodes + 2 * size_t(cur_begin) + 2);
-				const float4 b1 = __ldg(nodes + 2 * size_t(cur_begin) + 3);
-				if (STATS) { if (in_mesh) cnt->mesh_nodes += 2; else cnt->top_nodes += 2; }
-				float ta, tb;
-				const bool hit_a = slab_rn(a0, a1, o, d, near_, ta) && range_ok(ta, far_);
-				const bool hit_b = slab_rn(b0, b1, o, d, near_, tb) && range_ok(tb, far_);
-				if (hit_a)
-				{
-					if (hit_b) st.push((in_mesh ? kEntryMeshNode : kEntryTopNode) | (cur_begin + 1u), 0u);
-					cur_begin = __float_as_uint(a1.z);
-					cur_tc = __float_as_uint(a1.w);
-					continue;
-				}
-				if (hit_b)
-				{
-					cur_begin = __float_as_uint(b1.z);
-					cur_tc = __float_as_uint(b1.w);
-					continue;
-				}
-				have_cur = false;
-				continue;
-			}
-			if (st.sp == 0) break;
-			const uint2 e = st.pop();
-			const uint32_t ekind = e.x & kEntryKindMask;
-			const uint32_t idx = e.x & kEntryIndexMask;
-			if (ekind != kEntryMeshNode && in_mesh)
-			{
-				in_mesh = false;
-				o = wo; d = wd; near_ = near_in; far_ = far_in;
-			}
-			if (ekind == kEntryInstRange)
-			{
-				if (idx + 1u < e.y) st.push(kEntryInstRange | (idx + 1u), e.y);
-				if (STATS) cnt->instances++;
-				const DInstance in = load_instance(sc.instances, idx);
-				float tmin;
-				const float4 n0 = make_float4(in.bminx, in.bminy, in.bminz, in.bmaxx);
-				const float4 n1 = make_float4(in.bmaxy, in.bmaxz, 0.0f, 0.0f);
-				if (!(slab_rn(n0, n1, o, d, near_, tmin) && range_ok(tmin, far_))) continue;
-				if (in.mesh_root == kNoIndex) continue;
-				V3 lo, ld;
-				float l;
-				ray_to_local(in, wo, wd, lo, ld, l);
-				const float lnear = fmul(near_, l), lfar = fmul(far_, l);
-				const float4 r0 = __ldg(nodes + 2 * size_t(in.mesh_root));
-				const float4 r1 = __ldg(nodes + 2 * size_t(in.mesh_root) + 1);
-				if (STATS) cnt->mesh_nodes++;
-				if (!(slab_rn(r0, r1, lo, ld, lnear, tmin) && range_ok(tmin, lfar))) continue;
-				in_mesh = true;
-				mat_offset = in.mat_offset; mat_count = in.mat_count;
-				o = lo; d = ld; near_ = lnear; far_ = lfar;
-				cur_begin = __float_as_uint(r1.z);
-				cur_tc = __float_as_uint(r1.w);
-				have_cur = true;
-				continue;
-			}
-			const float4 n1 = __ldg(nodes + 2 * size_t(idx) + 1);
-			cur_begin = __float_as_uint(n1.z);
-			cur_tc = __float_as_uint(n1.w);
-			have_cur = true;
-		}
-		return mask;
+		const float4 c0 = __ldg(sc.tri_cold + 5 * size_t(i));
+		const float4 c1 = __ldg(sc.tri_cold + 5 * size_t(i) + 1);
+		const float4 c2 = __ldg(sc.tri_cold + 5 * size_t(i) + 2);
+		const float4 c3 = __ldg(sc.tri_cold + 5 * size_t(i) + 3);
+		const float4 c4 = __ldg(sc.tri_cold + 5 * size_t(i) + 4);
+		const float b3 = 1.0f - tb1 - tb2;
+		const float u = c0.w * b3 + c2.w * tb1 + c4.x * tb2;
+		const float v = c1.w * b3 + c3.w * tb1 + c4.y * tb2;
+		const uint32_t slot = __float_as_uint(__ldg(sc.tri_hot + 3 * size_t(i) + 2).y);
+		const float4 oc = material_opacity_color(sc, sc.materials[instance_material(sc, mat_offset, mat_count, slot)], u, v);
+		mask = make_float4(mask.x * oc.x, mask.y * oc.y, mask.z * oc.z, mask.w * oc.w);
 	}
 }

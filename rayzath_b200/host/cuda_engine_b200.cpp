@@ -1,0 +1,222 @@
+// Drop-in implementation of RayZath::Cuda::Engine on top of the B200 render path's C ABI (include/rzb200.h).
+//
+// The reference's facade keeps `std::unique_ptr<RayZath::Cuda::Engine> m_cuda_engine` (rayzath.hpp:31) and calls
+//   m_cuda_engine->renderWorld(*m_world, m_render_config, block, sync)      rayzath.cpp:64-90
+//   m_cuda_engine->timingsString()                                          rayzath.cpp:96-113
+// This file defines that class (declaration unchanged: /root/reference/RayZath/cuda_engine.cuh:21-40) and the
+// `RayZath::Cuda::EngineCore` the reference's Camera befriends (camera.hpp:121), so linking it INSTEAD of the
+// reference's cuda_*.cu files replaces the whole CUDA engine while rayzath.hpp, World, RenderConfig, json_loader
+// and the headless entry stay byte-for-byte the reference's. What it replaces:
+//   EngineCore::renderWorld / CopyRenderToHost    cuda_engine_core.cu:32-240
+//   Renderer::renderFunction                      cuda_engine_renderer.cu:73-262
+//   World/Mesh/Instance/...::reconstruct          cuda_world.cu, cuda_instance.cu, cuda_bvh.cuh (-> world_flatten.hpp)
+//
+// Behaviour kept: dirty-flag protocol (world modified -> re-mirror, camera modified -> restart accumulation,
+// flags cleared afterwards), `rpp` passes per call, results written to Camera::m_image_buffer / m_depth_buffer /
+// m_ray_count / m_raycasted_*, errors as RayZath::Cuda::Exception, CUDA init failure -> the facade falls back to
+// the CPU engine (rayzath.cpp:21-28). Behaviour changed (documented in INTEGRATION.md): the call is synchronous
+// for both values of `sync` (the reference pipelines one frame when sync == false); the per-call random seeds of
+// cuda_kernel_data.cu:10-18 become one seed per engine (RZB200_SEED or std::random_device) + the pass counter.
+// Multi-GPU: RZB200_DEVICES="0,1,..." renders one disjoint sample stream per listed device and sums the
+// accumulators in the fused peer resolve (rzb_resolve_peers) on the first device.
+#include "cuda_engine.cuh"
+#include "cuda_exception.hpp"
+
+#include "world_flatten.hpp"
+
+#include <cstdlib>
+#include <map>
+#include <mutex>
+#include <random>
+#include <sstream>
+
+namespace RayZath::Cuda
+{
+	namespace RZ = RayZath::Engine;
+
+	class EngineCore
+	{
+		struct CameraState
+		{
+			std::vector<rzb_ctx*> ctxs; // one per device
+			uint32_t width = 0, height = 0;
+			bool scene_current = false;
+			std::vector<uint8_t> rgba;
+			std::vector<float> depth;
+		};
+		std::mutex m_mtx;
+		std::vector<int> m_devices;
+		std::map<uint32_t, CameraState> m_cameras; // by camera container index
+		uint64_t m_seed = 0;
+		uint64_t m_scene_version = 0;
+		rzb_host::FlatScene m_flat;
+		std::string m_timings;
+
+		[[noreturn]] static void fail(rzb_ctx* ctx, const char* what)
+		{
+			throw Exception(std::string(what) + ": " + rzb_last_error(ctx));
+		}
+		static void check(rzb_ctx* ctx, int rc, const char* what)
+		{
+			if (rc != RZB_OK) fail(ctx, what);
+		}
+
+	public:
+		EngineCore()
+		{
+			if (const char* env = std::getenv("RZB200_DEVICES"))
+			{
+				std::stringstream ss(env);
+				for (std::string tok; std::getline(ss, tok, ',');)
+					if (!tok.empty()) m_devices.push_back(std::atoi(tok.c_str()));
+			}
+			if (m_devices.empty()) m_devices.push_back(0);
+			if (const char* env = std::getenv("RZB200_SEED")) m_seed = std::strtoull(env, nullptr, 0);
+			else
+			{
+				std::random_device rd;
+				m_seed = (uint64_t(rd()) << 32) | rd();
+			}
+			// probe the first device now: a missing GPU must surface from the constructor so that
+			// RayZath::Engine::Engine falls back to the CPU engine
+			rzb_ctx* probe = nullptr;
+			if (rzb_create(m_devices[0], &probe) != RZB_OK) fail(nullptr, "B200 render path unavailable");
+			rzb_destroy(probe);
+		}
+		~EngineCore()
+		{
+			for (auto& [idx, cam] : m_cameras)
+				for (rzb_ctx* c : cam.ctxs) rzb_destroy(c);
+		}
+
+		void renderWorld(RZ::World& hWorld, const RZ::RenderConfig& config)
+		{
+			std::lock_guard<std::mutex> lg(m_mtx);
+
+			// dirty flags, exactly as EngineCore::renderWorld reads them (cuda_engine_core.cu:48-60)
+			const bool world_update = hWorld.stateRegister().IsModified();
+			auto& hCameras = hWorld.container<RZ::ObjectType::Camera>();
+			if (world_update)
+				for (uint32_t i = 0; i < hCameras.count(); i++)
+					if (hCameras[i]) hCameras[i]->stateRegister().RequestUpdate();
+			hWorld.update();
+			hCameras.update();
+
+			if (world_update || m_scene_version == 0)
+			{
+				rzb_host::WorldFlattener(hWorld, m_flat).run();
+				++m_scene_version;
+				for (auto& [idx, cam] : m_cameras) cam.scene_current = false;
+				clearFlags(hWorld);
+			}
+			const rzb_scene scene = m_flat.view();
+
+			for (uint32_t ci = 0; ci < hCameras.count(); ++ci)
+			{
+				const auto& hCamera = hCameras[ci];
+				if (!hCamera || !hCamera->enabled()) continue;
+				CameraState& cs = m_cameras[ci];
+				if (cs.ctxs.empty())
+					for (int dev : m_devices)
+					{
+						rzb_ctx* c = nullptr;
+						if (rzb_create(dev, &c) != RZB_OK) fail(nullptr, "rzb_create");
+						cs.ctxs.push_back(c);
+					}
+				const bool camera_update = hCamera->stateRegister().IsModified() || !cs.scene_current ||
+					cs.width != hCamera->width() || cs.height != hCamera->height();
+				const rzb_camera cam = rzb_host::flattenCamera(*hCamera);
+				for (size_t d = 0; d < cs.ctxs.size(); ++d)
+				{
+					rzb_ctx* c = cs.ctxs[d];
+					if (!cs.scene_current) check(c, rzb_set_scene(c, &scene), "rzb_set_scene");
+					// one disjoint sample stream per device
+					rzb_config cfg = rzb_host::flattenConfig(config, m_seed + 0x9E3779B97F4A7C15ull * (uint64_t(ci) * 64 + d));
+					check(c, rzb_set_config(c, &cfg), "rzb_set_config");
+					if (camera_update)
+					{
+						// camera moved / world changed: restart accumulation (passReset + generateCameraRay + renderFirstPass,
+						// cuda_engine_renderer.cu:87-160)
+						check(c, rzb_set_camera(c, &cam), "rzb_set_camera");
+						check(c, rzb_reset(c), "rzb_reset");
+					}
+					check(c, rzb_render(c, std::max<uint32_t>(config.tracing().rpp(), 1u)), "rzb_render");
+				}
+				cs.scene_current = true;
+				cs.width = hCamera->width();
+				cs.height = hCamera->height();
+				hCamera->stateRegister().MakeUnmodified();
+
+				// copy-back (CopyRenderToHost, cuda_engine_core.cu:163-240)
+				const size_t n = size_t(cs.width) * cs.height;
+				cs.rgba.resize(n * 4);
+				cs.depth.resize(n);
+				uint64_t rays = 0;
+				rzb_ctx* root = cs.ctxs[0];
+				check(root, rzb_resolve_peers(root, cs.ctxs.data() + 1, uint32_t(cs.ctxs.size() - 1), cs.rgba.data(),
+					cs.depth.data(), &rays), "rzb_resolve_peers");
+				hCamera->m_ray_count = rays;
+				hCamera->m_image_buffer.CopyFromMemory(cs.rgba.data(), n * 4, 0, 0);
+				hCamera->m_depth_buffer.CopyFromMemory(cs.depth.data(), n * sizeof(float), 0, 0);
+
+				uint32_t inst = RZB_NO_INDEX, slot = RZB_NO_INDEX;
+				check(root, rzb_raycast(root, &inst, &slot), "rzb_raycast");
+				auto& hInstances = hWorld.container<RZ::ObjectType::Instance>();
+				if (inst < hInstances.count() && hInstances[inst])
+				{
+					hCamera->m_raycasted_instance = hInstances[inst];
+					if (slot < RZ::Instance::materialCapacity()) hCamera->m_raycasted_material = hInstances[inst]->material(slot);
+					else hCamera->m_raycasted_material.release();
+				}
+				else
+				{
+					hCamera->m_raycasted_instance.release();
+					hCamera->m_raycasted_material.release();
+				}
+
+				char buf[1024];
+				if (rzb_timings(root, buf, sizeof(buf)) == RZB_OK) m_timings = buf;
+			}
+			hWorld.stateRegister().MakeUnmodified();
+		}
+		const std::string& timings() const { return m_timings; }
+
+	private:
+		// every reconstruct() of the reference ends with MakeUnmodified() on what it mirrored (e.g. cuda_instance.cu:225,
+		// 281, cuda_world.cu:69-76); the GUI and the CPU engine read the same flags
+		template <RZ::ObjectType T>
+		static void clearContainer(RZ::World& w)
+		{
+			auto& c = w.container<T>();
+			for (uint32_t i = 0; i < c.count(); ++i)
+				if (c[i]) c[i]->stateRegister().MakeUnmodified();
+			c.stateRegister().MakeUnmodified();
+		}
+		static void clearFlags(RZ::World& w)
+		{
+			clearContainer<RZ::ObjectType::Texture>(w);
+			clearContainer<RZ::ObjectType::NormalMap>(w);
+			clearContainer<RZ::ObjectType::MetalnessMap>(w);
+			clearContainer<RZ::ObjectType::RoughnessMap>(w);
+			clearContainer<RZ::ObjectType::EmissionMap>(w);
+			clearContainer<RZ::ObjectType::Material>(w);
+			clearContainer<RZ::ObjectType::Mesh>(w);
+			clearContainer<RZ::ObjectType::SpotLight>(w);
+			clearContainer<RZ::ObjectType::DirectLight>(w);
+			clearContainer<RZ::ObjectType::Instance>(w);
+			w.material().stateRegister().MakeUnmodified();
+			w.defaultMaterial().stateRegister().MakeUnmodified();
+		}
+	};
+
+	Engine::Engine() : m_engine_core(std::make_unique<EngineCore>()) {}
+	Engine::~Engine() = default;
+
+	void Engine::renderWorld(RayZath::Engine::World& hWorld, const RayZath::Engine::RenderConfig& render_config,
+		const bool /*block*/, const bool /*sync*/)
+	{
+		m_engine_core->renderWorld(hWorld, render_config);
+		m_timing_string = m_engine_core->timings();
+	}
+	std::string Engine::timingsString() { return m_timing_string; }
+}
