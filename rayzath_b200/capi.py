@@ -15,7 +15,7 @@ from typing import Dict, Optional
 
 import numpy as np
 
-LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "librzb200.so")
+LIB_PATH = os.environ.get("RZB200_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "librzb200.so")
 
 NO_INDEX = 0xFFFFFFFF
 FLAG_NONE = 0

@@ -79,6 +79,7 @@ struct rzb_ctx
 	uint64_t passes = 0, launches = 0;
 	float last_render_ms = 0.0f, last_trace_ms = 0.0f, last_shade_ms = 0.0f, last_shadow_ms = 0.0f;
 	int trace_grid = 0, shadow_grid = 0, rays_grid = 0, any_grid = 0;
+	bool debug_sync = false;       // RZB200_DEBUG_SYNC: synchronise after every kernel of rzb_render and name the one that faulted
 	uint32_t refill_threshold = 1; // RZB200_REFILL: idle lanes per warp that trigger a work fetch (tuning knob)
 };
 
@@ -243,6 +244,7 @@ extern "C" int rzb_create(int device, rzb_ctx** out)
 	cudaMemsetAsync(ctx->d_work, 0, 128, ctx->stream);
 	if ((e = cudaMalloc(reinterpret_cast<void**>(&ctx->d_counters), 256)) != cudaSuccess) { delete ctx; return cudaFail(nullptr, e, "cudaMalloc(counters)"); }
 	cudaMemsetAsync(ctx->d_counters, 0, 256, ctx->stream);
+	ctx->debug_sync = std::getenv("RZB200_DEBUG_SYNC") != nullptr;
 	if (const char* env = std::getenv("RZB200_REFILL")) ctx->refill_threshold = std::min(32u, std::max(1u, uint32_t(std::atoi(env))));
 	ctx->trace_grid = gridFor(ctx, reinterpret_cast<const void*>(&k_trace_paths<false>), kTraceBlock);
 	ctx->shadow_grid = gridFor(ctx, reinterpret_cast<const void*>(&k_trace_shadow<false>), kTraceBlock);
@@ -600,8 +602,18 @@ extern "C" int rzb_render(rzb_ctx* ctx, uint32_t passes)
 		if (timed) cudaEventRecord(ev[0], ctx->stream);
 		if (count) k_trace_paths<true><<<ctx->trace_grid, kTraceBlock, 0, ctx->stream>>>(ctx->sc, f);
 		else k_trace_paths<false><<<ctx->trace_grid, kTraceBlock, 0, ctx->stream>>>(ctx->sc, f);
+		if (ctx->debug_sync)
+		{
+			const cudaError_t e = cudaStreamSynchronize(ctx->stream);
+			if (e != cudaSuccess) return cudaFail(ctx, e, ("k_trace_paths, pass " + std::to_string(ctx->passes)).c_str());
+		}
 		if (timed) cudaEventRecord(ev[1], ctx->stream);
 		k_shade<<<(f.n_slots + 127) / 128, 128, 0, ctx->stream>>>(ctx->sc, f);
+		if (ctx->debug_sync)
+		{
+			const cudaError_t e = cudaStreamSynchronize(ctx->stream);
+			if (e != cudaSuccess) return cudaFail(ctx, e, ("k_shade, pass " + std::to_string(ctx->passes)).c_str());
+		}
 		if (timed) cudaEventRecord(ev[2], ctx->stream);
 		ctx->launches += 2;
 		if (lights)
@@ -609,6 +621,11 @@ extern "C" int rzb_render(rzb_ctx* ctx, uint32_t passes)
 			if (count) k_trace_shadow<true><<<ctx->shadow_grid, kTraceBlock, 0, ctx->stream>>>(ctx->sc, f);
 			else k_trace_shadow<false><<<ctx->shadow_grid, kTraceBlock, 0, ctx->stream>>>(ctx->sc, f);
 			ctx->launches += 1;
+			if (ctx->debug_sync)
+			{
+				const cudaError_t e = cudaStreamSynchronize(ctx->stream);
+				if (e != cudaSuccess) return cudaFail(ctx, e, ("k_trace_shadow, pass " + std::to_string(ctx->passes)).c_str());
+			}
 		}
 		if (timed)
 		{

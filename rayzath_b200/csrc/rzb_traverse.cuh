@@ -35,7 +35,12 @@ namespace rzb
 	};
 
 	// exact predicate (the reference's arithmetic)
-	__device__ __noinline__ SlabResult slab_exact(const float4 n0, const float4 n1, const V3 o, const V3 d,
+#ifndef RZB_SLAB_EXACT_INLINE
+#define RZB_SLAB_EXACT_ATTR __noinline__
+#else
+#define RZB_SLAB_EXACT_ATTR __forceinline__
+#endif
+	__device__ RZB_SLAB_EXACT_ATTR SlabResult slab_exact(const float4 n0, const float4 n1, const V3 o, const V3 d,
 		const float near_, const float far_)
 	{
 		SlabResult r;

@@ -24,6 +24,7 @@
 
 #include "world_flatten.hpp"
 
+#include <cstdio>
 #include <cstdlib>
 #include <map>
 #include <mutex>
@@ -85,6 +86,9 @@ namespace RayZath::Cuda
 		}
 		~EngineCore()
 		{
+			// RZB200_VERBOSE: leave a trace on stderr that the B200 path (not the CPU fallback) rendered
+			if (std::getenv("RZB200_VERBOSE") && !m_timings.empty())
+				std::fprintf(stderr, "[rzb200] %zu device(s), seed %llu\n%s", m_devices.size(), (unsigned long long)m_seed, m_timings.c_str());
 			for (auto& [idx, cam] : m_cameras)
 				for (rzb_ctx* c : cam.ctxs) rzb_destroy(c);
 		}

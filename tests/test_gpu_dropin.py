@@ -1,0 +1,37 @@
+"""The C++ drop-in: the reference's own headless runner (Application/headless.cpp, compiled in place) with
+RayZath::Cuda::Engine implemented by rayzath_b200/host/cuda_engine_b200.cpp on the C ABI. Needs the prebuilt
+rayzath_b200/host/_build/rz_b200_headless (built where /root/reference exists; it travels to the GPU box)."""
+import json
+import os
+import re
+import subprocess
+
+import pytest
+
+from rayzath_b200 import scenes
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+BIN = os.path.join(ROOT, "rayzath_b200", "host", "_build", "rz_b200_headless")
+
+
+@pytest.mark.skipif(not os.path.exists(BIN), reason="drop-in binary not built (needs /root/reference at build time)")
+def test_headless_runner_renders_on_the_b200_path(tmp_path):
+    w = scenes.materials_scene(resolution=(320, 180), res=24)
+    w.save_reference(str(tmp_path), "scene")
+    json.dump({"tasks": [{"scene path": "scene.json", "engine": ["CUDAGPU"], "rpp": 200, "timeout": 30.0}]},
+              open(tmp_path / "tasks.json", "w"))
+    os.makedirs(tmp_path / "report")
+    env = dict(os.environ, RZB200_VERBOSE="1", RZB200_SEED="7")
+    r = subprocess.run([BIN, "--headless", "tasks.json", "report", "-r"], cwd=tmp_path, env=env, capture_output=True,
+                       text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert "[rzb200]" in r.stderr and "B200 wavefront engine" in r.stderr, "the CUDA engine did not run: " + r.stderr[-500:]
+    reports = [os.path.join(dp, f) for dp, _, fs in os.walk(tmp_path / "report") for f in fs if f == "report.txt"]
+    assert len(reports) == 1
+    text = open(reports[0]).read()
+    assert "CUDAGPU" in text
+    m = re.search(r"traced\s+([0-9.]+)([kMGT]?)", text)
+    assert m, text
+    images = [f for dp, _, fs in os.walk(tmp_path / "report") for f in fs if f.lower().endswith((".png", ".jpg"))]
+    assert images, "no rendered image saved"
