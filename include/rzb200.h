@@ -227,6 +227,7 @@ typedef struct rzb_work_counters
 	uint64_t shadow_top_nodes, shadow_instances, shadow_mesh_nodes, shadow_triangles;
 	uint64_t shadow_rays;
 	uint64_t segments; /* closest-hit queries = passes * pixels */
+	uint64_t invalid_rays; /* path segments generated with a non-finite origin or direction */
 } rzb_work_counters;
 
 /* ---- context ---- */
@@ -290,6 +291,10 @@ int rzb_trace_closest(rzb_ctx* ctx, const float* origins, const float* direction
  * after enqueueing on the context stream; elapsed_ms_or_null forces a sync and reports CUDA-event time. */
 int rzb_trace_closest_device(rzb_ctx* ctx, const void* rays_o_near, const void* rays_d_far,
 	uint32_t n, void* hits_out_device, float* elapsed_ms_or_null);
+/* Same, with the counting kernel: each 32-byte device hit record additionally carries the ray's own work in its
+ * words 5 and 6 (pair steps, triangle tests). Measurement aid. */
+int rzb_trace_closest_device_counted(rzb_ctx* ctx, const void* rays_o_near, const void* rays_d_far,
+	uint32_t n, void* hits_out_device);
 /* Shadow query: World::anyIntersection (cuda_world.cuh:101-104); mask_out[n][4] = RGBA shadow mask. */
 int rzb_trace_any(rzb_ctx* ctx, const float* origins, const float* directions,
 	const float* near_far, uint32_t n, float* mask_out);

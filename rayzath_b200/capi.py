@@ -57,7 +57,8 @@ render_stats_dtype = np.dtype([("passes", u8), ("ray_count", u8), ("shadow_rays"
 
 work_counters_dtype = np.dtype([(n, u8) for n in (
     "closest_top_nodes", "closest_instances", "closest_mesh_nodes", "closest_triangles",
-    "shadow_top_nodes", "shadow_instances", "shadow_mesh_nodes", "shadow_triangles", "shadow_rays", "segments")])
+    "shadow_top_nodes", "shadow_instances", "shadow_mesh_nodes", "shadow_triangles", "shadow_rays", "segments",
+    "invalid_rays")])
 
 EXPECTED_SIZES = {
     "rzb_node": (node_dtype, 32), "rzb_triangle": (triangle_dtype, 112), "rzb_mesh": (mesh_dtype, 16),
@@ -114,6 +115,7 @@ SYMBOLS = {
     "rzb_timings": (C.c_int, [_P, C.c_char_p, C.c_size_t]),
     "rzb_trace_closest": (C.c_int, [_P, _P, _P, _P, C.c_uint32, _P, _P]),
     "rzb_trace_closest_device": (C.c_int, [_P, _P, _P, C.c_uint32, _P, C.POINTER(C.c_float)]),
+    "rzb_trace_closest_device_counted": (C.c_int, [_P, _P, _P, C.c_uint32, _P]),
     "rzb_trace_any": (C.c_int, [_P, _P, _P, _P, C.c_uint32, _P]),
     "rzb_generate_camera_rays": (C.c_int, [_P, _P, _P, _P]),
     "rzb_build_mesh_bvh": (C.c_int, [_P, C.c_uint32, _P, C.c_uint32, _P, C.c_uint32, C.POINTER(C.c_uint32), _P]),
@@ -421,6 +423,9 @@ class Context:
         self._check(self._l.rzb_trace_closest_device(self._h, o_near_ptr, d_far_ptr, n, hits_ptr,
                                                      C.byref(ms) if timed else None))
         return ms.value
+
+    def trace_closest_device_counted(self, o_near_ptr: int, d_far_ptr: int, n: int, hits_ptr: int):
+        self._check(self._l.rzb_trace_closest_device_counted(self._h, o_near_ptr, d_far_ptr, n, hits_ptr))
 
     def trace_any(self, origins, directions, near_far) -> np.ndarray:
         o, d, nf = _c(origins, f4).reshape(-1, 3), _c(directions, f4).reshape(-1, 3), _c(near_far, f4).reshape(-1, 2)

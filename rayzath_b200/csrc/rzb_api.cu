@@ -80,7 +80,6 @@ struct rzb_ctx
 	float last_render_ms = 0.0f, last_trace_ms = 0.0f, last_shade_ms = 0.0f, last_shadow_ms = 0.0f;
 	int trace_grid = 0, shadow_grid = 0, rays_grid = 0, any_grid = 0;
 	bool debug_sync = false;       // RZB200_DEBUG_SYNC: synchronise after every kernel of rzb_render and name the one that faulted
-	uint32_t refill_threshold = 1; // RZB200_REFILL: idle lanes per warp that trigger a work fetch (tuning knob)
 };
 
 namespace
@@ -166,9 +165,9 @@ namespace
 		DFrame& f = ctx->frame;
 		f = DFrame{};
 		f.cam = makeDeviceCamera(ctx->cam);
-		f.tiles_x = (ctx->cam.width + 7u) / 8u;
-		f.tiles_y = (ctx->cam.height + 3u) / 4u;
-		f.n_slots = f.tiles_x * f.tiles_y * 32u;
+		f.tiles_x = (ctx->cam.width + 15u) / 16u;  // 16x16-pixel chunks of 256 slots
+		f.tiles_y = (ctx->cam.height + 15u) / 16u;
+		f.n_slots = f.tiles_x * f.tiles_y * 256u;
 		const size_t n_pixels = size_t(ctx->cam.width) * ctx->cam.height;
 		auto alloc = [&](void** p, size_t bytes) -> int {
 			RZB_CUDA(ctx, cudaMalloc(p, bytes));
@@ -245,7 +244,6 @@ extern "C" int rzb_create(int device, rzb_ctx** out)
 	if ((e = cudaMalloc(reinterpret_cast<void**>(&ctx->d_counters), 256)) != cudaSuccess) { delete ctx; return cudaFail(nullptr, e, "cudaMalloc(counters)"); }
 	cudaMemsetAsync(ctx->d_counters, 0, 256, ctx->stream);
 	ctx->debug_sync = std::getenv("RZB200_DEBUG_SYNC") != nullptr;
-	if (const char* env = std::getenv("RZB200_REFILL")) ctx->refill_threshold = std::min(32u, std::max(1u, uint32_t(std::atoi(env))));
 	ctx->trace_grid = gridFor(ctx, reinterpret_cast<const void*>(&k_trace_paths<false>), kTraceBlock);
 	ctx->shadow_grid = gridFor(ctx, reinterpret_cast<const void*>(&k_trace_shadow<false>), kTraceBlock);
 	ctx->rays_grid = gridFor(ctx, reinterpret_cast<const void*>(&k_trace_rays<false>), kTraceBlock);
@@ -548,9 +546,10 @@ extern "C" int rzb_reset(rzb_ctx* ctx)
 	DeviceGuard guard(ctx->device);
 	DFrame& f = ctx->frame;
 	f.cam = makeDeviceCamera(ctx->cam);
-	k_reset<<<(f.n_slots + 255) / 256, 256, 0, ctx->stream>>>(f, ctx->sc.world_material);
+	f.counters = ctx->d_counters;
+	RZB_CUDA(ctx, cudaMemsetAsync(ctx->d_counters, 0, 256, ctx->stream));
+	k_reset<<<(f.n_slots + 127) / 128, 128, 0, ctx->stream>>>(f, ctx->sc.world_material);
 	RZB_CUDA(ctx, cudaGetLastError());
-	RZB_CUDA(ctx, cudaMemsetAsync(ctx->d_counters, 0, 64, ctx->stream));
 	RZB_CUDA(ctx, cudaMemsetAsync(ctx->d_work, 0, 128, ctx->stream));
 	ctx->counted_segments = 0;
 	ctx->launches += 1;
@@ -577,7 +576,6 @@ extern "C" int rzb_render(rzb_ctx* ctx, uint32_t passes)
 	f.direct_samples = ctx->cfg.direct_light_samples;
 	f.spot_samples = ctx->cfg.spot_light_samples;
 	f.seed = ctx->cfg.seed;
-	f.refill_threshold = ctx->refill_threshold;
 	const bool lights = (ctx->sc.direct_light_count && f.direct_samples) || (ctx->sc.spot_light_count && f.spot_samples);
 	const bool count = (ctx->cfg.flags & RZB_FLAG_COUNT_WORK) != 0u;
 	f.work = ctx->d_work;
@@ -798,6 +796,7 @@ extern "C" int rzb_get_work_counters(rzb_ctx* ctx, rzb_work_counters* out)
 	out->shadow_top_nodes = h[4]; out->shadow_instances = h[5]; out->shadow_mesh_nodes = h[6]; out->shadow_triangles = h[7];
 	out->shadow_rays = h[8];
 	out->segments = ctx->counted_segments;
+	out->invalid_rays = h[9];
 	return RZB_OK;
 }
 
@@ -884,7 +883,7 @@ extern "C" int rzb_trace_closest_device(rzb_ctx* ctx, const void* rays_o_near, c
 	if (elapsed_ms) RZB_CUDA(ctx, cudaEventRecord(ctx->ev_begin, ctx->stream));
 	k_trace_rays<false><<<ctx->rays_grid, kTraceBlock, 0, ctx->stream>>>(ctx->sc,
 		static_cast<const float4*>(rays_o_near), static_cast<const float4*>(rays_d_far), n,
-		static_cast<DHit*>(hits_out_device), ctx->d_counters + 8, nullptr, ctx->refill_threshold);
+		static_cast<DHit*>(hits_out_device), ctx->d_counters + 8, nullptr);
 	ctx->launches += 1;
 	RZB_CUDA(ctx, cudaGetLastError());
 	if (elapsed_ms)
@@ -893,6 +892,23 @@ extern "C" int rzb_trace_closest_device(rzb_ctx* ctx, const void* rays_o_near, c
 		RZB_CUDA(ctx, cudaEventSynchronize(ctx->ev_end));
 		RZB_CUDA(ctx, cudaEventElapsedTime(elapsed_ms, ctx->ev_begin, ctx->ev_end));
 	}
+	return RZB_OK;
+}
+
+extern "C" int rzb_trace_closest_device_counted(rzb_ctx* ctx, const void* rays_o_near, const void* rays_d_far,
+	uint32_t n, void* hits_out_device)
+{
+	if (!ctx || !rays_o_near || !rays_d_far || !hits_out_device) return fail(ctx, RZB_ERR_INVALID, "rzb_trace_closest_device_counted: NULL argument");
+	if (!ctx->has_scene) return fail(ctx, RZB_ERR_STATE, "rzb_trace_closest_device_counted: no scene");
+	DeviceGuard guard(ctx->device);
+	unsigned long long* d_stats = reinterpret_cast<unsigned long long*>(ctx->d_counters + 10);
+	RZB_CUDA(ctx, cudaMemsetAsync(ctx->d_counters + 8, 0, 40, ctx->stream));
+	k_trace_rays<true><<<ctx->rays_grid, kTraceBlock, 0, ctx->stream>>>(ctx->sc,
+		static_cast<const float4*>(rays_o_near), static_cast<const float4*>(rays_d_far), n,
+		static_cast<DHit*>(hits_out_device), ctx->d_counters + 8, d_stats);
+	ctx->launches += 1;
+	RZB_CUDA(ctx, cudaGetLastError());
+	RZB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
 	return RZB_OK;
 }
 
@@ -912,11 +928,11 @@ extern "C" int rzb_trace_closest(rzb_ctx* ctx, const float* origins, const float
 	if (stats)
 		k_trace_rays<true><<<ctx->rays_grid, kTraceBlock, 0, ctx->stream>>>(ctx->sc,
 			static_cast<const float4*>(ctx->scratch[0].ptr), static_cast<const float4*>(ctx->scratch[1].ptr), n,
-			static_cast<DHit*>(ctx->scratch[2].ptr), ctx->d_counters + 8, d_stats, ctx->refill_threshold);
+			static_cast<DHit*>(ctx->scratch[2].ptr), ctx->d_counters + 8, d_stats);
 	else
 		k_trace_rays<false><<<ctx->rays_grid, kTraceBlock, 0, ctx->stream>>>(ctx->sc,
 			static_cast<const float4*>(ctx->scratch[0].ptr), static_cast<const float4*>(ctx->scratch[1].ptr), n,
-			static_cast<DHit*>(ctx->scratch[2].ptr), ctx->d_counters + 8, nullptr, ctx->refill_threshold);
+			static_cast<DHit*>(ctx->scratch[2].ptr), ctx->d_counters + 8, nullptr);
 	k_convert_hits<<<(n + 255) / 256, 256, 0, ctx->stream>>>(ctx->sc, static_cast<const DHit*>(ctx->scratch[2].ptr),
 		static_cast<rzb_hit*>(ctx->scratch[3].ptr), n);
 	ctx->launches += 2;
@@ -946,7 +962,7 @@ extern "C" int rzb_trace_any(rzb_ctx* ctx, const float* origins, const float* di
 	RZB_CUDA(ctx, cudaMemsetAsync(ctx->d_counters + 8, 0, 4, ctx->stream));
 	k_trace_any_rays<<<ctx->any_grid, kTraceBlock, 0, ctx->stream>>>(ctx->sc,
 		static_cast<const float4*>(ctx->scratch[0].ptr), static_cast<const float4*>(ctx->scratch[1].ptr), n,
-		static_cast<float4*>(ctx->scratch[2].ptr), ctx->d_counters + 8, ctx->refill_threshold);
+		static_cast<float4*>(ctx->scratch[2].ptr), ctx->d_counters + 8);
 	ctx->launches += 1;
 	RZB_CUDA(ctx, cudaGetLastError());
 	RZB_CUDA(ctx, cudaMemcpyAsync(mask_out, ctx->scratch[2].ptr, size_t(n) * 16, cudaMemcpyDeviceToHost, ctx->stream));

@@ -44,16 +44,18 @@ namespace rzb
 		unsigned long long* work; // RZB_FLAG_COUNT_WORK: [0..3] closest top/inst/mesh/tri, [4..7] shadow, [8] shadow rays
 		uint32_t shadow_capacity;
 		uint32_t pass_index;
-		uint32_t refill_threshold; // idle lanes per warp that trigger a work fetch
+
 		uint32_t max_depth, direct_samples, spot_samples;
 		uint64_t seed;
 	};
 
+	// slot -> pixel: 256-slot chunks cover 16x16 pixels (8 tiles of 8x4, 2 across x 4 down); a warp works through one
+	// chunk at a time, so all its rays start in one small screen region
 	__device__ __forceinline__ bool slot_to_pixel(const DFrame& f, uint32_t slot, uint32_t& x, uint32_t& y)
 	{
-		const uint32_t tile = slot >> 5, within = slot & 31u;
-		x = (tile % f.tiles_x) * 8u + (within & 7u);
-		y = (tile / f.tiles_x) * 4u + (within >> 3);
+		const uint32_t chunk = slot >> 8, tile = (slot >> 5) & 7u, within = slot & 31u;
+		x = (chunk % f.tiles_x) * 16u + (tile & 1u) * 8u + (within & 7u);
+		y = (chunk / f.tiles_x) * 16u + (tile >> 1) * 4u + (within >> 3);
 		return x < f.cam.width && y < f.cam.height;
 	}
 
@@ -121,40 +123,32 @@ namespace rzb
 	}
 
 	// ---------------------------------------------------------------- k_reset
-	__global__ void k_reset(DFrame f, uint32_t world_material)
+	__global__ void __launch_bounds__(128) k_reset(DFrame f, uint32_t world_material)
 	{
 		const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
-		if (slot >= f.n_slots) return;
-		uint32_t x, y;
-		if (!slot_to_pixel(f, slot, x, y)) return;
-		V3 o, d;
-		camera_simple_ray(f.cam, x, y, o, d);
-		f.st_o[slot] = make_float4(o.x, o.y, o.z, __uint_as_float(world_material << kMediumShift));
-		f.st_d[slot] = make_float4(d.x, d.y, d.z, 1.0f);
-		f.st_c[slot] = make_float2(1.0f, 1.0f);
-		const size_t p = size_t(y) * f.cam.width + x;
-		f.accum[p] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-		f.depth[p] = 0.0f;
+		uint32_t x = 0, y = 0;
+		const bool valid = slot < f.n_slots && slot_to_pixel(f, slot, x, y);
+		if (valid)
+		{
+			V3 o, d;
+			camera_simple_ray(f.cam, x, y, o, d);
+			f.st_o[slot] = make_float4(o.x, o.y, o.z, __uint_as_float(world_material << kMediumShift));
+			f.st_d[slot] = make_float4(d.x, d.y, d.z, 1.0f);
+			f.st_c[slot] = make_float2(1.0f, 1.0f);
+			const size_t p = size_t(y) * f.cam.width + x;
+			f.accum[p] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+			f.depth[p] = 0.0f;
+		}
 	}
 
-	// ---------------------------------------------------------------- dynamic work fetch
-	// Lanes whose ray is finished pull the next index from a global counter: one ballot + one atomic per warp and
-	// refill. `exhausted` becomes (warp-uniformly) true once the counter has passed `n`. Returns kNoIndex for lanes
-	// that got nothing. The refill happens when at least `threshold` lanes are idle (or the warp is completely idle).
-	__device__ __forceinline__ uint32_t warp_fetch(uint32_t* counter, const uint32_t n, const bool idle, bool& exhausted,
-		const uint32_t threshold)
+	// ---------------------------------------------------------------- work distribution
+	// Persistent warps pull batches of 32 consecutive work items with one atomic. Whole-warp batches of neighbouring
+	// slots beat every finer-grained scheme that was measured (see rzb_traverse.cuh header).
+	__device__ __forceinline__ uint32_t warp_batch(uint32_t* counter)
 	{
-		const uint32_t lane = threadIdx.x & 31u;
-		const uint32_t need = __ballot_sync(0xFFFFFFFFu, idle);
-		const uint32_t count = __popc(need);
-		if (exhausted || count == 0u || (count < threshold && count != 32u)) return kNoIndex;
-		uint32_t base = 0;
-		if (lane == 0u) base = atomicAdd(counter, count);
-		base = __shfl_sync(0xFFFFFFFFu, base, 0);
-		if (base + count >= n) exhausted = true;
-		if (!idle) return kNoIndex;
-		const uint32_t idx = base + __popc(need & ((1u << lane) - 1u));
-		return idx < n ? idx : kNoIndex;
+		uint32_t base = 0u;
+		if ((threadIdx.x & 31u) == 0u) base = atomicAdd(counter, 32u);
+		return __shfl_sync(0xFFFFFFFFu, base, 0);
 	}
 
 	// ---------------------------------------------------------------- k_trace_paths
@@ -172,59 +166,44 @@ namespace rzb
 	}
 
 	template <bool STATS>
-	__global__ void __launch_bounds__(kTraceBlock) k_trace_paths(DScene sc, DFrame f)
+	__global__ void __launch_bounds__(kTraceBlock, 6) k_trace_paths(DScene sc, DFrame f)
 	{
 		__shared__ uint2 smem_stack[kSmemStack * kTraceBlock];
+		__shared__ ParkedRay smem_park[kTraceBlock];
 		Stack st = make_stack(smem_stack);
+		ParkedRay& park = smem_park[threadIdx.x];
 		TraceCounters cnt{0u, 0u, 0u, 0u};
-		Traversal<false> tv;
-		tv.state = kTravDone;
-		uint32_t slot = kNoIndex, flags = 0u;
-		bool exhausted = false;
 		for (;;)
 		{
-			// retire finished rays
-			if (tv.done() && slot != kNoIndex)
-			{
-				uint32_t tri_bits = flags | (tv.ext ? kHitExternalBit : 0u);
-				tri_bits |= (tv.hit_tri == kNoIndex) ? kHitTriMask : (tv.hit_tri & kHitTriMask);
-				f.hit_a[slot] = make_float4(tv.wfar, tv.b1, tv.b2, __uint_as_float(tri_bits));
-				f.hit_inst[slot] = tv.hit_inst;
-				slot = kNoIndex;
-			}
-			const uint32_t next = warp_fetch(&f.counters[0], f.n_slots, tv.done(), exhausted, f.refill_threshold);
+			const uint32_t base = warp_batch(&f.counters[0]);
+			if (base >= f.n_slots) break;
+			const uint32_t slot = base + (threadIdx.x & 31u);
 			uint32_t x, y;
-			if (next != kNoIndex && slot_to_pixel(f, next, x, y))
+			if (slot >= f.n_slots || !slot_to_pixel(f, slot, x, y)) continue;
+			const float4 so = f.st_o[slot];
+			const float4 sd = f.st_d[slot];
+			const uint32_t bits = __float_as_uint(so.w);
+			const uint32_t depth = bits & 0xFFu, medium = bits >> kMediumShift;
+			float near_ = 0.0f, far_ = kFltMax;
+			if (depth == 0u) { near_ = f.cam.near_; far_ = f.cam.far_; }
+			uint32_t flags = 0u;
+			// World::closestIntersection: free flight in the current medium first (cuda_material.cuh:141-159)
+			if (!(sc.flags & RZB_FLAG_CPU_SEMANTICS))
 			{
-				slot = next;
-				const float4 so = f.st_o[slot];
-				const float4 sd = f.st_d[slot];
-				const uint32_t bits = __float_as_uint(so.w);
-				const uint32_t depth = bits & 0xFFu, medium = bits >> kMediumShift;
-				float near_ = 0.0f, far_ = kFltMax;
-				if (depth == 0u) { near_ = f.cam.near_; far_ = f.cam.far_; }
-				flags = 0u;
-				// World::closestIntersection: free flight in the current medium first (cuda_material.cuh:141-159)
-				if (!(sc.flags & RZB_FLAG_CPU_SEMANTICS))
+				const float sigma = sc.materials[medium].scattering;
+				if (sigma > 1.0e-4f)
 				{
-					const float sigma = sc.materials[medium].scattering;
-					if (sigma > 1.0e-4f)
-					{
-						Rng rng(f.seed, slot, f.pass_index);
-						const float dist = (-__logf(rng.next() + 1.0e-4f)) / sigma;
-						if (dist < far_) { far_ = dist; flags |= kHitScatterBit; }
-					}
+					Rng rng(f.seed, slot, f.pass_index);
+					const float dist = (-__logf(rng.next() + 1.0e-4f)) / sigma;
+					if (dist < far_) { far_ = dist; flags |= kHitScatterBit; }
 				}
-				tv.begin<STATS>(sc, v3(so.x, so.y, so.z), v3(sd.x, sd.y, sd.z), near_, far_, st, cnt);
 			}
-			if (__all_sync(0xFFFFFFFFu, tv.done() && slot == kNoIndex))
-			{
-				if (exhausted) break;
-				continue;
-			}
-			tv.inner_phase<STATS>(sc, st, cnt);
-			tv.leaf_phase<STATS>(sc, st, cnt);
-			tv.transition_phase<STATS>(sc, st, cnt);
+			RayResult r;
+			trace_ray<false, STATS>(sc, v3(so.x, so.y, so.z), v3(sd.x, sd.y, sd.z), near_, far_, st, park, cnt, r);
+			uint32_t tri_bits = flags | (r.external ? kHitExternalBit : 0u);
+			tri_bits |= (r.tri == kNoIndex) ? kHitTriMask : (r.tri & kHitTriMask);
+			f.hit_a[slot] = make_float4(r.t, r.b1, r.b2, __uint_as_float(tri_bits));
+			f.hit_inst[slot] = r.inst;
 		}
 		if (STATS) flush_counters(cnt, f.work);
 	}
@@ -426,72 +405,59 @@ namespace rzb
 			thr = thr + (thr * s.color - thr) * s.tint_factor;
 			path_continues = depth < f.max_depth;
 		}
-		if (!valid) return;
-
 		// ---- epilogue (cuda_render_kernel.cu:98-120)
-		const size_t p = size_t(y) * f.cam.width + x;
-		float4 acc = f.accum[p];
-		acc.x += final_color.x; acc.y += final_color.y; acc.z += final_color.z;
-		acc.w += path_continues ? 0.0f : 1.0f;
-		f.accum[p] = acc;
-		if (f.pass_index == 0u) f.depth[p] = far_;
-
-		if (!path_continues)
+		if (valid)
 		{
-			camera_generate_ray(f.cam, x, y, rng, next_o, next_d);
-			medium = sc.world_material;
-			thr = f3(1.0f, 1.0f, 1.0f);
-			depth = 0u;
+			const size_t p = size_t(y) * f.cam.width + x;
+			float4 acc = f.accum[p];
+			acc.x += final_color.x; acc.y += final_color.y; acc.z += final_color.z;
+			acc.w += path_continues ? 0.0f : 1.0f;
+			f.accum[p] = acc;
+			if (f.pass_index == 0u) f.depth[p] = far_;
+
+			if (!path_continues)
+			{
+				camera_generate_ray(f.cam, x, y, rng, next_o, next_d);
+				medium = sc.world_material;
+				thr = f3(1.0f, 1.0f, 1.0f);
+				depth = 0u;
+			}
+			if ((sc.flags & RZB_FLAG_COUNT_WORK) && !isfinite(next_o.x + next_o.y + next_o.z + next_d.x + next_d.y + next_d.z))
+				atomicAdd(f.work + 9, 1ull); // rays with a non-finite origin or direction (they would walk the whole tree)
+			f.st_o[slot] = make_float4(next_o.x, next_o.y, next_o.z, __uint_as_float((medium << kMediumShift) | depth));
+			f.st_d[slot] = make_float4(next_d.x, next_d.y, next_d.z, thr.x);
+			f.st_c[slot] = make_float2(thr.y, thr.z);
 		}
-		f.st_o[slot] = make_float4(next_o.x, next_o.y, next_o.z, __uint_as_float((medium << kMediumShift) | depth));
-		f.st_d[slot] = make_float4(next_d.x, next_d.y, next_d.z, thr.x);
-		f.st_c[slot] = make_float2(thr.y, thr.z);
 	}
 
 	// ---------------------------------------------------------------- k_trace_shadow
 	template <bool STATS>
-	__global__ void __launch_bounds__(kTraceBlock) k_trace_shadow(DScene sc, DFrame f)
+	__global__ void __launch_bounds__(kTraceBlock, 6) k_trace_shadow(DScene sc, DFrame f)
 	{
 		__shared__ uint2 smem_stack[kSmemStack * kTraceBlock];
+		__shared__ ParkedRay smem_park[kTraceBlock];
 		Stack st = make_stack(smem_stack);
+		ParkedRay& park = smem_park[threadIdx.x];
 		const uint32_t n = min(f.counters[1], f.shadow_capacity);
 		TraceCounters cnt{0u, 0u, 0u, 0u};
 		if (STATS && blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(f.work + 8, (unsigned long long)n);
-		Traversal<true> tv;
-		tv.state = kTravDone;
-		uint32_t item = kNoIndex;
-		bool exhausted = false;
 		for (;;)
 		{
-			if (tv.done() && item != kNoIndex)
-			{
-				const float w = tv.mask.w;
-				if (w > 0.0f)
-				{
-					const float4 c = f.sh_c[item];
-					float* a = reinterpret_cast<float*>(f.accum + __float_as_uint(f.sh_d[item].w));
-					atomicAdd(a + 0, c.x * tv.mask.x * w);
-					atomicAdd(a + 1, c.y * tv.mask.y * w);
-					atomicAdd(a + 2, c.z * tv.mask.z * w);
-				}
-				item = kNoIndex;
-			}
-			const uint32_t next = warp_fetch(&f.counters[2], n, tv.done(), exhausted, f.refill_threshold);
-			if (next != kNoIndex)
-			{
-				item = next;
-				const float4 o = f.sh_o[item];
-				const float4 d = f.sh_d[item];
-				tv.begin<STATS>(sc, v3(o.x, o.y, o.z), v3(d.x, d.y, d.z), 0.0f, o.w, st, cnt);
-			}
-			if (__all_sync(0xFFFFFFFFu, tv.done() && item == kNoIndex))
-			{
-				if (exhausted) break;
-				continue;
-			}
-			tv.inner_phase<STATS>(sc, st, cnt);
-			tv.leaf_phase<STATS>(sc, st, cnt);
-			tv.transition_phase<STATS>(sc, st, cnt);
+			const uint32_t base = warp_batch(&f.counters[2]);
+			if (base >= n) break;
+			const uint32_t i = base + (threadIdx.x & 31u);
+			if (i >= n) continue;
+			const float4 o = f.sh_o[i];
+			const float4 d = f.sh_d[i];
+			RayResult r;
+			trace_ray<true, STATS>(sc, v3(o.x, o.y, o.z), v3(d.x, d.y, d.z), 0.0f, o.w, st, park, cnt, r);
+			const float w = r.mask.w;
+			if (w <= 0.0f) continue;
+			const float4 c = f.sh_c[i];
+			float* a = reinterpret_cast<float*>(f.accum + __float_as_uint(d.w));
+			atomicAdd(a + 0, c.x * r.mask.x * w);
+			atomicAdd(a + 1, c.y * r.mask.y * w);
+			atomicAdd(a + 2, c.z * r.mask.z * w);
 		}
 		if (STATS) flush_counters(cnt, f.work + 4);
 	}
@@ -544,44 +510,29 @@ namespace rzb
 	static_assert(sizeof(DHit) == 32, "DHit");
 
 	template <bool STATS>
-	__global__ void __launch_bounds__(kTraceBlock) k_trace_rays(DScene sc, const float4* __restrict__ ray_o_near,
+	__global__ void __launch_bounds__(kTraceBlock, 6) k_trace_rays(DScene sc, const float4* __restrict__ ray_o_near,
 		const float4* __restrict__ ray_d_far, uint32_t n, DHit* __restrict__ hits, uint32_t* counter,
-		unsigned long long* stats, uint32_t refill_threshold)
+		unsigned long long* stats)
 	{
 		__shared__ uint2 smem_stack[kSmemStack * kTraceBlock];
+		__shared__ ParkedRay smem_park[kTraceBlock];
 		Stack st = make_stack(smem_stack);
+		ParkedRay& park = smem_park[threadIdx.x];
 		TraceCounters cnt{0u, 0u, 0u, 0u};
-		Traversal<false> tv;
-		tv.state = kTravDone;
-		uint32_t item = kNoIndex;
-		bool exhausted = false;
 		for (;;)
 		{
-			if (tv.done() && item != kNoIndex)
-			{
-				const uint32_t tri_bits = (tv.hit_tri == kNoIndex ? kHitTriMask : (tv.hit_tri & kHitTriMask)) |
-					(tv.ext ? kHitExternalBit : 0u);
-				float4* dst = reinterpret_cast<float4*>(hits + item);
-				dst[0] = make_float4(tv.wfar, tv.b1, tv.b2, __uint_as_float(tri_bits));
-				dst[1] = make_float4(__uint_as_float(tv.hit_inst), 0.0f, 0.0f, 0.0f);
-				item = kNoIndex;
-			}
-			const uint32_t next = warp_fetch(counter, n, tv.done(), exhausted, refill_threshold);
-			if (next != kNoIndex)
-			{
-				item = next;
-				const float4 o = __ldg(ray_o_near + item);
-				const float4 d = __ldg(ray_d_far + item);
-				tv.begin<STATS>(sc, v3(o.x, o.y, o.z), v3(d.x, d.y, d.z), o.w, d.w, st, cnt);
-			}
-			if (__all_sync(0xFFFFFFFFu, tv.done() && item == kNoIndex))
-			{
-				if (exhausted) break;
-				continue;
-			}
-			tv.inner_phase<STATS>(sc, st, cnt);
-			tv.leaf_phase<STATS>(sc, st, cnt);
-			tv.transition_phase<STATS>(sc, st, cnt);
+			const uint32_t base = warp_batch(counter);
+			if (base >= n) break;
+			const uint32_t i = base + (threadIdx.x & 31u);
+			if (i >= n) continue;
+			const float4 o = __ldg(ray_o_near + i);
+			const float4 d = __ldg(ray_d_far + i);
+			RayResult r;
+			trace_ray<false, STATS>(sc, v3(o.x, o.y, o.z), v3(d.x, d.y, d.z), o.w, d.w, st, park, cnt, r);
+			const uint32_t tri_bits = (r.tri == kNoIndex ? kHitTriMask : (r.tri & kHitTriMask)) | (r.external ? kHitExternalBit : 0u);
+			float4* dst = reinterpret_cast<float4*>(hits + i);
+			dst[0] = make_float4(r.t, r.b1, r.b2, __uint_as_float(tri_bits));
+			dst[1] = make_float4(__uint_as_float(r.inst), __uint_as_float(STATS ? r.steps : 0u), __uint_as_float(STATS ? r.tris : 0u), 0.0f);
 		}
 		if (STATS) flush_counters(cnt, stats);
 	}
@@ -608,40 +559,25 @@ namespace rzb
 		out[i] = r;
 	}
 
-	__global__ void __launch_bounds__(kTraceBlock) k_trace_any_rays(DScene sc, const float4* __restrict__ ray_o_near,
-		const float4* __restrict__ ray_d_far, uint32_t n, float4* __restrict__ masks, uint32_t* counter,
-		uint32_t refill_threshold)
+	__global__ void __launch_bounds__(kTraceBlock, 6) k_trace_any_rays(DScene sc, const float4* __restrict__ ray_o_near,
+		const float4* __restrict__ ray_d_far, uint32_t n, float4* __restrict__ masks, uint32_t* counter)
 	{
 		__shared__ uint2 smem_stack[kSmemStack * kTraceBlock];
+		__shared__ ParkedRay smem_park[kTraceBlock];
 		Stack st = make_stack(smem_stack);
+		ParkedRay& park = smem_park[threadIdx.x];
 		TraceCounters cnt{0u, 0u, 0u, 0u};
-		Traversal<true> tv;
-		tv.state = kTravDone;
-		uint32_t item = kNoIndex;
-		bool exhausted = false;
 		for (;;)
 		{
-			if (tv.done() && item != kNoIndex)
-			{
-				masks[item] = tv.mask;
-				item = kNoIndex;
-			}
-			const uint32_t next = warp_fetch(counter, n, tv.done(), exhausted, refill_threshold);
-			if (next != kNoIndex)
-			{
-				item = next;
-				const float4 o = __ldg(ray_o_near + item);
-				const float4 d = __ldg(ray_d_far + item);
-				tv.begin<false>(sc, v3(o.x, o.y, o.z), v3(d.x, d.y, d.z), o.w, d.w, st, cnt);
-			}
-			if (__all_sync(0xFFFFFFFFu, tv.done() && item == kNoIndex))
-			{
-				if (exhausted) break;
-				continue;
-			}
-			tv.inner_phase<false>(sc, st, cnt);
-			tv.leaf_phase<false>(sc, st, cnt);
-			tv.transition_phase<false>(sc, st, cnt);
+			const uint32_t base = warp_batch(counter);
+			if (base >= n) break;
+			const uint32_t i = base + (threadIdx.x & 31u);
+			if (i >= n) continue;
+			const float4 o = __ldg(ray_o_near + i);
+			const float4 d = __ldg(ray_d_far + i);
+			RayResult r;
+			trace_ray<true, false>(sc, v3(o.x, o.y, o.z), v3(d.x, d.y, d.z), o.w, d.w, st, park, cnt, r);
+			masks[i] = r.mask;
 		}
 	}
 

@@ -415,8 +415,8 @@ namespace rzb
 	}
 
 	// ------------------------------------------------------------------ any-hit attenuation (cuda_instance.cuh:105-112)
-	template <bool ANY>
-	__device__ __forceinline__ void Traversal<ANY>::shadow_attenuate(const DScene& sc, const uint32_t i, const float tb1, const float tb2)
+	__device__ __forceinline__ float4 shadow_attenuation(const DScene& sc, const uint32_t i, const float tb1, const float tb2,
+		const uint32_t mat_offset, const uint32_t mat_count)
 	{
 		const float4 c0 = __ldg(sc.tri_cold + 5 * size_t(i));
 		const float4 c1 = __ldg(sc.tri_cold + 5 * size_t(i) + 1);
@@ -427,7 +427,6 @@ namespace rzb
 		const float u = c0.w * b3 + c2.w * tb1 + c4.x * tb2;
 		const float v = c1.w * b3 + c3.w * tb1 + c4.y * tb2;
 		const uint32_t slot = __float_as_uint(__ldg(sc.tri_hot + 3 * size_t(i) + 2).y);
-		const float4 oc = material_opacity_color(sc, sc.materials[instance_material(sc, mat_offset, mat_count, slot)], u, v);
-		mask = make_float4(mask.x * oc.x, mask.y * oc.y, mask.z * oc.z, mask.w * oc.w);
+		return material_opacity_color(sc, sc.materials[instance_material(sc, mat_offset, mat_count, slot)], u, v);
 	}
 }

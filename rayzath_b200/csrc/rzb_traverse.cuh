@@ -8,17 +8,20 @@
 //                    /root/reference/RayZath/cuda_instance.cuh:35-91, cuda_bvh.cuh:114-171 (near child first by ray
 //                    sign on the split axis; the far child sees the range as it is AFTER the near subtree)
 // The control structure is not the reference's:
-//   * sibling pairs are one 64-byte aligned fetch (4 x LDG.128); triangles are a 48-byte hot record (3 x LDG.128);
+//   * sibling pairs are one 64-byte aligned fetch (4 x LDG.128 from one base address); triangles are a 48-byte hot
+//     record (3 x LDG.128);
 //   * the six IEEE divisions of a slab test are replaced by multiplications with the reciprocal direction and an
 //     error margin: the product differs from the correctly rounded quotient by < 2 ulp, so whenever the three
 //     comparisons of the predicate are decided by more than that margin the decision equals the reference's;
 //     otherwise (about one test in 10^5) the exact divisions are evaluated. ncu on the first version of this
-//     kernel showed 38 % of all issued instructions inside division sequences (profiles/r01_*);
+//     kernel showed 38 % of all issued instructions inside division sequences (profiles/);
 //   * the far child is deferred on a short stack (shared memory, interleaved by lane) together with its entry
 //     distance, so the reference's late range test is a compare at pop time instead of a second box test;
-//   * traversal is phase-structured (inner nodes / leaf triangles / instance transitions) so that the lanes of a
-//     warp run the same phase together, and lanes whose ray has finished pull a new ray immediately
-//     (per-warp ballot + one atomic) instead of idling until the slowest lane of the warp is done.
+//   * one flat while-while loop serves both levels; the world ray and the committed hit live in shared memory while a
+//     mesh is being walked (they are only touched at instance transitions), which keeps the loop at <= 80 registers.
+// What was measured and dropped (B200, 1M-triangle scene): per-lane ray refill (startup = root test +
+// instance transform is too expensive to run for single lanes), warp-private work chunks, vote-scheduled phases and a
+// camera-ray / bounce-ray queue split -- none beat whole-warp batches of 32 neighbouring slots.
 #pragma once
 
 #include "rzb_device.cuh"
@@ -26,32 +29,30 @@
 namespace rzb
 {
 	constexpr float kSlabMargin = 4.0e-7f; // > 2 ulp relative (2^-22 = 2.4e-7)
+	constexpr float kInf = __builtin_huge_valf();
 
-	struct SlabResult
+	// exact predicate (the reference's arithmetic); bit 0 = box, bit 1 = range; tmin returned through the reference
+	__device__ __noinline__ uint32_t slab_exact(const float4 n0, const float4 n1, const V3 o, const V3 d,
+		const float near_, const float far_, float& tmin)
 	{
-		bool box;   // !(tmax < near || tmin > tmax)
-		bool range; // !(tmin > far)
-		float tmin; // entry distance (approximate unless the exact path ran)
-	};
-
-	// exact predicate (the reference's arithmetic)
-#ifndef RZB_SLAB_EXACT_INLINE
-#define RZB_SLAB_EXACT_ATTR __noinline__
-#else
-#define RZB_SLAB_EXACT_ATTR __forceinline__
-#endif
-	__device__ RZB_SLAB_EXACT_ATTR SlabResult slab_exact(const float4 n0, const float4 n1, const V3 o, const V3 d,
-		const float near_, const float far_)
-	{
-		SlabResult r;
-		r.box = slab_rn(n0, n1, o, d, near_, r.tmin);
-		r.range = range_ok(r.tmin, far_);
-		return r;
+		const bool box = slab_rn(n0, n1, o, d, near_, tmin);
+		return (box ? 1u : 0u) | (range_ok(tmin, far_) ? 2u : 0u);
 	}
 
-	// fast predicate with fallback; `rcp` = 1/d per component (IEEE), `exact_only` forces the fallback (denormal d)
-	__device__ __forceinline__ SlabResult slab_fast(const float4 n0, const float4 n1, const V3& o, const V3& d, const V3& rcp,
-		const float near_, const float far_, const bool exact_only)
+	__device__ __forceinline__ V3 reciprocal_rn(const V3& d) { return v3(fdiv(1.0f, d.x), fdiv(1.0f, d.y), fdiv(1.0f, d.z)); }
+	// relative margin of the fast slab test for a ray direction: kSlabMargin, or infinity (= always take the exact
+	// path) when a component is so small that its reciprocal overflows while quotients may not
+	__device__ __forceinline__ float margin_for(const V3& d)
+	{
+		const float ax = fabsf(d.x), ay = fabsf(d.y), az = fabsf(d.z);
+		const bool tiny = (ax != 0.0f && ax < 1.0e-30f) || (ay != 0.0f && ay < 1.0e-30f) || (az != 0.0f && az < 1.0e-30f);
+		return tiny ? kInf : kSlabMargin;
+	}
+
+	// Fast slab predicate. Returns true when the box is hit AND its entry distance is within the range; tmin_out is
+	// the (approximate, or exact after the fallback) entry distance.
+	__device__ __forceinline__ bool slab_hit(const float4 n0, const float4 n1, const V3& o, const V3& d, const V3& rcp,
+		const float near_, const float far_, const float margin, float& tmin_out)
 	{
 		const float t1 = fmul(fsub(n0.x, o.x), rcp.x);
 		const float t2 = fmul(fsub(n0.w, o.x), rcp.x);
@@ -61,272 +62,244 @@ namespace rzb
 		const float t6 = fmul(fsub(n1.y, o.z), rcp.z);
 		const float tmin = fmaxf(fmaxf(fminf(t1, t2), fminf(t3, t4)), fminf(t5, t6));
 		const float tmax = fminf(fminf(fmaxf(t1, t2), fmaxf(t3, t4)), fmaxf(t5, t6));
-		// margins relative to the approximate values themselves (near/far are exact operands); infinities
-		// (a direction component == 0) are exact in both formulations and never "close"
-		const float m_min = fmaf(kSlabMargin, fminf(fabsf(tmin), 1.0e30f), 1.0e-37f);
-		const float m_max = fmaf(kSlabMargin, fminf(fabsf(tmax), 1.0e30f), 1.0e-37f);
-		const bool ambiguous = exact_only ||
-			fabsf(tmax - near_) <= m_max || fabsf(tmin - tmax) <= fmaxf(m_min, m_max) || fabsf(tmin - far_) <= m_min;
-		if (ambiguous) return slab_exact(n0, n1, o, d, near_, far_);
-		SlabResult r;
-		r.box = !(tmax < near_ || tmin > tmax);
-		r.range = !(tmin > far_);
-		r.tmin = tmin;
-		return r;
-	}
-
-	__device__ __forceinline__ V3 reciprocal_rn(const V3& d) { return v3(fdiv(1.0f, d.x), fdiv(1.0f, d.y), fdiv(1.0f, d.z)); }
-	// a direction component so small that its reciprocal overflows while quotients may not: use exact divisions
-	__device__ __forceinline__ bool needs_exact(const V3& d)
-	{
-		const float ax = fabsf(d.x), ay = fabsf(d.y), az = fabsf(d.z);
-		return (ax != 0.0f && ax < 1.0e-30f) || (ay != 0.0f && ay < 1.0e-30f) || (az != 0.0f && az < 1.0e-30f);
-	}
-
-	enum : uint32_t { kTravNode = 0u, kTravPop = 1u, kTravDone = 2u };
-
-	// Per-lane traversal state. MODE_ANY = shadow query (fixed child order, mask product, early out).
-	template <bool ANY>
-	struct Traversal
-	{
-		V3 wo, wd;            // world ray
-		float wnear, wfar;    // world range (far shrinks with every registered hit)
-		V3 o, d, rcp;         // current level
-		float near_, far_, len;
-		uint32_t sbits;
-		uint32_t cur_begin, cur_tc;
-		uint32_t state;       // kTrav*
-		uint32_t cur_inst;
-		bool in_mesh, mesh_hit, exact_only;
-		// closest-hit result
-		uint32_t hit_inst, hit_tri, ltri;
-		float b1, b2, lb1, lb2;
-		bool ext, lext;
-		// any-hit result
-		float4 mask;
-		uint32_t mat_offset, mat_count;
-
-		__device__ __forceinline__ void to_world_level()
+		// closest distance between any two compared quantities versus the error bound of the approximate ones;
+		// infinities (a direction component == 0) are exact in both formulations and never "close"
+		const float gap = fminf(fminf(fabsf(tmax - near_), fabsf(tmin - tmax)), fabsf(tmin - far_));
+		const float bound = margin * fmaxf(fminf(fmaxf(fabsf(tmin), fabsf(tmax)), 1.0e30f), 1.0e-30f);
+		tmin_out = tmin;
+		if (gap <= bound)
 		{
-			o = wo; d = wd;
-			rcp = reciprocal_rn(wd);
-			exact_only = needs_exact(wd);
-			sbits = ANY ? 0u : sign_bits(wd);
-			near_ = wnear; far_ = wfar;
-			len = 1.0f;
-			in_mesh = false;
+			const uint32_t r = slab_exact(n0, n1, o, d, near_, far_, tmin_out);
+			return r == 3u;
 		}
+		return !(tmax < near_ || tmin > tmax || tmin > far_);
+	}
 
-		// start a ray: root test of the instance tree
-		template <bool STATS>
-		__device__ __forceinline__ void begin(const DScene& sc, const V3 origin, const V3 dir, const float n, const float f,
-			Stack& st, TraceCounters& cnt)
+	struct RayResult
+	{
+		// closest hit
+		float t, near_;      // ray.near_far after traversal
+		float b1, b2;
+		uint32_t tri, inst;  // BVH-order triangle, BVH-order instance (kNoIndex = miss)
+		bool external;
+		// any hit
+		float4 mask;
+		// per-ray work (STATS only)
+		uint32_t steps, tris;
+	};
+
+	// every intersected triangle multiplies the shadow mask by its material's opacity colour (defined in rzb_shade.cuh)
+	__device__ __forceinline__ float4 shadow_attenuation(const DScene& sc, const uint32_t tri, const float b1, const float b2,
+		const uint32_t mat_offset, const uint32_t mat_count);
+
+	// What a lane parks in shared memory while it walks a mesh (touched only at instance transitions).
+	struct __align__(16) ParkedRay
+	{
+		float ox, oy, oz, near_;
+		float dx, dy, dz, far_;
+		float b1, b2;
+		uint32_t tri, inst;
+	};
+	static_assert(sizeof(ParkedRay) == 48, "ParkedRay");
+
+	template <bool ANY, bool STATS>
+	__device__ __forceinline__ void trace_ray(const DScene& sc, const V3 origin, const V3 direction, const float near_in,
+		const float far_in, Stack& st, ParkedRay& park, TraceCounters& cnt, RayResult& res)
+	{
+		res.t = far_in; res.near_ = near_in; res.b1 = 0.0f; res.b2 = 0.0f;
+		res.tri = kNoIndex; res.inst = kNoIndex; res.external = true;
+		res.mask = make_float4(1.0f, 1.0f, 1.0f, 1.0f);
+		res.steps = res.tris = 0u;
+		if (sc.instance_count == 0u)
 		{
-			wo = origin; wd = dir; wnear = n; wfar = f;
-			hit_inst = kNoIndex; hit_tri = kNoIndex; b1 = 0.0f; b2 = 0.0f; ext = true;
-			ltri = kNoIndex; lb1 = lb2 = 0.0f; lext = true;
-			mask = make_float4(1.0f, 1.0f, 1.0f, 1.0f);
-			mat_offset = mat_count = 0u;
-			mesh_hit = false; cur_inst = kNoIndex;
-			st.sp = 0;
-			to_world_level();
-			state = kTravDone;
-			if (sc.instance_count == 0u)
-			{
-				// no instances: the CPU engine's shadow query answers "occluded" (cpu_engine_kernel.cpp:401), the CUDA one "free"
-				if (ANY && (sc.flags & RZB_FLAG_CPU_SEMANTICS)) mask = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-				return;
-			}
-			const float4 n0 = __ldg(sc.nodes + 2 * size_t(sc.top_root));
-			const float4 n1 = __ldg(sc.nodes + 2 * size_t(sc.top_root) + 1);
+			// no instances: the CPU engine's shadow query answers "occluded" (cpu_engine_kernel.cpp:401), the CUDA one "free"
+			if (ANY && (sc.flags & RZB_FLAG_CPU_SEMANTICS)) res.mask = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+			return;
+		}
+		const float4* __restrict__ nodes = sc.nodes;
+
+		// current level (world first)
+		V3 o = origin, d = direction;
+		V3 rcp = reciprocal_rn(d);
+		float margin = margin_for(d);
+		float near_ = near_in, far_ = far_in, len = 1.0f;
+		uint32_t sbits = ANY ? 0u : sign_bits(d);
+		bool in_mesh = false, mesh_hit = false, lext = true;
+		uint32_t cur_inst = kNoIndex, ltri = kNoIndex;
+		float lb1 = 0.0f, lb2 = 0.0f;
+		uint32_t mat_offset = 0u, mat_count = 0u;
+		park.ox = origin.x; park.oy = origin.y; park.oz = origin.z; park.near_ = near_in;
+		park.dx = direction.x; park.dy = direction.y; park.dz = direction.z; park.far_ = far_in;
+		park.b1 = 0.0f; park.b2 = 0.0f; park.tri = kNoIndex; park.inst = kNoIndex;
+		bool committed_ext = true;
+		st.sp = 0;
+
+		uint32_t cur_begin, cur_tc;
+		{
+			const float4 n0 = __ldg(nodes + 2 * size_t(sc.top_root));
+			const float4 n1 = __ldg(nodes + 2 * size_t(sc.top_root) + 1);
 			if (STATS) cnt.top_nodes++;
-			const SlabResult r = slab_fast(n0, n1, o, d, rcp, near_, far_, exact_only);
-			if (!(r.box && r.range)) return;
+			float tmin;
+			if (!slab_hit(n0, n1, o, d, rcp, near_, far_, margin, tmin)) return;
 			cur_begin = __float_as_uint(n1.z);
 			cur_tc = __float_as_uint(n1.w);
-			state = kTravNode;
 		}
 
-		// Phase 1: walk inner nodes (and pop deferred nodes) until a leaf is current, or something other than a node
-		// of the current level has to be popped (state = kTravPop with the entry left on the stack), or the stack is empty.
-		template <bool STATS>
-		__device__ __forceinline__ void inner_phase(const DScene& sc, Stack& st, TraceCounters& cnt)
+		for (;;)
 		{
-			const float4* __restrict__ nodes = sc.nodes;
-			if (state == kTravDone) return;
-			for (;;)
+			bool have_cur = true;
+			// ---- descend through inner nodes
+			while ((cur_tc & 0x3FFFFFFFu) == 0u)
 			{
-				if (state == kTravPop)
-				{
-					if (st.sp == 0) return;
-					const uint2 e = st.peek();
-					const uint32_t kind = e.x & kEntryKindMask;
-					if (kind == kEntryInstRange || (in_mesh && kind != kEntryMeshNode)) return; // transition phase
-					st.sp--;
-					const uint32_t idx = e.x & kEntryIndexMask;
-					if (!ANY)
-					{
-						// late range test of a deferred node (the reference tests the far child after the near subtree)
-						const float tmin = __uint_as_float(e.y);
-						const float m = fmaf(kSlabMargin, fminf(fabsf(tmin), 1.0e30f), 1.0e-37f);
-						if (tmin > far_ + m) continue;
-						if (!(tmin < far_ - m))
-						{
-							// too close to call with the approximate entry distance: evaluate the reference's arithmetic
-							const float4 x0 = __ldg(nodes + 2 * size_t(idx));
-							const float4 x1 = __ldg(nodes + 2 * size_t(idx) + 1);
-							const SlabResult r = slab_exact(x0, x1, o, d, near_, far_);
-							if (!r.range) continue;
-						}
-					}
-					const float4 n1 = __ldg(nodes + 2 * size_t(idx) + 1);
-					cur_begin = __float_as_uint(n1.z);
-					cur_tc = __float_as_uint(n1.w);
-					state = kTravNode;
-				}
-				if ((cur_tc & 0x3FFFFFFFu) != 0u) return; // leaf
-				// inner node: fetch the sibling pair (64 B, 64-byte aligned)
-				const uint32_t flip = ANY ? 0u : ((sbits >> (cur_tc >> 30)) & 1u);
-				const uint32_t ia = cur_begin + flip, ib = cur_begin + (flip ^ 1u);
-				const float4 a0 = __ldg(nodes + 2 * size_t(ia));
-				const float4 a1 = __ldg(nodes + 2 * size_t(ia) + 1);
-				const float4 c0 = __ldg(nodes + 2 * size_t(ib));
-				const float4 c1 = __ldg(nodes + 2 * size_t(ib) + 1);
-				if (STATS) { if (in_mesh) cnt.mesh_nodes += 2; else cnt.top_nodes += 2; }
-				const SlabResult ra = slab_fast(a0, a1, o, d, rcp, near_, far_, exact_only);
-				const SlabResult rb = slab_fast(c0, c1, o, d, rcp, near_, far_, exact_only);
-				const bool hit_a = ra.box && ra.range, hit_b = rb.box && rb.range;
+				const float4* pair = nodes + 2 * size_t(cur_begin); // 64-byte aligned sibling pair
+				const float4 p0 = __ldg(pair), p1 = __ldg(pair + 1), p2 = __ldg(pair + 2), p3 = __ldg(pair + 3);
+				if (STATS) { if (in_mesh) cnt.mesh_nodes += 2; else cnt.top_nodes += 2; res.steps++; }
+				float tm0, tm1;
+				const bool h0 = slab_hit(p0, p1, o, d, rcp, near_, far_, margin, tm0);
+				const bool h1 = slab_hit(p2, p3, o, d, rcp, near_, far_, margin, tm1);
+				// near child first: `flip` = the second child is the near one
+				const bool flip = !ANY && ((sbits >> (cur_tc >> 30)) & 1u) != 0u;
+				const bool hit_a = flip ? h1 : h0, hit_b = flip ? h0 : h1;
 				if (hit_a)
 				{
 					// B is deferred with its entry distance: it is range-tested again when popped, i.e. after A's subtree
-					if (hit_b) st.push((in_mesh ? kEntryMeshNode : kEntryTopNode) | ib, __float_as_uint(rb.tmin));
-					cur_begin = __float_as_uint(a1.z);
-					cur_tc = __float_as_uint(a1.w);
+					if (hit_b) st.push((in_mesh ? kEntryMeshNode : kEntryTopNode) | (cur_begin + (flip ? 0u : 1u)),
+						__float_as_uint(flip ? tm0 : tm1));
+					cur_tc = __float_as_uint(flip ? p3.w : p1.w);
+					cur_begin = __float_as_uint(flip ? p3.z : p1.z);
 				}
 				else if (hit_b)
 				{
-					cur_begin = __float_as_uint(c1.z);
-					cur_tc = __float_as_uint(c1.w);
-				}
-				else state = kTravPop;
-			}
-		}
-
-		// Phase 2: the current node is a leaf.
-		template <bool STATS>
-		__device__ __forceinline__ void leaf_phase(const DScene& sc, Stack& st, TraceCounters& cnt)
-		{
-			if (state != kTravNode) return;
-			const uint32_t count = cur_tc & 0x3FFFFFFFu;
-			if (count == 0u) return;
-			state = kTravPop;
-			if (!in_mesh)
-			{
-				st.push(kEntryInstRange | cur_begin, cur_begin + count);
-				return;
-			}
-			const uint32_t end = cur_begin + count;
-			for (uint32_t i = cur_begin; i < end; ++i)
-			{
-				if (STATS) cnt.triangles++;
-				if (!ANY)
-				{
-					if (triangle_closest(sc.tri_hot, i, o, d, near_, far_, lb1, lb2, lext))
-					{
-						ltri = i;
-						mesh_hit = true;
-					}
+					cur_tc = __float_as_uint(flip ? p1.w : p3.w);
+					cur_begin = __float_as_uint(flip ? p1.z : p3.z);
 				}
 				else
 				{
-					float tf = far_, tb1, tb2;
-					bool text;
-					if (!triangle_closest(sc.tri_hot, i, o, d, near_, tf, tb1, tb2, text)) continue;
-					if (sc.flags & RZB_FLAG_CPU_SEMANTICS) mask = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-					else shadow_attenuate(sc, i, tb1, tb2);
-					if (mask.w < 1.0e-4f)
+					have_cur = false;
+					break;
+				}
+			}
+			// ---- leaf
+			if (have_cur)
+			{
+				const uint32_t count = cur_tc & 0x3FFFFFFFu;
+				if (!in_mesh) st.push(kEntryInstRange | cur_begin, cur_begin + count);
+				else
+				{
+					const uint32_t end = cur_begin + count;
+					for (uint32_t i = cur_begin; i < end; ++i)
 					{
-						state = kTravDone;
-						return;
+						if (STATS) { cnt.triangles++; res.tris++; }
+						if (!ANY)
+						{
+							if (triangle_closest(sc.tri_hot, i, o, d, near_, far_, lb1, lb2, lext))
+							{
+								ltri = i;
+								mesh_hit = true;
+							}
+						}
+						else
+						{
+							float tf = far_, tb1, tb2;
+							bool text;
+							if (!triangle_closest(sc.tri_hot, i, o, d, near_, tf, tb1, tb2, text)) continue;
+							if (sc.flags & RZB_FLAG_CPU_SEMANTICS) res.mask = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+							else
+							{
+								const float4 a = shadow_attenuation(sc, i, tb1, tb2, mat_offset, mat_count);
+								res.mask = make_float4(res.mask.x * a.x, res.mask.y * a.y, res.mask.z * a.z, res.mask.w * a.w);
+							}
+							if (res.mask.w < 1.0e-4f) return;
+						}
 					}
 				}
 			}
-		}
-
-		// every intersected triangle multiplies the mask by its material's opacity colour (cuda_instance.cuh:105-112)
-		__device__ __forceinline__ void shadow_attenuate(const DScene& sc, const uint32_t i, const float tb1, const float tb2);
-
-		// Phase 3: leave a finished mesh, enter the next instance of a range, or finish the ray.
-		template <bool STATS>
-		__device__ __forceinline__ void transition_phase(const DScene& sc, Stack& st, TraceCounters& cnt)
-		{
-			if (state != kTravPop) return;
-			uint2 e = make_uint2(kEntryTopNode, 0u);
-			const bool have = st.sp != 0;
-			if (have) e = st.peek();
-			const uint32_t kind = e.x & kEntryKindMask;
-			if (in_mesh && (!have || kind != kEntryMeshNode))
+			// ---- pop until a node with a passed box is current
+			for (;;)
 			{
-				// the current mesh is exhausted: leave the instance (cuda_instance.cuh:203-213)
-				if (!ANY && mesh_hit)
+				const bool have = st.sp != 0;
+				uint2 e = make_uint2(kEntryTopNode, 0u);
+				if (have) e = st.pop();
+				const uint32_t kind = e.x & kEntryKindMask;
+				if (in_mesh && (!have || kind != kEntryMeshNode))
 				{
-					hit_inst = cur_inst; hit_tri = ltri; b1 = lb1; b2 = lb2; ext = lext;
-					wnear = fdiv(near_, len);
-					wfar = fdiv(far_, len);
+					// the current mesh is exhausted: leave the instance (cuda_instance.cuh:203-213)
+					if (!ANY && mesh_hit)
+					{
+						park.inst = cur_inst; park.tri = ltri; park.b1 = lb1; park.b2 = lb2;
+						committed_ext = lext;
+						park.near_ = fdiv(near_, len);
+						park.far_ = fdiv(far_, len);
+					}
+					o = v3(park.ox, park.oy, park.oz);
+					d = v3(park.dx, park.dy, park.dz);
+					rcp = reciprocal_rn(d);
+					margin = margin_for(d);
+					sbits = ANY ? 0u : sign_bits(d);
+					near_ = park.near_; far_ = park.far_;
+					len = 1.0f;
+					in_mesh = false;
 				}
-				to_world_level();
+				if (!have)
+				{
+					res.t = park.far_; res.near_ = park.near_; res.b1 = park.b1; res.b2 = park.b2;
+					res.tri = park.tri; res.inst = park.inst; res.external = committed_ext;
+					return;
+				}
+				const uint32_t idx = e.x & kEntryIndexMask;
+				if (kind == kEntryInstRange)
+				{
+					const uint32_t end = e.y;
+					if (idx + 1u < end) st.push(kEntryInstRange | (idx + 1u), end);
+					// Instance::closestIntersection / anyIntersection (cuda_instance.cuh:186-229)
+					if (STATS) cnt.instances++;
+					const DInstance in = load_instance(sc.instances, idx);
+					const float4 n0 = make_float4(in.bminx, in.bminy, in.bminz, in.bmaxx);
+					const float4 n1 = make_float4(in.bmaxy, in.bmaxz, 0.0f, 0.0f);
+					float tmin;
+					if (!slab_hit(n0, n1, o, d, rcp, near_, far_, margin, tmin)) continue;
+					if (in.mesh_root == kNoIndex) continue;
+					V3 lo, ld;
+					float l;
+					ray_to_local(in, o, d, lo, ld, l);
+					const float lnear = fmul(near_, l), lfar = fmul(far_, l);
+					const V3 lrcp = reciprocal_rn(ld);
+					const float lmargin = margin_for(ld);
+					const float4 r0 = __ldg(nodes + 2 * size_t(in.mesh_root));
+					const float4 r1 = __ldg(nodes + 2 * size_t(in.mesh_root) + 1);
+					if (STATS) cnt.mesh_nodes++;
+					if (!slab_hit(r0, r1, lo, ld, lrcp, lnear, lfar, lmargin, tmin)) continue;
+					in_mesh = true; mesh_hit = false;
+					cur_inst = idx;
+					mat_offset = in.mat_offset; mat_count = in.mat_count;
+					o = lo; d = ld; rcp = lrcp; margin = lmargin; len = l;
+					sbits = ANY ? 0u : sign_bits(ld);
+					near_ = lnear; far_ = lfar;
+					cur_begin = __float_as_uint(r1.z);
+					cur_tc = __float_as_uint(r1.w);
+					break;
+				}
+				// a deferred node of the current level
+				if (!ANY)
+				{
+					// late range test (the reference tests the far child after the near subtree has been searched)
+					const float tmin = __uint_as_float(e.y);
+					const float bound = margin * fmaxf(fminf(fabsf(tmin), 1.0e30f), 1.0e-30f);
+					if (tmin > far_ + bound) continue;
+					if (!(tmin < far_ - bound))
+					{
+						// too close to call with the approximate entry distance: evaluate the reference's arithmetic
+						const float4 x0 = __ldg(nodes + 2 * size_t(idx));
+						const float4 x1 = __ldg(nodes + 2 * size_t(idx) + 1);
+						float texact;
+						if (!(slab_exact(x0, x1, o, d, near_, far_, texact) & 2u)) continue;
+					}
+				}
+				const float4 n1 = __ldg(nodes + 2 * size_t(idx) + 1);
+				cur_begin = __float_as_uint(n1.z);
+				cur_tc = __float_as_uint(n1.w);
+				break;
 			}
-			if (!have)
-			{
-				state = kTravDone;
-				return;
-			}
-			if (kind != kEntryInstRange) return; // a deferred top-level node: the inner phase pops it
-			st.sp--;
-			const uint32_t idx = e.x & kEntryIndexMask, end = e.y;
-			if (idx + 1u < end) st.push(kEntryInstRange | (idx + 1u), end);
-			// Instance::closestIntersection / anyIntersection (cuda_instance.cuh:186-229)
-			if (STATS) cnt.instances++;
-			const DInstance in = load_instance(sc.instances, idx);
-			const float4 n0 = make_float4(in.bminx, in.bminy, in.bminz, in.bmaxx);
-			const float4 n1 = make_float4(in.bmaxy, in.bmaxz, 0.0f, 0.0f);
-			const SlabResult rb = slab_fast(n0, n1, o, d, rcp, near_, far_, exact_only);
-			if (!(rb.box && rb.range)) return;
-			if (in.mesh_root == kNoIndex) return;
-			V3 lo, ld;
-			float l;
-			ray_to_local(in, wo, wd, lo, ld, l);
-			const float lnear = fmul(near_, l), lfar = fmul(far_, l);
-			const V3 lrcp = reciprocal_rn(ld);
-			const bool lexact = needs_exact(ld);
-			const float4 r0 = __ldg(sc.nodes + 2 * size_t(in.mesh_root));
-			const float4 r1 = __ldg(sc.nodes + 2 * size_t(in.mesh_root) + 1);
-			if (STATS) cnt.mesh_nodes++;
-			const SlabResult rr = slab_fast(r0, r1, lo, ld, lrcp, lnear, lfar, lexact);
-			if (!(rr.box && rr.range)) return;
-			in_mesh = true; mesh_hit = false;
-			cur_inst = idx;
-			mat_offset = in.mat_offset; mat_count = in.mat_count;
-			o = lo; d = ld; rcp = lrcp; exact_only = lexact; len = l;
-			sbits = ANY ? 0u : sign_bits(ld);
-			near_ = lnear; far_ = lfar;
-			cur_begin = __float_as_uint(r1.z);
-			cur_tc = __float_as_uint(r1.w);
-			state = kTravNode;
 		}
-
-		__device__ __forceinline__ bool done() const { return state == kTravDone; }
-
-		// run one ray to completion (used where rays are not pulled dynamically)
-		template <bool STATS>
-		__device__ __forceinline__ void run(const DScene& sc, Stack& st, TraceCounters& cnt)
-		{
-			while (!done())
-			{
-				inner_phase<STATS>(sc, st, cnt);
-				leaf_phase<STATS>(sc, st, cnt);
-				transition_phase<STATS>(sc, st, cnt);
-			}
-		}
-	};
+	}
 }

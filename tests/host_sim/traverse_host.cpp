@@ -25,9 +25,14 @@ struct { unsigned x = 0; } threadIdx;
 
 using namespace rzb;
 
-// the real shadow_attenuate lives in rzb_shade.cuh; the host simulation only runs CPU-semantics shadows
-template <bool ANY>
-void Traversal<ANY>::shadow_attenuate(const DScene&, const uint32_t, const float, const float) { mask = make_float4(0, 0, 0, 0); }
+// the real shadow_attenuation lives in rzb_shade.cuh; the host simulation only runs CPU-semantics shadows
+namespace rzb
+{
+	float4 shadow_attenuation(const DScene&, const uint32_t, const float, const float, const uint32_t, const uint32_t)
+	{
+		return make_float4(0, 0, 0, 0);
+	}
+}
 
 extern "C" int trav_host_run(const rzb_scene* s, const float* origins, const float* dirs, const float* near_far, uint32_t n,
 	int any, rzb_hit* hits_out, float* masks_out, uint64_t* counters4)
@@ -105,26 +110,24 @@ extern "C" int trav_host_run(const rzb_scene* s, const float* origins, const flo
 		const V3 o = v3(origins[3 * i], origins[3 * i + 1], origins[3 * i + 2]);
 		const V3 d = v3(dirs[3 * i], dirs[3 * i + 1], dirs[3 * i + 2]);
 		cnt = TraceCounters{0u, 0u, 0u, 0u};
+		ParkedRay park;
+		RayResult r;
 		if (any)
 		{
-			Traversal<true> tv;
-			tv.begin<true>(sc, o, d, near_far[2 * i], near_far[2 * i + 1], st, cnt);
-			tv.run<true>(sc, st, cnt);
-			masks_out[4 * i] = tv.mask.x; masks_out[4 * i + 1] = tv.mask.y; masks_out[4 * i + 2] = tv.mask.z; masks_out[4 * i + 3] = tv.mask.w;
+			trace_ray<true, true>(sc, o, d, near_far[2 * i], near_far[2 * i + 1], st, park, cnt, r);
+			masks_out[4 * i] = r.mask.x; masks_out[4 * i + 1] = r.mask.y; masks_out[4 * i + 2] = r.mask.z; masks_out[4 * i + 3] = r.mask.w;
 		}
 		else
 		{
-			Traversal<false> tv;
-			tv.begin<true>(sc, o, d, near_far[2 * i], near_far[2 * i + 1], st, cnt);
-			tv.run<true>(sc, st, cnt);
+			trace_ray<false, true>(sc, o, d, near_far[2 * i], near_far[2 * i + 1], st, park, cnt, r);
 			rzb_hit h{};
 			h.instance = RZB_NO_INDEX; h.triangle = RZB_NO_INDEX;
-			h.t = tv.wfar;
-			if (tv.hit_inst != kNoIndex)
+			h.t = r.t;
+			if (r.inst != kNoIndex)
 			{
-				h.instance = s->instances[tv.hit_inst].host_index;
-				h.triangle = s->tri_host_index ? s->tri_host_index[tv.hit_tri] : tv.hit_tri;
-				h.b1 = tv.b1; h.b2 = tv.b2; h.external = tv.ext ? 1u : 0u;
+				h.instance = s->instances[r.inst].host_index;
+				h.triangle = s->tri_host_index ? s->tri_host_index[r.tri] : r.tri;
+				h.b1 = r.b1; h.b2 = r.b2; h.external = r.external ? 1u : 0u;
 			}
 			hits_out[i] = h;
 		}
