@@ -179,16 +179,16 @@ namespace rzb
 			if (base >= f.n_slots) break;
 			const uint32_t slot = base + (threadIdx.x & 31u);
 			uint32_t x, y;
-			if (slot >= f.n_slots || !slot_to_pixel(f, slot, x, y)) continue;
-			const float4 so = f.st_o[slot];
-			const float4 sd = f.st_d[slot];
+			const bool active = slot < f.n_slots && slot_to_pixel(f, slot, x, y);
+			float4 so = make_float4(0.0f, 0.0f, 0.0f, 0.0f), sd = make_float4(0.0f, 0.0f, 1.0f, 0.0f);
+			if (active) { so = f.st_o[slot]; sd = f.st_d[slot]; }
 			const uint32_t bits = __float_as_uint(so.w);
-			const uint32_t depth = bits & 0xFFu, medium = bits >> kMediumShift;
+			const uint32_t depth = bits & 0xFFu, medium = active ? (bits >> kMediumShift) : sc.world_material;
 			float near_ = 0.0f, far_ = kFltMax;
 			if (depth == 0u) { near_ = f.cam.near_; far_ = f.cam.far_; }
 			uint32_t flags = 0u;
 			// World::closestIntersection: free flight in the current medium first (cuda_material.cuh:141-159)
-			if (!(sc.flags & RZB_FLAG_CPU_SEMANTICS))
+			if (active && !(sc.flags & RZB_FLAG_CPU_SEMANTICS))
 			{
 				const float sigma = sc.materials[medium].scattering;
 				if (sigma > 1.0e-4f)
@@ -199,7 +199,8 @@ namespace rzb
 				}
 			}
 			RayResult r;
-			trace_ray<false, STATS>(sc, v3(so.x, so.y, so.z), v3(sd.x, sd.y, sd.z), near_, far_, st, park, cnt, r);
+			trace_ray<false, STATS>(sc, active, v3(so.x, so.y, so.z), v3(sd.x, sd.y, sd.z), near_, far_, st, park, cnt, r);
+			if (!active) continue;
 			uint32_t tri_bits = flags | (r.external ? kHitExternalBit : 0u);
 			tri_bits |= (r.tri == kNoIndex) ? kHitTriMask : (r.tri & kHitTriMask);
 			f.hit_a[slot] = make_float4(r.t, r.b1, r.b2, __uint_as_float(tri_bits));
@@ -446,13 +447,13 @@ namespace rzb
 			const uint32_t base = warp_batch(&f.counters[2]);
 			if (base >= n) break;
 			const uint32_t i = base + (threadIdx.x & 31u);
-			if (i >= n) continue;
-			const float4 o = f.sh_o[i];
-			const float4 d = f.sh_d[i];
+			const bool active = i < n;
+			float4 o = make_float4(0.0f, 0.0f, 0.0f, 0.0f), d = make_float4(0.0f, 0.0f, 1.0f, 0.0f);
+			if (active) { o = f.sh_o[i]; d = f.sh_d[i]; }
 			RayResult r;
-			trace_ray<true, STATS>(sc, v3(o.x, o.y, o.z), v3(d.x, d.y, d.z), 0.0f, o.w, st, park, cnt, r);
+			trace_ray<true, STATS>(sc, active, v3(o.x, o.y, o.z), v3(d.x, d.y, d.z), 0.0f, o.w, st, park, cnt, r);
 			const float w = r.mask.w;
-			if (w <= 0.0f) continue;
+			if (!active || w <= 0.0f) continue;
 			const float4 c = f.sh_c[i];
 			float* a = reinterpret_cast<float*>(f.accum + __float_as_uint(d.w));
 			atomicAdd(a + 0, c.x * r.mask.x * w);
@@ -524,11 +525,12 @@ namespace rzb
 			const uint32_t base = warp_batch(counter);
 			if (base >= n) break;
 			const uint32_t i = base + (threadIdx.x & 31u);
-			if (i >= n) continue;
-			const float4 o = __ldg(ray_o_near + i);
-			const float4 d = __ldg(ray_d_far + i);
+			const bool active = i < n;
+			float4 o = make_float4(0.0f, 0.0f, 0.0f, 0.0f), d = make_float4(0.0f, 0.0f, 1.0f, 0.0f);
+			if (active) { o = __ldg(ray_o_near + i); d = __ldg(ray_d_far + i); }
 			RayResult r;
-			trace_ray<false, STATS>(sc, v3(o.x, o.y, o.z), v3(d.x, d.y, d.z), o.w, d.w, st, park, cnt, r);
+			trace_ray<false, STATS>(sc, active, v3(o.x, o.y, o.z), v3(d.x, d.y, d.z), o.w, d.w, st, park, cnt, r);
+			if (!active) continue;
 			const uint32_t tri_bits = (r.tri == kNoIndex ? kHitTriMask : (r.tri & kHitTriMask)) | (r.external ? kHitExternalBit : 0u);
 			float4* dst = reinterpret_cast<float4*>(hits + i);
 			dst[0] = make_float4(r.t, r.b1, r.b2, __uint_as_float(tri_bits));
@@ -572,12 +574,12 @@ namespace rzb
 			const uint32_t base = warp_batch(counter);
 			if (base >= n) break;
 			const uint32_t i = base + (threadIdx.x & 31u);
-			if (i >= n) continue;
-			const float4 o = __ldg(ray_o_near + i);
-			const float4 d = __ldg(ray_d_far + i);
+			const bool active = i < n;
+			float4 o = make_float4(0.0f, 0.0f, 0.0f, 0.0f), d = make_float4(0.0f, 0.0f, 1.0f, 0.0f);
+			if (active) { o = __ldg(ray_o_near + i); d = __ldg(ray_d_far + i); }
 			RayResult r;
-			trace_ray<true, false>(sc, v3(o.x, o.y, o.z), v3(d.x, d.y, d.z), o.w, d.w, st, park, cnt, r);
-			masks[i] = r.mask;
+			trace_ray<true, false>(sc, active, v3(o.x, o.y, o.z), v3(d.x, d.y, d.z), o.w, d.w, st, park, cnt, r);
+			if (active) masks[i] = r.mask;
 		}
 	}
 

@@ -16,6 +16,7 @@ static inline float __fsqrt_rn(float a) { return sqrtf(a); }
 static inline uint32_t __float_as_uint(float f) { uint32_t u; std::memcpy(&u, &f, 4); return u; }
 static inline float __uint_as_float(uint32_t u) { float f; std::memcpy(&f, &u, 4); return f; }
 template <typename T> static inline T __ldg(const T* p) { return *p; }
+static inline int __any_sync(unsigned, int p) { return p; }
 struct { unsigned x = 0; } threadIdx;
 #define RZB_HOST_SIM 1
 #ifndef __noinline__
@@ -114,12 +115,12 @@ extern "C" int trav_host_run(const rzb_scene* s, const float* origins, const flo
 		RayResult r;
 		if (any)
 		{
-			trace_ray<true, true>(sc, o, d, near_far[2 * i], near_far[2 * i + 1], st, park, cnt, r);
+			trace_ray<true, true>(sc, true, o, d, near_far[2 * i], near_far[2 * i + 1], st, park, cnt, r);
 			masks_out[4 * i] = r.mask.x; masks_out[4 * i + 1] = r.mask.y; masks_out[4 * i + 2] = r.mask.z; masks_out[4 * i + 3] = r.mask.w;
 		}
 		else
 		{
-			trace_ray<false, true>(sc, o, d, near_far[2 * i], near_far[2 * i + 1], st, park, cnt, r);
+			trace_ray<false, true>(sc, true, o, d, near_far[2 * i], near_far[2 * i + 1], st, park, cnt, r);
 			rzb_hit h{};
 			h.instance = RZB_NO_INDEX; h.triangle = RZB_NO_INDEX;
 			h.t = r.t;
