@@ -131,7 +131,7 @@ def reference_run(workload, steps, warmup, budget_s=150.0):
         kw2["resolution"] = res
         w = scenes.CONFIGS[name](**kw2)
         path = w.save_reference(os.path.join(tmp, "%dx%d" % res))
-        return O.ref_tool("render", path, passes, "-", MAX_DEPTH, 1, 1, wu)
+        return O.ref_tool("render", path, passes, "-", MAX_DEPTH, 1, 1, wu, timeout=max(60.0, 3.0 * budget_s), attempts=2)
 
     probe_res = (max(full[0] // 8, 16), max(full[1] // 8, 16))
     probe = run(probe_res, 3, 1)

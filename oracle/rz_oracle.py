@@ -116,10 +116,19 @@ def have_ref_tool() -> bool:
     return os.path.exists(REF_TOOL) and os.access(REF_TOOL, os.X_OK)
 
 
-def ref_tool(*args, timeout=None):
-    """Run oracle/_ref/rz_ref_tool; returns the JSON object of its last stdout line."""
-    r = subprocess.run([REF_TOOL, *map(str, args)], capture_output=True, text=True, timeout=timeout)
-    if r.returncode != 0:
-        raise RuntimeError("rz_ref_tool %s failed (%d): %s" % (args[0], r.returncode, r.stderr[-800:]))
-    lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
-    return json.loads(lines[-1]) if lines else {}
+def ref_tool(*args, timeout=600.0, attempts=3):
+    """Run oracle/_ref/rz_ref_tool; returns the JSON object of its last stdout line.
+    The reference CPU engine's worker-thread gates occasionally deadlock (seen here as a render that sleeps forever
+    at 0 % CPU), so every call runs under a timeout and is retried."""
+    last = None
+    for _ in range(attempts):
+        try:
+            r = subprocess.run([REF_TOOL, *map(str, args)], capture_output=True, text=True, timeout=timeout)
+        except subprocess.TimeoutExpired as e:
+            last = e
+            continue
+        if r.returncode != 0:
+            raise RuntimeError("rz_ref_tool %s failed (%d): %s" % (args[0], r.returncode, r.stderr[-800:]))
+        lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
+        return json.loads(lines[-1]) if lines else {}
+    raise RuntimeError("rz_ref_tool %s timed out %d times (%s)" % (args[0], attempts, last))

@@ -118,26 +118,32 @@ def torus_mesh(major_res=128, minor_res=64, R=1.0, r=0.35):
     return v, tris, uv, n
 
 
-def cylinder_mesh(res=64, radius=0.5, height=1.0):
+def cylinder_mesh(res=64, radius=0.5, height=1.0, rings=None):
+    """Capped cylinder: `res` segments around, `rings` segments along the axis (default res/4: roughly square quads --
+    full-height side triangles would be unsplittable for the reference's builder and end up in one huge leaf)."""
+    rings = max(res // 4, 1) if rings is None else rings
     ang = np.linspace(0.0, 2.0 * np.pi, res + 1)
+    ys = np.linspace(-0.5 * height, 0.5 * height, rings + 1)
+    A, Y = np.meshgrid(ang, ys, indexing="ij")
+    side_v = np.stack([radius * np.cos(A), Y, radius * np.sin(A)], axis=-1).reshape(-1, 3)
+    side_n = np.stack([np.cos(A), np.zeros_like(A), np.sin(A)], axis=-1).reshape(-1, 3)
+    side_uv = np.stack([A / (2 * np.pi), (Y / height) + 0.5], axis=-1).reshape(-1, 2)
     ring = np.stack([radius * np.cos(ang), np.zeros_like(ang), radius * np.sin(ang)], axis=-1)
     bot, top = ring.copy(), ring.copy()
     bot[:, 1], top[:, 1] = -0.5 * height, 0.5 * height
-    side_n = np.stack([np.cos(ang), np.zeros_like(ang), np.sin(ang)], axis=-1)
-    # side (smooth normals) + caps (flat normals) as separate vertex sets
-    v = np.concatenate([bot, top, bot, top, [[0, -0.5 * height, 0]], [[0, 0.5 * height, 0]]]).astype(f4)
-    n = np.concatenate([side_n, side_n, np.tile([0, -1, 0], (res + 1, 1)), np.tile([0, 1, 0], (res + 1, 1)),
-                        [[0, -1, 0]], [[0, 1, 0]]]).astype(f4)
-    u = ang / (2 * np.pi)
-    uv = np.concatenate([np.stack([u, np.zeros_like(u)], -1), np.stack([u, np.ones_like(u)], -1),
-                         np.stack([0.5 + 0.5 * np.cos(ang), 0.5 + 0.5 * np.sin(ang)], -1),
-                         np.stack([0.5 + 0.5 * np.cos(ang), 0.5 + 0.5 * np.sin(ang)], -1),
-                         [[0.5, 0.5]], [[0.5, 0.5]]]).astype(f4)
+    cap_uv = np.stack([0.5 + 0.5 * np.cos(ang), 0.5 + 0.5 * np.sin(ang)], -1)
+    ns = side_v.shape[0]
     k = res + 1
-    j = np.arange(res)
-    side = np.concatenate([np.stack([j, j + 1, k + j], 1), np.stack([k + j, j + 1, k + j + 1], 1)])
-    cb = np.stack([np.full(res, 4 * k), 2 * k + j, 2 * k + j + 1], 1)
-    ct = np.stack([np.full(res, 4 * k + 1), 3 * k + j, 3 * k + j + 1], 1)
+    v = np.concatenate([side_v, bot, top, [[0, -0.5 * height, 0]], [[0, 0.5 * height, 0]]]).astype(f4)
+    n = np.concatenate([side_n, np.tile([0, -1, 0], (k, 1)), np.tile([0, 1, 0], (k, 1)), [[0, -1, 0]], [[0, 1, 0]]]).astype(f4)
+    uv = np.concatenate([side_uv, cap_uv, cap_uv, [[0.5, 0.5]], [[0.5, 0.5]]]).astype(f4)
+    i, j = np.meshgrid(np.arange(res), np.arange(rings), indexing="ij")
+    a = (i * (rings + 1) + j).reshape(-1)
+    b, c, d = a + 1, a + (rings + 1), a + (rings + 1) + 1
+    side = np.concatenate([np.stack([a, b, c], 1), np.stack([c, b, d], 1)])
+    jj = np.arange(res)
+    cb = np.stack([np.full(res, ns + 2 * k), ns + jj, ns + jj + 1], 1)
+    ct = np.stack([np.full(res, ns + 2 * k + 1), ns + k + jj, ns + k + jj + 1], 1)
     tris = np.concatenate([side, cb, ct]).astype(np.uint32)
     vv, nn = v.astype(np.float64), n.astype(np.float64)
     fn = np.cross(vv[tris[:, 1]] - vv[tris[:, 0]], vv[tris[:, 2]] - vv[tris[:, 0]])

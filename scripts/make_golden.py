@@ -50,7 +50,7 @@ def main():
         if name in RENDER_SETTINGS:
             passes, depth = RENDER_SETTINGS[name]
             for tag in ("a", "b"):
-                O.ref_tool("render", path, passes, os.path.join(d, "render_%s.rzs" % tag), depth, 1, 1)
+                O.ref_tool("render", path, passes, os.path.join(d, "render_%s.rzs" % tag), depth, 1, 1, timeout=120.0)
                 r = rzs.read(os.path.join(d, "render_%s.rzs" % tag))
                 out["accum_" + tag] = r["accum"]
             out["depth"] = r["depth"]
