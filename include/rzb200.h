@@ -247,6 +247,10 @@ int rzb_set_stream(rzb_ctx* ctx, void* cuda_stream, int use_caller_stream);
 int rzb_set_scene(rzb_ctx* ctx, const rzb_scene* scene);
 int rzb_set_camera(rzb_ctx* ctx, const rzb_camera* camera);
 int rzb_set_config(rzb_ctx* ctx, const rzb_config* config);
+/* Tile split for multi-GPU frames: this context renders only image rows [row_begin, row_end) of the current camera
+ * (default: all rows; reset by rzb_set_camera with a new resolution). Rows outside the band stay zero in the
+ * accumulator, so the accumulators of disjoint bands (and of sample streams) combine by plain summation. */
+int rzb_set_rows(rzb_ctx* ctx, uint32_t row_begin, uint32_t row_end);
 
 /* ---- frame: replaces Renderer::renderFunction (cuda_engine_renderer.cu:73-262) ---- */
 /* drop accumulated samples, regenerate pixel-centre camera rays (passReset + generateCameraRay). */

@@ -99,6 +99,7 @@ SYMBOLS = {
     "rzb_set_scene": (C.c_int, [_P, C.POINTER(SceneStruct)]),
     "rzb_set_camera": (C.c_int, [_P, _P]),
     "rzb_set_config": (C.c_int, [_P, _P]),
+    "rzb_set_rows": (C.c_int, [_P, C.c_uint32, C.c_uint32]),
     "rzb_reset": (C.c_int, [_P]),
     "rzb_render": (C.c_int, [_P, C.c_uint32]),
     "rzb_resolve": (C.c_int, [_P, _P, _P, C.POINTER(C.c_uint64)]),
@@ -321,6 +322,10 @@ class Context:
         cfg = np.zeros(1, dtype=config_dtype)
         cfg[0] = (spot_light_samples, direct_light_samples, max_depth, flags, seed)
         self._check(self._l.rzb_set_config(self._h, cfg.ctypes.data))
+
+    def set_rows(self, row_begin: int, row_end: int):
+        """Tile split: render only image rows [row_begin, row_end)."""
+        self._check(self._l.rzb_set_rows(self._h, int(row_begin), int(row_end)))
 
     # -- frame
     def reset(self):

@@ -72,6 +72,7 @@ struct rzb_ctx
 	uint32_t* d_counters = nullptr;          // [0..2] work counters, [4..5] 64-bit shadow total
 	uint32_t shadow_capacity_alloc = 0;
 	void* d_shadow[3] = {nullptr, nullptr, nullptr};
+	uint32_t row_begin = 0, row_end = 0; // tile split (rzb_set_rows)
 
 	// scratch for ray-set calls
 	DeviceBuffer scratch[4];
@@ -168,6 +169,8 @@ namespace
 		f.tiles_x = (ctx->cam.width + 15u) / 16u;  // 16x16-pixel chunks of 256 slots
 		f.tiles_y = (ctx->cam.height + 15u) / 16u;
 		f.n_slots = f.tiles_x * f.tiles_y * 256u;
+		ctx->row_begin = 0;
+		ctx->row_end = ctx->cam.height;
 		const size_t n_pixels = size_t(ctx->cam.width) * ctx->cam.height;
 		auto alloc = [&](void** p, size_t bytes) -> int {
 			RZB_CUDA(ctx, cudaMalloc(p, bytes));
@@ -187,6 +190,15 @@ namespace
 		RZB_CUDA(ctx, cudaMemsetAsync(f.depth, 0, n_pixels * 4, ctx->stream));
 		ctx->frame_ready = false;
 		return RZB_OK;
+	}
+
+	void applyRows(rzb_ctx* ctx)
+	{
+		DFrame& f = ctx->frame;
+		f.row_begin = std::min(ctx->row_begin, ctx->cam.height);
+		f.row_end = std::min(std::max(ctx->row_end, f.row_begin), ctx->cam.height);
+		f.slot_begin = (f.row_begin / 16u) * f.tiles_x * 256u;
+		f.slot_end = f.row_end > f.row_begin ? ((f.row_end + 15u) / 16u) * f.tiles_x * 256u : f.slot_begin;
 	}
 
 	int ensureShadowQueue(rzb_ctx* ctx)
@@ -530,6 +542,17 @@ extern "C" int rzb_set_camera(rzb_ctx* ctx, const rzb_camera* camera)
 	return RZB_OK;
 }
 
+extern "C" int rzb_set_rows(rzb_ctx* ctx, uint32_t row_begin, uint32_t row_end)
+{
+	if (!ctx) return RZB_ERR_INVALID;
+	if (!ctx->has_camera) return fail(ctx, RZB_ERR_STATE, "rzb_set_rows: no camera");
+	if (row_begin > row_end || row_end > ctx->cam.height) return fail(ctx, RZB_ERR_INVALID, "rzb_set_rows: bad row range");
+	ctx->row_begin = row_begin;
+	ctx->row_end = row_end;
+	ctx->frame_ready = false; // the next render starts from a reset
+	return RZB_OK;
+}
+
 extern "C" int rzb_set_config(rzb_ctx* ctx, const rzb_config* config)
 {
 	if (!ctx || !config) return fail(ctx, RZB_ERR_INVALID, "rzb_set_config: NULL argument");
@@ -547,8 +570,13 @@ extern "C" int rzb_reset(rzb_ctx* ctx)
 	DFrame& f = ctx->frame;
 	f.cam = makeDeviceCamera(ctx->cam);
 	f.counters = ctx->d_counters;
+	applyRows(ctx);
+	const size_t n_pixels = size_t(ctx->cam.width) * ctx->cam.height;
+	RZB_CUDA(ctx, cudaMemsetAsync(f.accum, 0, n_pixels * 16, ctx->stream)); // rows outside the band stay zero
+	RZB_CUDA(ctx, cudaMemsetAsync(f.depth, 0, n_pixels * 4, ctx->stream));
 	RZB_CUDA(ctx, cudaMemsetAsync(ctx->d_counters, 0, 256, ctx->stream));
-	k_reset<<<(f.n_slots + 127) / 128, 128, 0, ctx->stream>>>(f, ctx->sc.world_material);
+	if (f.slot_end > f.slot_begin)
+		k_reset<<<(f.slot_end - f.slot_begin + 127) / 128, 128, 0, ctx->stream>>>(f, ctx->sc.world_material);
 	RZB_CUDA(ctx, cudaGetLastError());
 	RZB_CUDA(ctx, cudaMemsetAsync(ctx->d_work, 0, 128, ctx->stream));
 	ctx->counted_segments = 0;
@@ -571,6 +599,7 @@ extern "C" int rzb_render(rzb_ctx* ctx, uint32_t passes)
 	int rc = ensureShadowQueue(ctx);
 	if (rc) return rc;
 	DFrame& f = ctx->frame;
+	if (f.slot_end <= f.slot_begin) return RZB_OK; // empty row band
 	f.counters = ctx->d_counters;
 	f.max_depth = ctx->cfg.max_depth;
 	f.direct_samples = ctx->cfg.direct_light_samples;
@@ -606,7 +635,7 @@ extern "C" int rzb_render(rzb_ctx* ctx, uint32_t passes)
 			if (e != cudaSuccess) return cudaFail(ctx, e, ("k_trace_paths, pass " + std::to_string(ctx->passes)).c_str());
 		}
 		if (timed) cudaEventRecord(ev[1], ctx->stream);
-		k_shade<<<(f.n_slots + 127) / 128, 128, 0, ctx->stream>>>(ctx->sc, f);
+		k_shade<<<(f.slot_end - f.slot_begin + 127) / 128, 128, 0, ctx->stream>>>(ctx->sc, f);
 		if (ctx->debug_sync)
 		{
 			const cudaError_t e = cudaStreamSynchronize(ctx->stream);
@@ -631,7 +660,7 @@ extern "C" int rzb_render(rzb_ctx* ctx, uint32_t passes)
 			ctx->sampled_passes += 1;
 		}
 		ctx->passes += 1;
-		if (count) ctx->counted_segments += uint64_t(ctx->cam.width) * ctx->cam.height;
+		if (count) ctx->counted_segments += uint64_t(ctx->cam.width) * (f.row_end - f.row_begin);
 	}
 	RZB_CUDA(ctx, cudaEventRecord(ctx->ev_end, ctx->stream));
 	RZB_CUDA(ctx, cudaGetLastError());
@@ -674,7 +703,7 @@ extern "C" int rzb_resolve(rzb_ctx* ctx, uint8_t* rgba8, float* depth, uint64_t*
 	PeerList peers{};
 	const int rc = tonemapAndCopy(ctx, peers, rgba8, depth);
 	if (rc) return rc;
-	if (ray_count) *ray_count = ctx->passes * uint64_t(ctx->cam.width) * ctx->cam.height;
+	if (ray_count) *ray_count = ctx->passes * uint64_t(ctx->cam.width) * (ctx->frame.row_end - ctx->frame.row_begin);
 	return RZB_OK;
 }
 
@@ -684,7 +713,7 @@ extern "C" int rzb_resolve_peers(rzb_ctx* ctx, rzb_ctx* const* peers_in, uint32_
 	if (!ctx || (n_peers && !peers_in) || n_peers > 8) return fail(ctx, RZB_ERR_INVALID, "rzb_resolve_peers: bad arguments");
 	DeviceGuard guard(ctx->device);
 	PeerList peers{};
-	uint64_t rays = ctx->passes * uint64_t(ctx->cam.width) * ctx->cam.height;
+	uint64_t rays = ctx->passes * uint64_t(ctx->cam.width) * (ctx->frame.row_end - ctx->frame.row_begin);
 	for (uint32_t i = 0; i < n_peers; ++i)
 	{
 		rzb_ctx* p = peers_in[i];
@@ -704,7 +733,7 @@ extern "C" int rzb_resolve_peers(rzb_ctx* ctx, rzb_ctx* const* peers_in, uint32_
 			RZB_CUDA(ctx, cudaStreamSynchronize(p->stream));
 		}
 		peers.accum[i] = p->frame.accum;
-		rays += p->passes * uint64_t(p->cam.width) * p->cam.height;
+		rays += p->passes * uint64_t(p->cam.width) * (p->frame.row_end - p->frame.row_begin);
 	}
 	peers.count = n_peers;
 	const int rc = tonemapAndCopy(ctx, peers, rgba8, depth);
@@ -753,7 +782,7 @@ extern "C" int rzb_get_render_stats(rzb_ctx* ctx, rzb_render_stats* out)
 	RZB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
 	std::memset(out, 0, sizeof(*out));
 	out->passes = ctx->passes;
-	out->ray_count = ctx->passes * uint64_t(ctx->cam.width) * ctx->cam.height;
+	out->ray_count = ctx->passes * uint64_t(ctx->cam.width) * (ctx->frame.row_end - ctx->frame.row_begin);
 	out->kernel_launches = ctx->launches;
 	if (ctx->passes)
 	{

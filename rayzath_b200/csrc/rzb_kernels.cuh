@@ -29,6 +29,8 @@ namespace rzb
 	{
 		DCamera cam;
 		uint32_t tiles_x, tiles_y, n_slots;
+		uint32_t row_begin, row_end;    // tile split: this context renders image rows [row_begin, row_end)
+		uint32_t slot_begin, slot_end;  // the 256-slot chunks that cover those rows
 		float4* st_o;   // {o.xyz, bits(depth | medium << 8)}
 		float4* st_d;   // {d.xyz, throughput.r}
 		float2* st_c;   // {throughput.g, throughput.b}
@@ -56,7 +58,7 @@ namespace rzb
 		const uint32_t chunk = slot >> 8, tile = (slot >> 5) & 7u, within = slot & 31u;
 		x = (chunk % f.tiles_x) * 16u + (tile & 1u) * 8u + (within & 7u);
 		y = (chunk / f.tiles_x) * 16u + (tile >> 1) * 4u + (within >> 3);
-		return x < f.cam.width && y < f.cam.height;
+		return x < f.cam.width && y >= f.row_begin && y < f.row_end;
 	}
 
 	__device__ __forceinline__ Stack make_stack(uint2* smem_base)
@@ -125,9 +127,9 @@ namespace rzb
 	// ---------------------------------------------------------------- k_reset
 	__global__ void __launch_bounds__(128) k_reset(DFrame f, uint32_t world_material)
 	{
-		const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
+		const uint32_t slot = f.slot_begin + blockIdx.x * blockDim.x + threadIdx.x;
 		uint32_t x = 0, y = 0;
-		const bool valid = slot < f.n_slots && slot_to_pixel(f, slot, x, y);
+		const bool valid = slot < f.slot_end && slot_to_pixel(f, slot, x, y);
 		if (valid)
 		{
 			V3 o, d;
@@ -175,11 +177,11 @@ namespace rzb
 		TraceCounters cnt{0u, 0u, 0u, 0u};
 		for (;;)
 		{
-			const uint32_t base = warp_batch(&f.counters[0]);
-			if (base >= f.n_slots) break;
+			const uint32_t base = f.slot_begin + warp_batch(&f.counters[0]);
+			if (base >= f.slot_end) break;
 			const uint32_t slot = base + (threadIdx.x & 31u);
 			uint32_t x, y;
-			const bool active = slot < f.n_slots && slot_to_pixel(f, slot, x, y);
+			const bool active = slot < f.slot_end && slot_to_pixel(f, slot, x, y);
 			float4 so = make_float4(0.0f, 0.0f, 0.0f, 0.0f), sd = make_float4(0.0f, 0.0f, 1.0f, 0.0f);
 			if (active) { so = f.st_o[slot]; sd = f.st_d[slot]; }
 			const uint32_t bits = __float_as_uint(so.w);
@@ -232,9 +234,9 @@ namespace rzb
 	// ---------------------------------------------------------------- k_shade
 	__global__ void __launch_bounds__(128) k_shade(DScene sc, DFrame f)
 	{
-		const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
+		const uint32_t slot = f.slot_begin + blockIdx.x * blockDim.x + threadIdx.x;
 		uint32_t x = 0, y = 0;
-		const bool valid = slot < f.n_slots && slot_to_pixel(f, slot, x, y);
+		const bool valid = slot < f.slot_end && slot_to_pixel(f, slot, x, y);
 		// threads without a pixel still take part in the warp-level queue appends
 		float4 so = make_float4(0, 0, 0, 0), sd = make_float4(0, 0, 1, 0), ha = make_float4(0, 0, 0, 0);
 		float2 scol = make_float2(0, 0);
