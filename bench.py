@@ -38,6 +38,8 @@ WORKLOADS = {
     "heightfield_1m_1080p": ("heightfield_1m", dict(resolution=(1920, 1080))),
     "instancing_10m_1080p": ("instancing_10m", dict(resolution=(1920, 1080))),
     "cornell_512": ("cornell", dict(resolution=(512, 512))),
+    # configs[4]: the 1M-triangle scene at 3840x2160 (use with --split hybrid on 8 GPUs: 4 row bands x 2 sample streams)
+    "heightfield_1m_4k": ("heightfield_1m", dict(resolution=(3840, 2160))),
 }
 # reference-layout byte constants for the algorithmic traffic figure (SURVEY.md 8d / DESIGN.md)
 B_NODE, B_TRI, B_STATE, B_HIT = 48, 144, 57, 24
@@ -169,6 +171,9 @@ def main():
     ap.add_argument("--workload", default="materials_1080p", choices=sorted(WORKLOADS))
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--reduce", default="ipc", choices=["ipc", "nccl"])
+    ap.add_argument("--split", default="samples", choices=["samples", "tiles", "hybrid"],
+                    help="N>1: samples = every rank renders the whole frame with its own RNG stream (weak scaling, default); "
+                         "tiles = rank r renders row band r of N (strong scaling); hybrid = N/2 bands x 2 streams")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-aux", action="store_true")
     args = ap.parse_args()
@@ -180,7 +185,7 @@ def main():
 
     base = {"metric": "Mrays/s at 1080p (path segments per second, passes*W*H/t)", "unit": "Mrays/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic"}
+            "scaling": "weak" if args.split == "samples" else "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic"}
 
     if args.impl == "reference":
         if rank != 0:
@@ -224,7 +229,18 @@ def main():
     ctx.set_stream(stream.cuda_stream)
     ctx.set_scene(flat)
     ctx.set_camera(cam)
-    seed = parallel.stream_seed(20261018, rank)
+    # how the frame is sharded over the ranks (no data-path collective in any mode; accumulators are summed at resolve)
+    bands, streams = 1, world
+    if world > 1 and args.split == "tiles":
+        bands, streams = world, 1
+    elif world > 1 and args.split == "hybrid" and world % 2 == 0:
+        bands, streams = world // 2, 2
+    band, stream_id = rank // streams, rank % streams
+    rows = parallel.row_band(H, bands, band)
+    if bands > 1:
+        ctx.set_rows(*rows)
+    n_px = W * (rows[1] - rows[0])  # pixels this rank traces per pass
+    seed = parallel.stream_seed(20261018, stream_id)
     ctx.set_config(1, 1, MAX_DEPTH, capi.FLAG_NONE, seed)
     ctx.reset()
     rgba_host = torch.empty((H, W, 4), dtype=torch.uint8, pin_memory=True).numpy()
@@ -263,15 +279,16 @@ def main():
     st = ctx.render_stats()
     trace_ms, shade_ms, shadow_ms = float(st["last_trace_ms"]), float(st["last_shade_ms"]), float(st["last_shadow_ms"])
     launches = int(st["kernel_launches"]) - launches0
-    t_all = torch.tensor([ms, (float(ctx.read_accum()[..., 3].mean()) - alpha0)], dtype=torch.float64, device="cuda")
-    ms_max, spp_sum = float(t_all[0].item()), float(t_all[1].item())
+    t_all = torch.tensor([ms, (float(ctx.read_accum()[..., 3].mean()) - alpha0), float(args.steps) * n_px],
+                         dtype=torch.float64, device="cuda")
+    ms_max, spp_sum, rays_sum = float(t_all[0].item()), float(t_all[1].item()), float(t_all[2].item())
     if dist is not None:
         t_max = t_all.clone()
         dist.all_reduce(t_max, op=dist.ReduceOp.MAX)
         dist.all_reduce(t_all, op=dist.ReduceOp.SUM)
-        ms_max, spp_sum = float(t_max[0].item()), float(t_all[1].item())
-    value = world * args.steps * n_px / (ms_max * 1e-3) / 1e6
-    spp_per_s = spp_sum / (ms_max * 1e-3)
+        ms_max, spp_sum, rays_sum = float(t_max[0].item()), float(t_all[1].item()), float(t_all[2].item())
+    value = rays_sum / (ms_max * 1e-3) / 1e6
+    spp_per_s = spp_sum / (ms_max * 1e-3)  # completed camera paths per pixel per second, whole job
 
     # ---- algorithmic bytes of the dominant kernel: replay the same passes with the counting kernels
     # (the RNG is counter-based on (seed, pixel, pass): after a reset the same pass indices retrace the same rays)
@@ -332,7 +349,10 @@ def main():
     e2e_t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
     if dist is not None:
         dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
-    e2e_value = world * e2e_frames * RPP_E2E * n_px / float(e2e_t.item()) / 1e6
+    e2e_rays = torch.tensor([float(e2e_frames) * RPP_E2E * n_px], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(e2e_rays, op=dist.ReduceOp.SUM)
+    e2e_value = float(e2e_rays.item()) / float(e2e_t.item()) / 1e6
 
     # ---- secondary workload (config 3 geometry) and the CPU baseline: rank 0, N=1 only
     aux = None
@@ -373,7 +393,7 @@ def main():
             "value": value, "ms_per_step": ms_max / args.steps,
             "config": {"workload": args.workload, "resolution": [W, H], "triangles": int(flat["triangles"].shape[0]),
                        "instances": int(flat["instances"].shape[0]), "max_depth": MAX_DEPTH, "light_samples": [1, 1],
-                       "sharding": "sample streams x%d" % world if world > 1 else "single GPU",
+                       "sharding": ("%d row band(s) x %d sample stream(s)" % (bands, streams)) if world > 1 else "single GPU",
                        "reduce": args.reduce if world > 1 else None,
                        "l2": "no flush: per-pass working set %.0f MB (path state + queues + accumulator + scene) > 126 MB L2"
                              % working_set,
