@@ -236,10 +236,9 @@ def main():
     elif world > 1 and args.split == "hybrid" and world % 2 == 0:
         bands, streams = world // 2, 2
     band, stream_id = rank // streams, rank % streams
-    rows = parallel.row_band(H, bands, band)
     if bands > 1:
-        ctx.set_rows(*rows)
-    n_px = W * (rows[1] - rows[0])  # pixels this rank traces per pass
+        ctx.set_row_interleave(band, bands)  # 16-row chunk rows dealt round-robin: balances sky rows and geometry rows
+    n_px = W * sum(min(r * 16 + 16, H) - r * 16 for r in range((H + 15) // 16) if r % bands == band)  # pixels per pass on this rank
     seed = parallel.stream_seed(20261018, stream_id)
     ctx.set_config(1, 1, MAX_DEPTH, capi.FLAG_NONE, seed)
     ctx.reset()

@@ -251,6 +251,9 @@ int rzb_set_config(rzb_ctx* ctx, const rzb_config* config);
  * (default: all rows; reset by rzb_set_camera with a new resolution). Rows outside the band stay zero in the
  * accumulator, so the accumulators of disjoint bands (and of sample streams) combine by plain summation. */
 int rzb_set_rows(rzb_ctx* ctx, uint32_t row_begin, uint32_t row_end);
+/* Interleaved variant (load-balanced: sky rows and geometry rows are spread over all contexts): this context renders
+ * the 16-pixel-high chunk rows r with r % count == index. Combines with rzb_set_rows; default index 0, count 1. */
+int rzb_set_row_interleave(rzb_ctx* ctx, uint32_t index, uint32_t count);
 
 /* ---- frame: replaces Renderer::renderFunction (cuda_engine_renderer.cu:73-262) ---- */
 /* drop accumulated samples, regenerate pixel-centre camera rays (passReset + generateCameraRay). */

@@ -100,6 +100,7 @@ SYMBOLS = {
     "rzb_set_camera": (C.c_int, [_P, _P]),
     "rzb_set_config": (C.c_int, [_P, _P]),
     "rzb_set_rows": (C.c_int, [_P, C.c_uint32, C.c_uint32]),
+    "rzb_set_row_interleave": (C.c_int, [_P, C.c_uint32, C.c_uint32]),
     "rzb_reset": (C.c_int, [_P]),
     "rzb_render": (C.c_int, [_P, C.c_uint32]),
     "rzb_resolve": (C.c_int, [_P, _P, _P, C.POINTER(C.c_uint64)]),
@@ -326,6 +327,10 @@ class Context:
     def set_rows(self, row_begin: int, row_end: int):
         """Tile split: render only image rows [row_begin, row_end)."""
         self._check(self._l.rzb_set_rows(self._h, int(row_begin), int(row_end)))
+
+    def set_row_interleave(self, index: int, count: int):
+        """Interleaved tile split: render the 16-row chunk rows r with r % count == index."""
+        self._check(self._l.rzb_set_row_interleave(self._h, int(index), int(count)))
 
     # -- frame
     def reset(self):

@@ -73,6 +73,7 @@ struct rzb_ctx
 	uint32_t shadow_capacity_alloc = 0;
 	void* d_shadow[3] = {nullptr, nullptr, nullptr};
 	uint32_t row_begin = 0, row_end = 0; // tile split (rzb_set_rows)
+	uint32_t il_index = 0, il_count = 1; // interleaved tile split (rzb_set_row_interleave)
 
 	// scratch for ray-set calls
 	DeviceBuffer scratch[4];
@@ -192,6 +193,20 @@ namespace
 		return RZB_OK;
 	}
 
+	// pixels this context traces per pass (row band intersected with its interleaved 16-row chunk rows)
+	uint64_t bandPixels(const rzb_ctx* ctx)
+	{
+		const DFrame& f = ctx->frame;
+		uint64_t rows = 0;
+		for (uint32_t r = f.row_begin / 16u; r * 16u < f.row_end; ++r)
+		{
+			if (r % std::max(f.il_count, 1u) != f.il_index) continue;
+			const uint32_t y0 = std::max(r * 16u, f.row_begin), y1 = std::min(r * 16u + 16u, f.row_end);
+			rows += y1 > y0 ? y1 - y0 : 0u;
+		}
+		return rows * ctx->cam.width;
+	}
+
 	void applyRows(rzb_ctx* ctx)
 	{
 		DFrame& f = ctx->frame;
@@ -199,6 +214,8 @@ namespace
 		f.row_end = std::min(std::max(ctx->row_end, f.row_begin), ctx->cam.height);
 		f.slot_begin = (f.row_begin / 16u) * f.tiles_x * 256u;
 		f.slot_end = f.row_end > f.row_begin ? ((f.row_end + 15u) / 16u) * f.tiles_x * 256u : f.slot_begin;
+		f.il_index = ctx->il_index;
+		f.il_count = std::max(ctx->il_count, 1u);
 	}
 
 	int ensureShadowQueue(rzb_ctx* ctx)
@@ -553,6 +570,16 @@ extern "C" int rzb_set_rows(rzb_ctx* ctx, uint32_t row_begin, uint32_t row_end)
 	return RZB_OK;
 }
 
+extern "C" int rzb_set_row_interleave(rzb_ctx* ctx, uint32_t index, uint32_t count)
+{
+	if (!ctx) return RZB_ERR_INVALID;
+	if (count == 0 || index >= count) return fail(ctx, RZB_ERR_INVALID, "rzb_set_row_interleave: need index < count");
+	ctx->il_index = index;
+	ctx->il_count = count;
+	ctx->frame_ready = false;
+	return RZB_OK;
+}
+
 extern "C" int rzb_set_config(rzb_ctx* ctx, const rzb_config* config)
 {
 	if (!ctx || !config) return fail(ctx, RZB_ERR_INVALID, "rzb_set_config: NULL argument");
@@ -660,7 +687,7 @@ extern "C" int rzb_render(rzb_ctx* ctx, uint32_t passes)
 			ctx->sampled_passes += 1;
 		}
 		ctx->passes += 1;
-		if (count) ctx->counted_segments += uint64_t(ctx->cam.width) * (f.row_end - f.row_begin);
+		if (count) ctx->counted_segments += bandPixels(ctx);
 	}
 	RZB_CUDA(ctx, cudaEventRecord(ctx->ev_end, ctx->stream));
 	RZB_CUDA(ctx, cudaGetLastError());
@@ -703,7 +730,7 @@ extern "C" int rzb_resolve(rzb_ctx* ctx, uint8_t* rgba8, float* depth, uint64_t*
 	PeerList peers{};
 	const int rc = tonemapAndCopy(ctx, peers, rgba8, depth);
 	if (rc) return rc;
-	if (ray_count) *ray_count = ctx->passes * uint64_t(ctx->cam.width) * (ctx->frame.row_end - ctx->frame.row_begin);
+	if (ray_count) *ray_count = ctx->passes * bandPixels(ctx);
 	return RZB_OK;
 }
 
@@ -713,7 +740,7 @@ extern "C" int rzb_resolve_peers(rzb_ctx* ctx, rzb_ctx* const* peers_in, uint32_
 	if (!ctx || (n_peers && !peers_in) || n_peers > 8) return fail(ctx, RZB_ERR_INVALID, "rzb_resolve_peers: bad arguments");
 	DeviceGuard guard(ctx->device);
 	PeerList peers{};
-	uint64_t rays = ctx->passes * uint64_t(ctx->cam.width) * (ctx->frame.row_end - ctx->frame.row_begin);
+	uint64_t rays = ctx->passes * bandPixels(ctx);
 	for (uint32_t i = 0; i < n_peers; ++i)
 	{
 		rzb_ctx* p = peers_in[i];
@@ -733,7 +760,7 @@ extern "C" int rzb_resolve_peers(rzb_ctx* ctx, rzb_ctx* const* peers_in, uint32_
 			RZB_CUDA(ctx, cudaStreamSynchronize(p->stream));
 		}
 		peers.accum[i] = p->frame.accum;
-		rays += p->passes * uint64_t(p->cam.width) * (p->frame.row_end - p->frame.row_begin);
+		rays += p->passes * bandPixels(p);
 	}
 	peers.count = n_peers;
 	const int rc = tonemapAndCopy(ctx, peers, rgba8, depth);
@@ -782,7 +809,7 @@ extern "C" int rzb_get_render_stats(rzb_ctx* ctx, rzb_render_stats* out)
 	RZB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
 	std::memset(out, 0, sizeof(*out));
 	out->passes = ctx->passes;
-	out->ray_count = ctx->passes * uint64_t(ctx->cam.width) * (ctx->frame.row_end - ctx->frame.row_begin);
+	out->ray_count = ctx->passes * bandPixels(ctx);
 	out->kernel_launches = ctx->launches;
 	if (ctx->passes)
 	{

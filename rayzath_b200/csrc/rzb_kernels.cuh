@@ -31,6 +31,7 @@ namespace rzb
 		uint32_t tiles_x, tiles_y, n_slots;
 		uint32_t row_begin, row_end;    // tile split: this context renders image rows [row_begin, row_end)
 		uint32_t slot_begin, slot_end;  // the 256-slot chunks that cover those rows
+		uint32_t il_index, il_count;    // interleaved tile split: only 16-row chunk rows r with r % il_count == il_index
 		float4* st_o;   // {o.xyz, bits(depth | medium << 8)}
 		float4* st_d;   // {d.xyz, throughput.r}
 		float2* st_c;   // {throughput.g, throughput.b}
@@ -58,7 +59,7 @@ namespace rzb
 		const uint32_t chunk = slot >> 8, tile = (slot >> 5) & 7u, within = slot & 31u;
 		x = (chunk % f.tiles_x) * 16u + (tile & 1u) * 8u + (within & 7u);
 		y = (chunk / f.tiles_x) * 16u + (tile >> 1) * 4u + (within >> 3);
-		return x < f.cam.width && y >= f.row_begin && y < f.row_end;
+		return x < f.cam.width && y >= f.row_begin && y < f.row_end && (chunk / f.tiles_x) % f.il_count == f.il_index;
 	}
 
 	__device__ __forceinline__ Stack make_stack(uint2* smem_base)

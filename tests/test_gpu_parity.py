@@ -372,7 +372,22 @@ def test_tile_split_sums_to_the_full_frame(flats, worlds):
     rgba, _, rays = bands[0].resolve_peers(bands[1:])
     assert rays == 10 * int(cam[0]["width"]) * h
     assert np.array_equal(rgba, full.resolve()[0])
-    for c in bands + [full]:
+    # interleaved split (16-row chunk rows dealt round-robin over 3 contexts)
+    inter = []
+    for i in range(3):
+        c = capi.Context(0)
+        c.set_scene(flats["cornell"])
+        c.set_camera(cam)
+        c.set_config(max_depth=6, seed=21)
+        c.set_row_interleave(i, 3)
+        c.reset()
+        c.render(10)
+        inter.append(c)
+    parts = [c.read_accum() for c in inter]
+    assert (parts[0][16:32] == 0).all() and (parts[1][:16] == 0).all() and parts[1][16:32, :, 3].sum() > 0
+    assert np.array_equal(parts[0] + parts[1] + parts[2], a_full)
+    assert sum(int(c.render_stats()["ray_count"]) for c in inter) == 10 * int(cam[0]["width"]) * h
+    for c in bands + inter + [full]:
         c.close()
 
 
