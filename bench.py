@@ -117,38 +117,44 @@ def build_world(workload):
 
 
 # ---------------------------------------------------------------------------------------------- reference arm
-def reference_run(workload, steps, warmup, budget_s=150.0):
+def reference_run(workload, steps, warmup, budget_s=240.0):
     """The reference's own CPU engine (oracle/_ref/rz_ref_tool render) on this box's cores. A step = one
-    Engine::renderWorld(CPU) = one pass over the frame; the frame is a bounded sample of the workload: same scene
-    and camera at a resolution reduced until (steps + warmup) passes fit the time budget."""
+    Engine::renderWorld(CPU) = one pass over the frame. The frame is the workload's own (full resolution) whenever
+    (steps + warmup) passes fit the time budget; otherwise a bounded sample of it: same scene and camera at the
+    largest resolution from a list of 128x128-tile-friendly sizes (the CPU engine hands 128x128 tiles to its worker
+    threads, cpu_engine_renderer.cpp:186-205; odd small frames would leave threads idle and understate it)."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import rz_oracle as O
     from rayzath_b200 import scenes
     name, kw = WORKLOADS[workload]
-    full = kw["resolution"]
+    full = tuple(kw["resolution"])
     tmp = tempfile.mkdtemp(prefix="rzb_bench_ref_")
 
-    def run(res, passes, wu):
+    def run(res, passes, wu, timeout):
         kw2 = dict(kw)
         kw2["resolution"] = res
         w = scenes.CONFIGS[name](**kw2)
         path = w.save_reference(os.path.join(tmp, "%dx%d" % res))
-        return O.ref_tool("render", path, passes, "-", MAX_DEPTH, 1, 1, wu, timeout=max(60.0, 3.0 * budget_s), attempts=2)
+        return O.ref_tool("render", path, passes, "-", MAX_DEPTH, 1, 1, wu, timeout=timeout, attempts=2)
 
-    probe_res = (max(full[0] // 8, 16), max(full[1] // 8, 16))
-    probe = run(probe_res, 3, 1)
-    rps = probe["timed_rays"] / max(probe["seconds"], 1e-9)
-    div = 1
-    while div < 16 and (steps + warmup) * (full[0] // div) * (full[1] // div) / rps > budget_s:
-        div *= 2
-    res = (max(full[0] // div, 16), max(full[1] // div, 16))
-    info = run(res, steps + warmup, max(warmup, 1))
+    probe = run(full, 3, 1, 300.0)  # 2 timed full-resolution passes
+    s_per_px = probe["seconds"] / max(probe["timed_rays"], 1)
+    aspect = full[0] / full[1]
+    options = [full] + [r for r in ((1536, 896), (1280, 768), (1024, 640), (768, 512), (512, 384), (384, 256), (256, 128))
+                        if r[0] * r[1] < full[0] * full[1]]
+    res = options[-1]
+    for r in options:
+        if (steps + warmup) * r[0] * r[1] * s_per_px <= budget_s:
+            res = r
+            break
+    info = run(res, steps + warmup, max(warmup, 1), max(120.0, 4.0 * budget_s))
     timed_passes = max(info["timed_passes"], 1)
     value = info["timed_rays"] / info["seconds"] / 1e6
+    frac = (res[0] * res[1]) / float(full[0] * full[1])
     return {
         "value": value, "ms_per_step": info["seconds"] / timed_passes * 1e3, "cores": info["threads"],
-        "sample": "%d passes of the %s scene at %dx%d (1/%d of the pixels of %dx%d), max depth %d, reference CPU engine"
-                  % (timed_passes, workload, res[0], res[1], div * div, full[0], full[1], MAX_DEPTH),
+        "sample": "%d passes of the %s scene at %dx%d (%.0f %% of the pixels of %dx%d), max depth %d, reference CPU engine"
+                  % (timed_passes, workload, res[0], res[1], 100.0 * frac, full[0], full[1], MAX_DEPTH),
         "kind": "reference",
     }
 
@@ -380,7 +386,7 @@ def main():
                 aux = {"workload": "heightfield_1m_1080p", "error": repr(e)}
         if not args.no_cpu_baseline:
             try:
-                r = reference_run(args.workload, 4, 1, budget_s=25.0)
+                r = reference_run(args.workload, 8, 1, budget_s=25.0)
                 cpu = {"value": r["value"], "unit": "Mrays/s", "cores": r["cores"], "kind": r["kind"], "sample": r["sample"]}
             except Exception as e:
                 cpu = {"value": None, "unit": "Mrays/s", "cores": os.cpu_count(), "kind": "reference", "sample": "failed: %r" % e}
