@@ -1061,31 +1061,14 @@ extern "C" int rzb_raycast(rzb_ctx* ctx, uint32_t* instance, uint32_t* material_
 	const uint32_t px = std::min(ctx->cam.raycast_pixel[0], ctx->cam.width - 1u);
 	const uint32_t py = std::min(ctx->cam.raycast_pixel[1], ctx->cam.height - 1u);
 	DeviceGuard guard(ctx->device);
-	// depth of the pick pixel, then a pixel-centre ray with range depth * [0.99, 1.01] (cuda_render_kernel.cu:130-144)
-	float depth = 0.0f;
+	uint32_t* d_out = ctx->d_counters + 40;
+	k_raycast<<<1, 32, 0, ctx->stream>>>(ctx->sc, makeDeviceCamera(ctx->cam), ctx->frame.depth, px, py, d_out);
+	ctx->launches += 1;
+	RZB_CUDA(ctx, cudaGetLastError());
+	uint32_t h[2] = {RZB_NO_INDEX, RZB_NO_INDEX};
+	RZB_CUDA(ctx, cudaMemcpyAsync(h, d_out, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
 	RZB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-	RZB_CUDA(ctx, cudaMemcpy(&depth, ctx->frame.depth + size_t(py) * ctx->cam.width + px, 4, cudaMemcpyDeviceToHost));
-	const uint32_t n = ctx->cam.width * ctx->cam.height;
-	std::vector<float> o(size_t(n) * 3), d(size_t(n) * 3), nf(size_t(n) * 2);
-	int rc = rzb_generate_camera_rays(ctx, o.data(), d.data(), nf.data());
-	if (rc) return rc;
-	const size_t i = size_t(py) * ctx->cam.width + px;
-	const float range[2] = {depth * 0.99f, depth * 1.01f};
-	rzb_hit hit{};
-	rc = rzb_trace_closest(ctx, &o[3 * i], &d[3 * i], range, 1, &hit, nullptr);
-	if (rc) return rc;
-	if (hit.instance != RZB_NO_INDEX)
-	{
-		*instance = hit.instance;
-		// material slot of the hit triangle: read back from the hot record through the BVH-order hit
-		DHit dh{};
-		RZB_CUDA(ctx, cudaMemcpy(&dh, ctx->scratch[2].ptr, sizeof(DHit), cudaMemcpyDeviceToHost));
-		const uint32_t tri = dh.tri_bits & kHitTriMask;
-		float4 h2{};
-		RZB_CUDA(ctx, cudaMemcpy(&h2, ctx->sc.tri_hot + 3 * size_t(tri) + 2, sizeof(float4), cudaMemcpyDeviceToHost));
-		uint32_t slot;
-		std::memcpy(&slot, &h2.y, 4);
-		*material_slot = slot;
-	}
+	*instance = h[0];
+	*material_slot = h[1];
 	return RZB_OK;
 }

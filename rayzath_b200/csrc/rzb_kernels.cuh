@@ -586,6 +586,31 @@ namespace rzb
 		}
 	}
 
+	// pick ray (rayCast kernel, cuda_render_kernel.cu:130-144): pixel-centre ray of the pick pixel with the range
+	// depth * [0.99, 1.01]; out[0] = host index of the instance, out[1] = material slot of the triangle
+	__global__ void __launch_bounds__(32) k_raycast(DScene sc, DCamera cam, const float* __restrict__ depth, uint32_t px,
+		uint32_t py, uint32_t* __restrict__ out)
+	{
+		__shared__ uint2 smem_stack[kSmemStack * kTraceBlock];
+		__shared__ ParkedRay smem_park[32];
+		Stack st = make_stack(smem_stack);
+		TraceCounters cnt{0u, 0u, 0u, 0u};
+		const bool active = threadIdx.x == 0;
+		V3 o, d;
+		camera_simple_ray(cam, px, py, o, d);
+		const float z = depth[size_t(py) * cam.width + px];
+		RayResult r;
+		trace_ray<false, false, true>(sc, active, o, d, z * 0.99f, z * 1.01f, st, smem_park[threadIdx.x], cnt, r);
+		if (!active) return;
+		out[0] = RZB_NO_INDEX;
+		out[1] = RZB_NO_INDEX;
+		if (r.inst != kNoIndex)
+		{
+			out[0] = sc.inst_host_index[r.inst];
+			out[1] = __float_as_uint(__ldg(sc.tri_hot + 3 * size_t(r.tri) + 2).y);
+		}
+	}
+
 	__global__ void k_camera_rays(DCamera cam, float4* __restrict__ ray_o_near, float4* __restrict__ ray_d_far)
 	{
 		const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;

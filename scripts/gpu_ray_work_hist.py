@@ -30,6 +30,7 @@ for wl in ("heightfield_1m_1080p", "materials_1080p"):
                 "| batch32: mean of max %.1f, efficiency %.2f" % (bs.max(1).mean(), bs.mean() / bs.max(1).mean()))
             ms = [ctx.trace_closest_device(ro.data_ptr(), rd.data_ptr(), o.shape[0], hits.data_ptr(), timed=True) for _ in range(4)]
             print("     time ms", min(ms), "Mrays/s", o.shape[0] / min(ms) / 1e3)
+            np.savez_compressed(os.path.join(ROOT, "gpurun_out", "raywork_%s_%s.npz" % (wl, label)), steps=steps.astype(np.uint16), tris=tris.astype(np.uint16))
             return raw, t
         o1, d1, nf1 = o[order], d[order], nf[order]
         raw, t = run(o1, d1, nf1, "primary")
