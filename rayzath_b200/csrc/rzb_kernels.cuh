@@ -2,18 +2,20 @@
 // reference: cuda_render_kernel.cu:67-121, but split by stage instead of one megakernel):
 //
 //   k_reset          zero the accumulator, pixel-centre rays into the path state      (passReset + generateCameraRay)
-//   k_trace_paths    closest hit for every live path; persistent warps pull 32-ray batches with one atomic
+//   k_trace_paths    closest hit for every path; persistent warps pull 32-slot batches with one atomic
 //   k_shade          surface analysis, emission, BSDF sampling, NEE set-up (shadow rays appended to a queue by
 //                    warp-ballot compaction), accumulation, continue-or-regenerate
 //   k_trace_shadow   any-hit over the compacted shadow queue; visible light is added to the accumulator
 //   k_tonemap        ComputeFinalColor (cuda_postprocess_kernel.cu:38-58), optionally summing peer accumulators
 //                    over NVLink loads in the same pass
+//   k_raycast        the pick ray (rayCast, cuda_render_kernel.cu:130-144)
+//   k_pack_*         scene repacking on the device (rzb_set_scene)
 // plus the ray-set entry points used for ID parity (k_trace_rays, k_trace_any_rays, k_convert_hits,
 // k_camera_rays).
 //
-// Path state lives in HBM as three coalesced arrays indexed by slot (40 B per pixel): slots follow 8x4 pixel
-// tiles so that a warp's 32 primary rays cover a compact screen patch (better node/triangle reuse in L1/L2 than
-// the reference's 32x1 rows).
+// Path state lives in HBM as three coalesced arrays indexed by slot (40 B per pixel): 256 consecutive slots cover a
+// 16x16-pixel chunk (eight 8x4 tiles), so the 32 rays of a batch start in one 8x4 screen patch (better node and
+// triangle reuse in L1/L2 than the reference's 32x1 rows) and a context can own a row band or interleaved chunk rows.
 #pragma once
 
 #include "rzb_shade.cuh"
