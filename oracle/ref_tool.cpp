@@ -12,6 +12,9 @@
 //                                               <passes> x Engine::renderWorld(CPU), the first <warmup> of them untimed (the first call
 //                                               also builds the BVHs) ; dumps float accumulator, RGBA8, depth ; prints timing JSON
 //   headless  <tasks.json> [report_dir] [-r]    the reference's own Application/headless.cpp entry
+//   rendercuda <scene.json> <calls> <rpp> <out.rzs|-> [max_depth] [spot_samples] [direct_samples] [warmup_calls=1]
+//                                               (rz_ref_tool_cuda only) <calls> x Engine::renderWorld(CUDAGPU) with <rpp> passes each:
+//                                               the reference's own CUDA engine; dumps RGBA8 + depth ; prints timing JSON
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -243,6 +246,57 @@ static int cmdRender(int argc, char** argv)
 	return 0;
 }
 
+#ifdef RZ_WITH_CUDA_ENGINE
+static int cmdRenderCuda(int argc, char** argv)
+{
+	const std::string scene = argv[2];
+	const uint32_t calls = uint32_t(std::atoi(argv[3]));
+	const uint32_t rpp = uint32_t(std::atoi(argv[4]));
+	const std::string out_path = argv[5];
+	auto& engine = RZ::Engine::instance();
+	auto& world = engine.world();
+	world.loader().loadScene(scene);
+	if (argc > 6) engine.renderConfig().tracing().maxDepth(uint8_t(std::atoi(argv[6])));
+	if (argc > 7) engine.renderConfig().lightSampling().spotLight(uint8_t(std::atoi(argv[7])));
+	if (argc > 8) engine.renderConfig().lightSampling().directLight(uint8_t(std::atoi(argv[8])));
+	const uint32_t warmup = std::min(calls, argc > 9 ? uint32_t(std::atoi(argv[9])) : 1u);
+	engine.renderConfig().tracing().rpp(rpp);
+	if (engine.renderEngine() != RZ::Engine::RenderEngine::CUDAGPU)
+	{
+		std::fprintf(stderr, "rz_ref_tool: the reference CUDA engine failed to initialise (no GPU?)\n");
+		return 3;
+	}
+	auto& cameras = world.container<RZ::ObjectType::Camera>();
+	auto rayCount = [&]() {
+		uint64_t rays = 0;
+		for (uint32_t i = 0; i < cameras.count(); ++i) if (cameras[i]) rays += cameras[i]->rayCount();
+		return rays;
+	};
+	for (uint32_t c = 0; c < warmup; ++c) engine.renderWorld(RZ::Engine::RenderEngine::CUDAGPU, true, true);
+	const uint64_t rays0 = rayCount();
+	const auto t0 = std::chrono::steady_clock::now();
+	for (uint32_t c = warmup; c < calls; ++c) engine.renderWorld(RZ::Engine::RenderEngine::CUDAGPU, true, true);
+	const double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+	const uint64_t rays1 = rayCount();
+	rzs::Writer w;
+	if (cameras.count() && cameras[0])
+	{
+		auto& cam = *cameras[0];
+		w.add("rgba8", cam.imageBuffer().GetMapAddress(), 4, uint64_t(cam.width()) * cam.height());
+		w.add("depth", cam.depthBuffer().GetMapAddress(), 4, uint64_t(cam.width()) * cam.height());
+		const uint32_t res[2] = {cam.width(), cam.height()};
+		w.add("resolution", res, 4, 2);
+	}
+	if (out_path != "-") w.write(out_path);
+	std::printf("{\"calls\": %u, \"rpp\": %u, \"timed_calls\": %u, \"timed_rays\": %llu, \"rays\": %llu, \"seconds\": %.6f}\n",
+		calls, rpp, calls - warmup, (unsigned long long)(rays1 - rays0), (unsigned long long)rays1, secs);
+	// the engine singleton is destroyed after the CUDA runtime has shut down (the reference throws from its destructor
+	// then: "driver shutting down"); results are complete, so leave without running static destructors
+	std::fflush(stdout);
+	std::_Exit(0);
+}
+#endif
+
 int main(int argc, char** argv)
 {
 	try
@@ -252,6 +306,9 @@ int main(int argc, char** argv)
 		if (cmd == "trace" && argc == 5) return cmdTrace(argv[2], argv[3], argv[4], false);
 		if (cmd == "traceany" && argc == 5) return cmdTrace(argv[2], argv[3], argv[4], true);
 		if (cmd == "render" && argc >= 5) return cmdRender(argc, argv);
+#ifdef RZ_WITH_CUDA_ENGINE
+		if (cmd == "rendercuda" && argc >= 6) return cmdRenderCuda(argc, argv);
+#endif
 #ifdef RZ_WITH_HEADLESS
 		if (cmd == "headless" && argc >= 3)
 		{
