@@ -306,6 +306,10 @@ def main():
     nodes_per_seg = float(wc["closest_top_nodes"] + wc["closest_mesh_nodes"]) / seg
     tris_per_seg = float(wc["closest_triangles"]) / seg
     shadow_per_seg = float(wc["shadow_rays"]) / seg
+    # share of lane-time the whole-warp batches keep busy (work of a ray = pair steps + triangle tests)
+    lane_util = {"closest": float(wc["closest_lane_work"]) / max(int(wc["closest_batch_work"]), 1),
+                 "shadow": float(wc["shadow_lane_work"]) / max(int(wc["shadow_batch_work"]), 1),
+                 "dropped_non_finite_samples": int(wc["invalid_rays"])}
     bytes_per_seg = B_STATE + nodes_per_seg * B_NODE + tris_per_seg * B_TRI + B_HIT
     achieved = bytes_per_seg * n_px / (trace_ms * 1e-3) / 1e9 if trace_ms > 0 else None
     traffic = None
@@ -413,7 +417,7 @@ def main():
                          "frac": (achieved / peak) if achieved else None, "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_segment": bytes_per_seg, "nodes_per_segment": nodes_per_seg,
                          "triangles_per_segment": tris_per_seg, "shadow_rays_per_segment": shadow_per_seg,
-                         "segments_per_launch": n_px},
+                         "segments_per_launch": n_px, "batch_lane_utilisation": lane_util},
             "cpu_baseline": cpu, "aux": aux,
         })
         print(json.dumps(line), flush=True)

@@ -227,7 +227,12 @@ typedef struct rzb_work_counters
 	uint64_t shadow_top_nodes, shadow_instances, shadow_mesh_nodes, shadow_triangles;
 	uint64_t shadow_rays;
 	uint64_t segments; /* closest-hit queries = passes * pixels */
-	uint64_t invalid_rays; /* path segments generated with a non-finite origin or direction */
+	uint64_t invalid_rays; /* path segments whose sample was non-finite: dropped, path ended (see k_shade) */
+	/* SIMT lane utilisation of the whole-warp ray batches: lane_work = sum over rays of (pair steps + triangle tests),
+	 * batch_work = sum over 32-ray batches of 32 x the largest such figure in the batch; lane_work / batch_work is the
+	 * fraction of lane-time a batch keeps busy if every step cost the same. */
+	uint64_t closest_lane_work, closest_batch_work;
+	uint64_t shadow_lane_work, shadow_batch_work;
 } rzb_work_counters;
 
 /* ---- context ---- */

@@ -58,7 +58,7 @@ render_stats_dtype = np.dtype([("passes", u8), ("ray_count", u8), ("shadow_rays"
 work_counters_dtype = np.dtype([(n, u8) for n in (
     "closest_top_nodes", "closest_instances", "closest_mesh_nodes", "closest_triangles",
     "shadow_top_nodes", "shadow_instances", "shadow_mesh_nodes", "shadow_triangles", "shadow_rays", "segments",
-    "invalid_rays")])
+    "invalid_rays", "closest_lane_work", "closest_batch_work", "shadow_lane_work", "shadow_batch_work")])
 
 EXPECTED_SIZES = {
     "rzb_node": (node_dtype, 32), "rzb_triangle": (triangle_dtype, 112), "rzb_mesh": (mesh_dtype, 16),

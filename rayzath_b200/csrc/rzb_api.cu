@@ -853,6 +853,8 @@ extern "C" int rzb_get_work_counters(rzb_ctx* ctx, rzb_work_counters* out)
 	out->shadow_rays = h[8];
 	out->segments = ctx->counted_segments;
 	out->invalid_rays = h[9];
+	out->closest_lane_work = h[10]; out->closest_batch_work = h[11];
+	out->shadow_lane_work = h[12]; out->shadow_batch_work = h[13];
 	return RZB_OK;
 }
 

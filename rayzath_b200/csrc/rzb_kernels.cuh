@@ -170,6 +170,17 @@ namespace rzb
 		}
 	}
 
+	// RZB_FLAG_COUNT_WORK: lane work and 32 x batch maximum of one whole-warp batch (rzb_work_counters)
+	__device__ __forceinline__ void batch_utilisation(const uint32_t work, unsigned long long* out)
+	{
+		const uint32_t sum = __reduce_add_sync(0xFFFFFFFFu, work), mx = __reduce_max_sync(0xFFFFFFFFu, work);
+		if ((threadIdx.x & 31u) == 0u)
+		{
+			atomicAdd(out, (unsigned long long)sum);
+			atomicAdd(out + 1, 32ull * mx);
+		}
+	}
+
 	template <bool STATS>
 	__global__ void __launch_bounds__(kTraceBlock, 6) k_trace_paths(DScene sc, DFrame f)
 	{
@@ -205,6 +216,7 @@ namespace rzb
 			}
 			RayResult r;
 			trace_ray<false, STATS>(sc, active, v3(so.x, so.y, so.z), v3(sd.x, sd.y, sd.z), near_, far_, st, park, cnt, r);
+			if (STATS) batch_utilisation(active ? r.steps + r.tris : 0u, f.work + 10);
 			if (!active) continue;
 			uint32_t tri_bits = flags | (r.external ? kHitExternalBit : 0u);
 			tri_bits |= (r.tri == kNoIndex) ? kHitTriMask : (r.tri & kHitTriMask);
@@ -232,6 +244,15 @@ namespace rzb
 		f.sh_o[idx] = make_float4(o.x, o.y, o.z, dist);
 		f.sh_d[idx] = make_float4(d.x, d.y, d.z, __uint_as_float(pixel));
 		f.sh_c[idx] = make_float4(contrib.x, contrib.y, contrib.z, 0.0f);
+	}
+
+	__device__ __forceinline__ bool all_finite(const float3 a, const float3 b, const float3 c)
+	{
+		// a sum of finite terms can overflow, so test the largest magnitude
+		const float m = fmaxf(fmaxf(fmaxf(fabsf(a.x), fabsf(a.y)), fmaxf(fabsf(a.z), fabsf(b.x))),
+			fmaxf(fmaxf(fmaxf(fabsf(b.y), fabsf(b.z)), fmaxf(fabsf(c.x), fabsf(c.y))), fabsf(c.z)));
+		// fmaxf drops NaN operands: catch them through the sum
+		return m < 3.0e38f && (a.x + a.y + a.z + b.x + b.y + b.z + c.x + c.y + c.z) == (a.x + a.y + a.z + b.x + b.y + b.z + c.x + c.y + c.z);
 	}
 
 	// ---------------------------------------------------------------- k_shade
@@ -356,8 +377,8 @@ namespace rzb
 						const float Lw = 1.0f - vSw;
 						const float Le = L.emission * solid_angle * b;
 						const float radiance = Le * Lw + Se * vSw;
-						const bool want = radiance >= 1.0e-4f;
 						const float3 c = f3(L.color[0], L.color[1], L.color[2]) * brdf_color * (radiance * inv_pdf) * carry;
+						const bool want = radiance >= 1.0e-4f && all_finite(c, next_o, vPLn);
 						shadow_push(f, want, next_o, vPLn, kFltMax, pixel, c);
 					}
 				}
@@ -401,8 +422,8 @@ namespace rzb
 						const float Lw = 1.0f - vSw;
 						const float Le = L.emission * solid_angle * b;
 						const float radiance = (Le * Lw + Se * vSw) * sctr * beam;
-						const bool want = b >= 1.0e-4f && beam >= 1.0e-4f && radiance >= 1.0e-4f;
 						const float3 c = f3(L.color[0], L.color[1], L.color[2]) * brdf_color * (radiance * inv_pdf) * carry;
+						const bool want = b >= 1.0e-4f && beam >= 1.0e-4f && radiance >= 1.0e-4f && all_finite(c, next_o, vPLn);
 						shadow_push(f, want, next_o, vPLn, dPL, pixel, c);
 					}
 				}
@@ -411,6 +432,14 @@ namespace rzb
 			thr = thr + (thr * s.color - thr) * s.tint_factor;
 			path_continues = depth < f.max_depth;
 		}
+		// The reference's samplers do not keep directions at unit length (localCoordinate builds an unnormalised basis,
+		// the "flip above the surface" step uses the normalised dot product: cuda_render_parts.cuh:1254-1301,
+		// cuda_material.cuh:238-240); a chain of scattering bounces can square the length every bounce until the ray
+		// overflows (seen once per ~4e8 segments on the materials scene; the reference then keeps a NaN pixel for
+		// good). Deliberate difference: a non-finite sample is dropped and its path ended.
+		bool discarded = false;
+		if (!all_finite(final_color, final_color, final_color)) { final_color = f3(0.0f, 0.0f, 0.0f); discarded = true; }
+		if (path_continues && !all_finite(next_o, next_d, thr)) { path_continues = false; discarded = true; }
 		// ---- epilogue (cuda_render_kernel.cu:98-120)
 		if (valid)
 		{
@@ -428,8 +457,7 @@ namespace rzb
 				thr = f3(1.0f, 1.0f, 1.0f);
 				depth = 0u;
 			}
-			if ((sc.flags & RZB_FLAG_COUNT_WORK) && !isfinite(next_o.x + next_o.y + next_o.z + next_d.x + next_d.y + next_d.z))
-				atomicAdd(f.work + 9, 1ull); // rays with a non-finite origin or direction (they would walk the whole tree)
+			if ((sc.flags & RZB_FLAG_COUNT_WORK) && discarded) atomicAdd(f.work + 9, 1ull); // rzb_work_counters::invalid_rays
 			f.st_o[slot] = make_float4(next_o.x, next_o.y, next_o.z, __uint_as_float((medium << kMediumShift) | depth));
 			f.st_d[slot] = make_float4(next_d.x, next_d.y, next_d.z, thr.x);
 			f.st_c[slot] = make_float2(thr.y, thr.z);
@@ -437,6 +465,10 @@ namespace rzb
 	}
 
 	// ---------------------------------------------------------------- k_trace_shadow
+	// Any-hit queries over the shadow queue, whole-warp batches of 32 entries in warp-synchronised rounds.
+	// Measured and dropped: giving finished lanes new rays between rounds (threshold 1..24 idle lanes) raises the share
+	// of busy lane-rounds from 0.44 to 0.70-0.88 on the materials scene but not the speed (1.33 -> 1.28..1.41 ms; 1M
+	// triangles 0.44 -> 0.46..0.62 ms): a round costs what its longest descend / leaf loop costs.
 	template <bool STATS>
 	__global__ void __launch_bounds__(kTraceBlock, 6) k_trace_shadow(DScene sc, DFrame f)
 	{
@@ -457,6 +489,7 @@ namespace rzb
 			if (active) { o = f.sh_o[i]; d = f.sh_d[i]; }
 			RayResult r;
 			trace_ray<true, STATS>(sc, active, v3(o.x, o.y, o.z), v3(d.x, d.y, d.z), 0.0f, o.w, st, park, cnt, r);
+			if (STATS) batch_utilisation(active ? r.steps + r.tris : 0u, f.work + 12);
 			const float w = r.mask.w;
 			if (!active || w <= 0.0f) continue;
 			const float4 c = f.sh_c[i];

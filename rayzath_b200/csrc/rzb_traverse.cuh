@@ -102,7 +102,243 @@ namespace rzb
 	};
 	static_assert(sizeof(ParkedRay) == 48, "ParkedRay");
 
-	// All 32 lanes of the warp must call this together; lanes without a ray pass active = false.
+	// Per-lane traversal state (registers). trav_begin / trav_round / trav_end are the three pieces of one query so that
+	// a kernel can either run a whole batch to completion (trace_ray) or replace finished lanes' rays between rounds
+	// (k_trace_shadow).
+	struct Trav
+	{
+		V3 o, d, rcp;               // current level (world first)
+		float margin, near_, far_, len;
+		uint32_t sbits;
+		bool in_mesh, mesh_hit, lext, committed_ext, alive;
+		uint32_t cur_inst, ltri;
+		float lb1, lb2;
+		uint32_t mat_offset, mat_count;
+		uint32_t cur_begin, cur_tc;
+		float4 mask;                // any hit
+		uint32_t steps, tris;       // STATS only
+	};
+
+	template <bool ANY, bool STATS>
+	__device__ __forceinline__ void trav_begin(const DScene& sc, Trav& t, const bool active, const V3 origin, const V3 direction,
+		const float near_in, const float far_in, Stack& st, ParkedRay& park, TraceCounters& cnt)
+	{
+		t.mask = make_float4(1.0f, 1.0f, 1.0f, 1.0f);
+		t.steps = t.tris = 0u;
+		// no instances: the CPU engine's shadow query answers "occluded" (cpu_engine_kernel.cpp:401), the CUDA one "free"
+		if (ANY && sc.instance_count == 0u && (sc.flags & RZB_FLAG_CPU_SEMANTICS)) t.mask = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+		t.o = origin; t.d = direction;
+		t.rcp = reciprocal_rn(direction);
+		t.margin = margin_for(direction);
+		t.near_ = near_in; t.far_ = far_in; t.len = 1.0f;
+		t.sbits = ANY ? 0u : sign_bits(direction);
+		t.in_mesh = false; t.mesh_hit = false; t.lext = true;
+		t.cur_inst = kNoIndex; t.ltri = kNoIndex;
+		t.lb1 = 0.0f; t.lb2 = 0.0f;
+		t.mat_offset = 0u; t.mat_count = 0u;
+		park.ox = origin.x; park.oy = origin.y; park.oz = origin.z; park.near_ = near_in;
+		park.dx = direction.x; park.dy = direction.y; park.dz = direction.z; park.far_ = far_in;
+		park.b1 = 0.0f; park.b2 = 0.0f; park.tri = kNoIndex; park.inst = kNoIndex;
+		t.committed_ext = true;
+		st.sp = 0;
+
+		t.alive = active && sc.instance_count != 0u;
+		t.cur_begin = 0u; t.cur_tc = 1u;
+		if (t.alive)
+		{
+			const float4 n0 = __ldg(sc.nodes + 2 * size_t(sc.top_root));
+			const float4 n1 = __ldg(sc.nodes + 2 * size_t(sc.top_root) + 1);
+			if (STATS) cnt.top_nodes++;
+			float tmin;
+			t.alive = slab_hit(n0, n1, t.o, t.d, t.rcp, t.near_, t.far_, t.margin, tmin);
+			t.cur_begin = __float_as_uint(n1.z);
+			t.cur_tc = __float_as_uint(n1.w);
+		}
+	}
+
+	// One round: descend from the current node to a leaf, intersect it, pop until a node with a passed box is current
+	// (or the ray is finished). Invariant: an alive lane has a current node whose box test has passed.
+	template <bool ANY, bool STATS>
+	__device__ __forceinline__ void trav_round(const DScene& sc, Trav& t, Stack& st, ParkedRay& park, TraceCounters& cnt)
+	{
+		const float4* __restrict__ nodes = sc.nodes;
+		bool have_cur = t.alive;
+		// ---- descend through inner nodes
+		if (t.alive)
+		{
+			while ((t.cur_tc & 0x3FFFFFFFu) == 0u)
+			{
+				const float4* pair = nodes + 2 * size_t(t.cur_begin); // 64-byte aligned sibling pair
+				const float4 p0 = __ldg(pair), p1 = __ldg(pair + 1), p2 = __ldg(pair + 2), p3 = __ldg(pair + 3);
+				if (STATS) { if (t.in_mesh) cnt.mesh_nodes += 2; else cnt.top_nodes += 2; t.steps++; }
+				float tm0, tm1;
+				const bool h0 = slab_hit(p0, p1, t.o, t.d, t.rcp, t.near_, t.far_, t.margin, tm0);
+				const bool h1 = slab_hit(p2, p3, t.o, t.d, t.rcp, t.near_, t.far_, t.margin, tm1);
+				// near child first: `flip` = the second child is the near one
+				const bool flip = !ANY && ((t.sbits >> (t.cur_tc >> 30)) & 1u) != 0u;
+				const bool hit_a = flip ? h1 : h0, hit_b = flip ? h0 : h1;
+				if (hit_a)
+				{
+					// B is deferred with its entry distance: it is range-tested again when popped, i.e. after A's subtree
+					if (hit_b) st.push((t.in_mesh ? kEntryMeshNode : kEntryTopNode) | (t.cur_begin + (flip ? 0u : 1u)),
+						__float_as_uint(flip ? tm0 : tm1));
+					t.cur_tc = __float_as_uint(flip ? p3.w : p1.w);
+					t.cur_begin = __float_as_uint(flip ? p3.z : p1.z);
+				}
+				else if (hit_b)
+				{
+					t.cur_tc = __float_as_uint(flip ? p1.w : p3.w);
+					t.cur_begin = __float_as_uint(flip ? p1.z : p3.z);
+				}
+				else
+				{
+					have_cur = false;
+					break;
+				}
+			}
+		}
+		// ---- leaf
+		if (have_cur)
+		{
+			const uint32_t count = t.cur_tc & 0x3FFFFFFFu;
+			if (!t.in_mesh) st.push(kEntryInstRange | t.cur_begin, t.cur_begin + count);
+			else
+			{
+				const uint32_t end = t.cur_begin + count;
+				for (uint32_t i = t.cur_begin; i < end; ++i)
+				{
+					if (STATS) { cnt.triangles++; t.tris++; }
+					if (!ANY)
+					{
+						if (triangle_closest(sc.tri_hot, i, t.o, t.d, t.near_, t.far_, t.lb1, t.lb2, t.lext))
+						{
+							t.ltri = i;
+							t.mesh_hit = true;
+						}
+					}
+					else
+					{
+						float tf = t.far_, tb1, tb2;
+						bool text;
+						if (!triangle_closest(sc.tri_hot, i, t.o, t.d, t.near_, tf, tb1, tb2, text)) continue;
+						if (sc.flags & RZB_FLAG_CPU_SEMANTICS) t.mask = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+						else
+						{
+							const float4 a = shadow_attenuation(sc, i, tb1, tb2, t.mat_offset, t.mat_count);
+							t.mask = make_float4(t.mask.x * a.x, t.mask.y * a.y, t.mask.z * a.z, t.mask.w * a.w);
+						}
+						if (t.mask.w < 1.0e-4f)
+						{
+							t.alive = false; // occluded
+							break;
+						}
+					}
+				}
+			}
+		}
+		// ---- pop until a node with a passed box is current (or the ray is finished)
+		while (t.alive)
+		{
+			const bool have = st.sp != 0;
+			uint2 e = make_uint2(kEntryTopNode, 0u);
+			if (have) e = st.pop();
+			const uint32_t kind = e.x & kEntryKindMask;
+			if (t.in_mesh && (!have || kind != kEntryMeshNode))
+			{
+				// the current mesh is exhausted: leave the instance (cuda_instance.cuh:203-213)
+				if (!ANY && t.mesh_hit)
+				{
+					park.inst = t.cur_inst; park.tri = t.ltri; park.b1 = t.lb1; park.b2 = t.lb2;
+					t.committed_ext = t.lext;
+					park.near_ = fdiv(t.near_, t.len);
+					park.far_ = fdiv(t.far_, t.len);
+				}
+				t.o = v3(park.ox, park.oy, park.oz);
+				t.d = v3(park.dx, park.dy, park.dz);
+				t.rcp = reciprocal_rn(t.d);
+				t.margin = margin_for(t.d);
+				t.sbits = ANY ? 0u : sign_bits(t.d);
+				t.near_ = park.near_; t.far_ = park.far_;
+				t.len = 1.0f;
+				t.in_mesh = false;
+			}
+			if (!have)
+			{
+				t.alive = false; // finished
+				break;
+			}
+			const uint32_t idx = e.x & kEntryIndexMask;
+			if (kind == kEntryInstRange)
+			{
+				const uint32_t end = e.y;
+				if (idx + 1u < end) st.push(kEntryInstRange | (idx + 1u), end);
+				// Instance::closestIntersection / anyIntersection (cuda_instance.cuh:186-229)
+				if (STATS) cnt.instances++;
+				const DInstance in = load_instance(sc.instances, idx);
+				const float4 n0 = make_float4(in.bminx, in.bminy, in.bminz, in.bmaxx);
+				const float4 n1 = make_float4(in.bmaxy, in.bmaxz, 0.0f, 0.0f);
+				float tmin;
+				if (!slab_hit(n0, n1, t.o, t.d, t.rcp, t.near_, t.far_, t.margin, tmin)) continue;
+				if (in.mesh_root == kNoIndex) continue;
+				V3 lo, ld;
+				float l;
+				ray_to_local(in, t.o, t.d, lo, ld, l);
+				const float lnear = fmul(t.near_, l), lfar = fmul(t.far_, l);
+				const V3 lrcp = reciprocal_rn(ld);
+				const float lmargin = margin_for(ld);
+				const float4 r0 = __ldg(nodes + 2 * size_t(in.mesh_root));
+				const float4 r1 = __ldg(nodes + 2 * size_t(in.mesh_root) + 1);
+				if (STATS) cnt.mesh_nodes++;
+				if (!slab_hit(r0, r1, lo, ld, lrcp, lnear, lfar, lmargin, tmin)) continue;
+				t.in_mesh = true; t.mesh_hit = false;
+				t.cur_inst = idx;
+				t.mat_offset = in.mat_offset; t.mat_count = in.mat_count;
+				t.o = lo; t.d = ld; t.rcp = lrcp; t.margin = lmargin; t.len = l;
+				t.sbits = ANY ? 0u : sign_bits(ld);
+				t.near_ = lnear; t.far_ = lfar;
+				t.cur_begin = __float_as_uint(r1.z);
+				t.cur_tc = __float_as_uint(r1.w);
+				break;
+			}
+			// a deferred node of the current level
+			if (!ANY)
+			{
+				// late range test (the reference tests the far child after the near subtree has been searched)
+				const float tmin = __uint_as_float(e.y);
+				const float bound = t.margin * fmaxf(fminf(fabsf(tmin), 1.0e30f), 1.0e-30f);
+				if (tmin > t.far_ + bound) continue;
+				if (!(tmin < t.far_ - bound))
+				{
+					// too close to call with the approximate entry distance: evaluate the reference's arithmetic
+					const float4 x0 = __ldg(nodes + 2 * size_t(idx));
+					const float4 x1 = __ldg(nodes + 2 * size_t(idx) + 1);
+					float texact;
+					if (!(slab_exact(x0, x1, t.o, t.d, t.near_, t.far_, texact) & 2u)) continue;
+				}
+			}
+			const float4 n1 = __ldg(nodes + 2 * size_t(idx) + 1);
+			t.cur_begin = __float_as_uint(n1.z);
+			t.cur_tc = __float_as_uint(n1.w);
+			break;
+		}
+	}
+
+	__device__ __forceinline__ void trav_end(const Trav& t, const bool active, const float near_in, const float far_in,
+		const ParkedRay& park, RayResult& res)
+	{
+		res.t = far_in; res.near_ = near_in; res.b1 = 0.0f; res.b2 = 0.0f;
+		res.tri = kNoIndex; res.inst = kNoIndex; res.external = true;
+		res.mask = t.mask;
+		res.steps = t.steps; res.tris = t.tris;
+		if (active)
+		{
+			res.t = park.far_; res.near_ = park.near_; res.b1 = park.b1; res.b2 = park.b2;
+			res.tri = park.tri; res.inst = park.inst; res.external = t.committed_ext;
+		}
+	}
+
+	// One query per lane, run to completion. All 32 lanes of the warp must call this together; lanes without a ray pass
+	// active = false.
 	// SYNC = true makes the outer loop warp-uniform (one __any_sync per round): in every round the lanes descend
 	// together, then intersect their leaves together, then pop / change level together. SYNC = false lets every lane
 	// run its own rounds. Measured on B200 (1M-triangle scene, ms per pass; profiles/): closest hit 1.38 free-running
@@ -112,210 +348,10 @@ namespace rzb
 	__device__ __forceinline__ void trace_ray(const DScene& sc, const bool active, const V3 origin, const V3 direction,
 		const float near_in, const float far_in, Stack& st, ParkedRay& park, TraceCounters& cnt, RayResult& res)
 	{
-		res.t = far_in; res.near_ = near_in; res.b1 = 0.0f; res.b2 = 0.0f;
-		res.tri = kNoIndex; res.inst = kNoIndex; res.external = true;
-		res.mask = make_float4(1.0f, 1.0f, 1.0f, 1.0f);
-		res.steps = res.tris = 0u;
-		// no instances: the CPU engine's shadow query answers "occluded" (cpu_engine_kernel.cpp:401), the CUDA one "free"
-		if (ANY && sc.instance_count == 0u && (sc.flags & RZB_FLAG_CPU_SEMANTICS)) res.mask = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-		const float4* __restrict__ nodes = sc.nodes;
-
-		// current level (world first)
-		V3 o = origin, d = direction;
-		V3 rcp = reciprocal_rn(d);
-		float margin = margin_for(d);
-		float near_ = near_in, far_ = far_in, len = 1.0f;
-		uint32_t sbits = ANY ? 0u : sign_bits(d);
-		bool in_mesh = false, mesh_hit = false, lext = true;
-		uint32_t cur_inst = kNoIndex, ltri = kNoIndex;
-		float lb1 = 0.0f, lb2 = 0.0f;
-		uint32_t mat_offset = 0u, mat_count = 0u;
-		park.ox = origin.x; park.oy = origin.y; park.oz = origin.z; park.near_ = near_in;
-		park.dx = direction.x; park.dy = direction.y; park.dz = direction.z; park.far_ = far_in;
-		park.b1 = 0.0f; park.b2 = 0.0f; park.tri = kNoIndex; park.inst = kNoIndex;
-		bool committed_ext = true;
-		st.sp = 0;
-
-		bool alive = active && sc.instance_count != 0u;
-		uint32_t cur_begin = 0u, cur_tc = 1u;
-		if (alive)
-		{
-			const float4 n0 = __ldg(nodes + 2 * size_t(sc.top_root));
-			const float4 n1 = __ldg(nodes + 2 * size_t(sc.top_root) + 1);
-			if (STATS) cnt.top_nodes++;
-			float tmin;
-			alive = slab_hit(n0, n1, o, d, rcp, near_, far_, margin, tmin);
-			cur_begin = __float_as_uint(n1.z);
-			cur_tc = __float_as_uint(n1.w);
-		}
-
-		while (SYNC ? __any_sync(0xFFFFFFFFu, alive) != 0 : alive)
-		{
-			// invariant: an alive lane has a current node whose box test has passed
-			bool have_cur = alive;
-			// ---- descend through inner nodes
-			if (alive)
-			{
-				while ((cur_tc & 0x3FFFFFFFu) == 0u)
-				{
-					const float4* pair = nodes + 2 * size_t(cur_begin); // 64-byte aligned sibling pair
-					const float4 p0 = __ldg(pair), p1 = __ldg(pair + 1), p2 = __ldg(pair + 2), p3 = __ldg(pair + 3);
-					if (STATS) { if (in_mesh) cnt.mesh_nodes += 2; else cnt.top_nodes += 2; res.steps++; }
-					float tm0, tm1;
-					const bool h0 = slab_hit(p0, p1, o, d, rcp, near_, far_, margin, tm0);
-					const bool h1 = slab_hit(p2, p3, o, d, rcp, near_, far_, margin, tm1);
-					// near child first: `flip` = the second child is the near one
-					const bool flip = !ANY && ((sbits >> (cur_tc >> 30)) & 1u) != 0u;
-					const bool hit_a = flip ? h1 : h0, hit_b = flip ? h0 : h1;
-					if (hit_a)
-					{
-						// B is deferred with its entry distance: it is range-tested again when popped, i.e. after A's subtree
-						if (hit_b) st.push((in_mesh ? kEntryMeshNode : kEntryTopNode) | (cur_begin + (flip ? 0u : 1u)),
-							__float_as_uint(flip ? tm0 : tm1));
-						cur_tc = __float_as_uint(flip ? p3.w : p1.w);
-						cur_begin = __float_as_uint(flip ? p3.z : p1.z);
-					}
-					else if (hit_b)
-					{
-						cur_tc = __float_as_uint(flip ? p1.w : p3.w);
-						cur_begin = __float_as_uint(flip ? p1.z : p3.z);
-					}
-					else
-					{
-						have_cur = false;
-						break;
-					}
-				}
-			}
-			// ---- leaf
-			if (have_cur)
-			{
-				const uint32_t count = cur_tc & 0x3FFFFFFFu;
-				if (!in_mesh) st.push(kEntryInstRange | cur_begin, cur_begin + count);
-				else
-				{
-					const uint32_t end = cur_begin + count;
-					for (uint32_t i = cur_begin; i < end; ++i)
-					{
-						if (STATS) { cnt.triangles++; res.tris++; }
-						if (!ANY)
-						{
-							if (triangle_closest(sc.tri_hot, i, o, d, near_, far_, lb1, lb2, lext))
-							{
-								ltri = i;
-								mesh_hit = true;
-							}
-						}
-						else
-						{
-							float tf = far_, tb1, tb2;
-							bool text;
-							if (!triangle_closest(sc.tri_hot, i, o, d, near_, tf, tb1, tb2, text)) continue;
-							if (sc.flags & RZB_FLAG_CPU_SEMANTICS) res.mask = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-							else
-							{
-								const float4 a = shadow_attenuation(sc, i, tb1, tb2, mat_offset, mat_count);
-								res.mask = make_float4(res.mask.x * a.x, res.mask.y * a.y, res.mask.z * a.z, res.mask.w * a.w);
-							}
-							if (res.mask.w < 1.0e-4f)
-							{
-								alive = false; // occluded
-								break;
-							}
-						}
-					}
-				}
-			}
-			// ---- pop until a node with a passed box is current (or the ray is finished)
-			while (alive)
-			{
-				const bool have = st.sp != 0;
-				uint2 e = make_uint2(kEntryTopNode, 0u);
-				if (have) e = st.pop();
-				const uint32_t kind = e.x & kEntryKindMask;
-				if (in_mesh && (!have || kind != kEntryMeshNode))
-				{
-					// the current mesh is exhausted: leave the instance (cuda_instance.cuh:203-213)
-					if (!ANY && mesh_hit)
-					{
-						park.inst = cur_inst; park.tri = ltri; park.b1 = lb1; park.b2 = lb2;
-						committed_ext = lext;
-						park.near_ = fdiv(near_, len);
-						park.far_ = fdiv(far_, len);
-					}
-					o = v3(park.ox, park.oy, park.oz);
-					d = v3(park.dx, park.dy, park.dz);
-					rcp = reciprocal_rn(d);
-					margin = margin_for(d);
-					sbits = ANY ? 0u : sign_bits(d);
-					near_ = park.near_; far_ = park.far_;
-					len = 1.0f;
-					in_mesh = false;
-				}
-				if (!have)
-				{
-					alive = false; // finished
-					break;
-				}
-				const uint32_t idx = e.x & kEntryIndexMask;
-				if (kind == kEntryInstRange)
-				{
-					const uint32_t end = e.y;
-					if (idx + 1u < end) st.push(kEntryInstRange | (idx + 1u), end);
-					// Instance::closestIntersection / anyIntersection (cuda_instance.cuh:186-229)
-					if (STATS) cnt.instances++;
-					const DInstance in = load_instance(sc.instances, idx);
-					const float4 n0 = make_float4(in.bminx, in.bminy, in.bminz, in.bmaxx);
-					const float4 n1 = make_float4(in.bmaxy, in.bmaxz, 0.0f, 0.0f);
-					float tmin;
-					if (!slab_hit(n0, n1, o, d, rcp, near_, far_, margin, tmin)) continue;
-					if (in.mesh_root == kNoIndex) continue;
-					V3 lo, ld;
-					float l;
-					ray_to_local(in, o, d, lo, ld, l);
-					const float lnear = fmul(near_, l), lfar = fmul(far_, l);
-					const V3 lrcp = reciprocal_rn(ld);
-					const float lmargin = margin_for(ld);
-					const float4 r0 = __ldg(nodes + 2 * size_t(in.mesh_root));
-					const float4 r1 = __ldg(nodes + 2 * size_t(in.mesh_root) + 1);
-					if (STATS) cnt.mesh_nodes++;
-					if (!slab_hit(r0, r1, lo, ld, lrcp, lnear, lfar, lmargin, tmin)) continue;
-					in_mesh = true; mesh_hit = false;
-					cur_inst = idx;
-					mat_offset = in.mat_offset; mat_count = in.mat_count;
-					o = lo; d = ld; rcp = lrcp; margin = lmargin; len = l;
-					sbits = ANY ? 0u : sign_bits(ld);
-					near_ = lnear; far_ = lfar;
-					cur_begin = __float_as_uint(r1.z);
-					cur_tc = __float_as_uint(r1.w);
-					break;
-				}
-				// a deferred node of the current level
-				if (!ANY)
-				{
-					// late range test (the reference tests the far child after the near subtree has been searched)
-					const float tmin = __uint_as_float(e.y);
-					const float bound = margin * fmaxf(fminf(fabsf(tmin), 1.0e30f), 1.0e-30f);
-					if (tmin > far_ + bound) continue;
-					if (!(tmin < far_ - bound))
-					{
-						// too close to call with the approximate entry distance: evaluate the reference's arithmetic
-						const float4 x0 = __ldg(nodes + 2 * size_t(idx));
-						const float4 x1 = __ldg(nodes + 2 * size_t(idx) + 1);
-						float texact;
-						if (!(slab_exact(x0, x1, o, d, near_, far_, texact) & 2u)) continue;
-					}
-				}
-				const float4 n1 = __ldg(nodes + 2 * size_t(idx) + 1);
-				cur_begin = __float_as_uint(n1.z);
-				cur_tc = __float_as_uint(n1.w);
-				break;
-			}
-		}
-		if (active)
-		{
-			res.t = park.far_; res.near_ = park.near_; res.b1 = park.b1; res.b2 = park.b2;
-			res.tri = park.tri; res.inst = park.inst; res.external = committed_ext;
-		}
+		Trav t;
+		trav_begin<ANY, STATS>(sc, t, active, origin, direction, near_in, far_in, st, park, cnt);
+		while (SYNC ? __any_sync(0xFFFFFFFFu, t.alive) != 0 : t.alive)
+			trav_round<ANY, STATS>(sc, t, st, park, cnt);
+		trav_end(t, active, near_in, far_in, park, res);
 	}
 }

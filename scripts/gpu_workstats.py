@@ -16,5 +16,7 @@ for wl in ("heightfield_1m_1080p", "materials_1080p"):
         print("  per segment: nodes %.1f tris %.1f shadow rays %.2f ; per shadow ray: nodes %.1f tris %.1f" % (
             (wc["closest_top_nodes"] + wc["closest_mesh_nodes"]) / seg, wc["closest_triangles"] / seg, wc["shadow_rays"] / seg,
             (wc["shadow_top_nodes"] + wc["shadow_mesh_nodes"]) / max(int(wc["shadow_rays"]), 1), wc["shadow_triangles"] / max(int(wc["shadow_rays"]), 1)))
+        print("  lane utilisation of whole-warp batches: closest %.3f shadow %.3f" % (
+            wc["closest_lane_work"] / max(int(wc["closest_batch_work"]), 1), wc["shadow_lane_work"] / max(int(wc["shadow_batch_work"]), 1)))
         acc = ctx.read_accum()
         print("  accum finite:", bool(np.isfinite(acc).all()), "spp", float(acc[..., 3].mean()))

@@ -480,3 +480,23 @@ def test_texture_fetch_modes(filt, addr):
     close = np.isclose(acc[:, :3], expect, rtol=1e-4, atol=1e-4).all(axis=1)
     # texel boundaries may fall differently for uv computed in fp32 with FMA: allow isolated pixels
     assert close.mean() > 0.99, close.mean()
+
+
+def test_non_finite_samples_are_dropped():
+    """The reference's direction samplers let a ray's direction drift from unit length and a chain of scattering
+    bounces can square that length per bounce until it overflows (k_shade comment). Row 929 of the 1080p materials
+    scene with seed 20261018 reaches such a path in pass 211: the sample is dropped, the accumulator stays finite and
+    the discard is counted."""
+    w = scenes.CONFIGS["materials"](resolution=(1920, 1080), res=64)
+    with capi.Context(0) as c:
+        c.set_scene(w.flatten())
+        c.set_camera(w.camera_struct())
+        c.set_config(1, 1, 16, capi.FLAG_COUNT_WORK, 20261018)
+        c.set_rows(929, 930)
+        c.reset()
+        c.render(216)
+        acc = c.read_accum()
+        wc = c.work_counters()
+    assert np.isfinite(acc).all()
+    assert int(wc["invalid_rays"]) >= 1
+    assert acc[929, :, 3].min() > 0 and (acc[:929] == 0).all() and (acc[930:] == 0).all()
