@@ -155,8 +155,17 @@ typedef struct rzb_scene
 	const rzb_spot_light* spot_lights; uint32_t spot_light_count;
 	rzb_material world_material;       /* World::material(): medium rays start in + sky */
 	uint32_t default_material;         /* index into materials used for empty slots */
-	uint32_t _pad;
+	uint32_t flags;                    /* RZB_SCENE_* */
 } rzb_scene;
+
+enum
+{
+	RZB_SCENE_REFERENCE_TREES = 0, /* the trees are the reference's own (rzb_build_mesh_bvh or the host World's): every box
+	                                  test decides exactly as the reference's arithmetic does -- the parity mode */
+	RZB_SCENE_OWN_TREES = 1        /* the mesh trees come from another builder (rzb_build_mesh_bvh_sah): nothing has to
+	                                  follow the reference's box decisions, so the kernels use a cheaper conservative
+	                                  box test; closest-hit records still equal the reference's except on exact ties */
+};
 
 /* Camera (cuda_camera.cuh:112-200, camera.hpp). Axes are the camera coordinate system. */
 typedef struct rzb_camera
@@ -320,6 +329,11 @@ int rzb_generate_camera_rays(rzb_ctx* ctx, float* origins, float* directions, fl
  * Outputs: nodes (capacity >= 2*nt+1), order[nt] = host triangle index per BVH-order slot.
  * Returns node count through node_count_out. */
 int rzb_build_mesh_bvh(const float* vertices, uint32_t nv, const uint32_t* tris, uint32_t nt,
+	rzb_node* nodes_out, uint32_t node_capacity, uint32_t* node_count_out, uint32_t* order_out);
+/* OPTIONAL builder, not the reference's tree: binned surface-area-heuristic splits, leaves of at
+ * most max_leaf triangles (8 = the reference's leaf size), depth <= 31, same node / order format, so every kernel runs
+ * on it unchanged. Closest-hit records equal the reference tree's except on exact-distance ties. */
+int rzb_build_mesh_bvh_sah(const float* vertices, uint32_t nv, const uint32_t* tris, uint32_t nt, uint32_t max_leaf,
 	rzb_node* nodes_out, uint32_t node_capacity, uint32_t* node_count_out, uint32_t* order_out);
 /* Instance BVH (bvh_tree_node.hpp:117-215 + cuda_bvh.cuh:86-111): boxes[n][6] = min xyz, max xyz. */
 int rzb_build_instance_bvh(const float* boxes, uint32_t n,

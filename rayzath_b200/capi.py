@@ -21,6 +21,7 @@ NO_INDEX = 0xFFFFFFFF
 FLAG_NONE = 0
 FLAG_CPU_SEMANTICS = 1
 FLAG_COUNT_WORK = 2
+SCENE_REFERENCE_TREES, SCENE_OWN_TREES = 0, 1
 MAP_RGBA8, MAP_R8, MAP_R32F = 0, 1, 2
 FILTER_POINT, FILTER_LINEAR = 0, 1
 ADDRESS_WRAP, ADDRESS_CLAMP, ADDRESS_MIRROR, ADDRESS_BORDER = 0, 1, 2, 3
@@ -84,7 +85,7 @@ class SceneStruct(C.Structure):
         ("spot_lights", C.c_void_p), ("spot_light_count", C.c_uint32),
         ("world_material", C.c_uint8 * 64),
         ("default_material", C.c_uint32),
-        ("_pad", C.c_uint32),
+        ("flags", C.c_uint32),
     ]
 
 
@@ -121,6 +122,7 @@ SYMBOLS = {
     "rzb_trace_any": (C.c_int, [_P, _P, _P, _P, C.c_uint32, _P]),
     "rzb_generate_camera_rays": (C.c_int, [_P, _P, _P, _P]),
     "rzb_build_mesh_bvh": (C.c_int, [_P, C.c_uint32, _P, C.c_uint32, _P, C.c_uint32, C.POINTER(C.c_uint32), _P]),
+    "rzb_build_mesh_bvh_sah": (C.c_int, [_P, C.c_uint32, _P, C.c_uint32, C.c_uint32, _P, C.c_uint32, C.POINTER(C.c_uint32), _P]),
     "rzb_build_instance_bvh": (C.c_int, [_P, C.c_uint32, _P, C.c_uint32, C.POINTER(C.c_uint32), _P]),
     "rzb_rotation_axes": (C.c_int, [_P, C.c_int, _P]),
     "rzb_instance_bbox": (C.c_int, [_P, C.c_uint32, _P, _P, _P, _P]),
@@ -174,6 +176,21 @@ def build_mesh_bvh(vertices: np.ndarray, tris: np.ndarray):
                                   C.byref(count), order.ctypes.data)
     if rc:
         raise RzbError(rc, "rzb_build_mesh_bvh failed")
+    return nodes[:count.value].copy(), order
+
+
+def build_mesh_bvh_sah(vertices: np.ndarray, tris: np.ndarray, max_leaf: int = 8):
+    """rzb_build_mesh_bvh_sah: the optional SAH triangle BVH (not the reference's tree). Returns (nodes, order)."""
+    v = _c(vertices, f4).reshape(-1, 3)
+    t = _c(tris, u4).reshape(-1, 3)
+    nt = t.shape[0]
+    nodes = np.zeros(2 * nt + 1, dtype=node_dtype)
+    order = np.zeros(nt, dtype=u4)
+    count = C.c_uint32(0)
+    rc = lib().rzb_build_mesh_bvh_sah(v.ctypes.data, v.shape[0], t.ctypes.data, nt, int(max_leaf), nodes.ctypes.data,
+                                      nodes.shape[0], C.byref(count), order.ctypes.data)
+    if rc:
+        raise RzbError(rc, "rzb_build_mesh_bvh_sah failed")
     return nodes[:count.value].copy(), order
 
 
@@ -310,6 +327,7 @@ class Context:
         wm = arr("world_material", material_dtype).reshape(-1)
         C.memmove(s.world_material, wm.ctypes.data, 64)
         s.default_material = int(np.asarray(scene["default_material"]).reshape(-1)[0])
+        s.flags = int(np.asarray(scene.get("scene_flags", 0)).reshape(-1)[0])
         self._check(self._l.rzb_set_scene(self._h, C.byref(s)))
         self._keep = None
 

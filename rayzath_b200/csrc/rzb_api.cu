@@ -81,6 +81,7 @@ struct rzb_ctx
 	uint64_t passes = 0, launches = 0;
 	float last_render_ms = 0.0f, last_trace_ms = 0.0f, last_shade_ms = 0.0f, last_shadow_ms = 0.0f;
 	int trace_grid = 0, shadow_grid = 0, rays_grid = 0, any_grid = 0;
+	bool own_trees = false;        // rzb_scene::flags & RZB_SCENE_OWN_TREES: conservative box tests
 	bool debug_sync = false;       // RZB200_DEBUG_SYNC: synchronise after every kernel of rzb_render and name the one that faulted
 };
 
@@ -273,10 +274,10 @@ extern "C" int rzb_create(int device, rzb_ctx** out)
 	if ((e = cudaMalloc(reinterpret_cast<void**>(&ctx->d_counters), 256)) != cudaSuccess) { delete ctx; return cudaFail(nullptr, e, "cudaMalloc(counters)"); }
 	cudaMemsetAsync(ctx->d_counters, 0, 256, ctx->stream);
 	ctx->debug_sync = std::getenv("RZB200_DEBUG_SYNC") != nullptr;
-	ctx->trace_grid = gridFor(ctx, reinterpret_cast<const void*>(&k_trace_paths<false>), kTraceBlock);
-	ctx->shadow_grid = gridFor(ctx, reinterpret_cast<const void*>(&k_trace_shadow<false>), kTraceBlock);
-	ctx->rays_grid = gridFor(ctx, reinterpret_cast<const void*>(&k_trace_rays<false>), kTraceBlock);
-	ctx->any_grid = gridFor(ctx, reinterpret_cast<const void*>(&k_trace_any_rays), kTraceBlock);
+	ctx->trace_grid = gridFor(ctx, reinterpret_cast<const void*>(&k_trace_paths<false, false>), kTraceBlock);
+	ctx->shadow_grid = gridFor(ctx, reinterpret_cast<const void*>(&k_trace_shadow<false, false>), kTraceBlock);
+	ctx->rays_grid = gridFor(ctx, reinterpret_cast<const void*>(&k_trace_rays<false, false>), kTraceBlock);
+	ctx->any_grid = gridFor(ctx, reinterpret_cast<const void*>(&k_trace_any_rays<false>), kTraceBlock);
 	*out = ctx;
 	return RZB_OK;
 }
@@ -535,6 +536,7 @@ extern "C" int rzb_set_scene(rzb_ctx* ctx, const rzb_scene* s)
 	sc.flags = ctx->cfg.flags;
 	RZB_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); // host staging vectors die at return; the caller may reuse its arrays
 	ctx->sc = sc;
+	ctx->own_trees = (s->flags & RZB_SCENE_OWN_TREES) != 0u;
 	ctx->has_scene = true;
 	return RZB_OK;
 }
@@ -634,6 +636,7 @@ extern "C" int rzb_render(rzb_ctx* ctx, uint32_t passes)
 	f.seed = ctx->cfg.seed;
 	const bool lights = (ctx->sc.direct_light_count && f.direct_samples) || (ctx->sc.spot_light_count && f.spot_samples);
 	const bool count = (ctx->cfg.flags & RZB_FLAG_COUNT_WORK) != 0u;
+	const bool fast = ctx->own_trees;
 	f.work = ctx->d_work;
 	// per-stage device timing: up to 256 passes of this call are bracketed by events (4 per sampled pass)
 	const uint32_t stride = (passes + 255u) / 256u;
@@ -654,8 +657,8 @@ extern "C" int rzb_render(rzb_ctx* ctx, uint32_t passes)
 		cudaEvent_t* ev = timed ? &ctx->ev_stage[size_t(ctx->sampled_passes) * 4] : nullptr;
 		RZB_CUDA(ctx, cudaMemsetAsync(ctx->d_counters, 0, 12, ctx->stream));
 		if (timed) cudaEventRecord(ev[0], ctx->stream);
-		if (count) k_trace_paths<true><<<ctx->trace_grid, kTraceBlock, 0, ctx->stream>>>(ctx->sc, f);
-		else k_trace_paths<false><<<ctx->trace_grid, kTraceBlock, 0, ctx->stream>>>(ctx->sc, f);
+		if (count) { if (fast) k_trace_paths<true, true><<<ctx->trace_grid, kTraceBlock, 0, ctx->stream>>>(ctx->sc, f); else k_trace_paths<true, false><<<ctx->trace_grid, kTraceBlock, 0, ctx->stream>>>(ctx->sc, f); }
+		else { if (fast) k_trace_paths<false, true><<<ctx->trace_grid, kTraceBlock, 0, ctx->stream>>>(ctx->sc, f); else k_trace_paths<false, false><<<ctx->trace_grid, kTraceBlock, 0, ctx->stream>>>(ctx->sc, f); }
 		if (ctx->debug_sync)
 		{
 			const cudaError_t e = cudaStreamSynchronize(ctx->stream);
@@ -672,8 +675,8 @@ extern "C" int rzb_render(rzb_ctx* ctx, uint32_t passes)
 		ctx->launches += 2;
 		if (lights)
 		{
-			if (count) k_trace_shadow<true><<<ctx->shadow_grid, kTraceBlock, 0, ctx->stream>>>(ctx->sc, f);
-			else k_trace_shadow<false><<<ctx->shadow_grid, kTraceBlock, 0, ctx->stream>>>(ctx->sc, f);
+			if (count) { if (fast) k_trace_shadow<true, true><<<ctx->shadow_grid, kTraceBlock, 0, ctx->stream>>>(ctx->sc, f); else k_trace_shadow<true, false><<<ctx->shadow_grid, kTraceBlock, 0, ctx->stream>>>(ctx->sc, f); }
+			else { if (fast) k_trace_shadow<false, true><<<ctx->shadow_grid, kTraceBlock, 0, ctx->stream>>>(ctx->sc, f); else k_trace_shadow<false, false><<<ctx->shadow_grid, kTraceBlock, 0, ctx->stream>>>(ctx->sc, f); }
 			ctx->launches += 1;
 			if (ctx->debug_sync)
 			{
@@ -939,7 +942,7 @@ extern "C" int rzb_trace_closest_device(rzb_ctx* ctx, const void* rays_o_near, c
 	DeviceGuard guard(ctx->device);
 	RZB_CUDA(ctx, cudaMemsetAsync(ctx->d_counters + 8, 0, 4, ctx->stream));
 	if (elapsed_ms) RZB_CUDA(ctx, cudaEventRecord(ctx->ev_begin, ctx->stream));
-	k_trace_rays<false><<<ctx->rays_grid, kTraceBlock, 0, ctx->stream>>>(ctx->sc,
+	(ctx->own_trees ? k_trace_rays<false, true> : k_trace_rays<false, false>)<<<ctx->rays_grid, kTraceBlock, 0, ctx->stream>>>(ctx->sc,
 		static_cast<const float4*>(rays_o_near), static_cast<const float4*>(rays_d_far), n,
 		static_cast<DHit*>(hits_out_device), ctx->d_counters + 8, nullptr);
 	ctx->launches += 1;
@@ -961,7 +964,7 @@ extern "C" int rzb_trace_closest_device_counted(rzb_ctx* ctx, const void* rays_o
 	DeviceGuard guard(ctx->device);
 	unsigned long long* d_stats = reinterpret_cast<unsigned long long*>(ctx->d_counters + 10);
 	RZB_CUDA(ctx, cudaMemsetAsync(ctx->d_counters + 8, 0, 40, ctx->stream));
-	k_trace_rays<true><<<ctx->rays_grid, kTraceBlock, 0, ctx->stream>>>(ctx->sc,
+	(ctx->own_trees ? k_trace_rays<true, true> : k_trace_rays<true, false>)<<<ctx->rays_grid, kTraceBlock, 0, ctx->stream>>>(ctx->sc,
 		static_cast<const float4*>(rays_o_near), static_cast<const float4*>(rays_d_far), n,
 		static_cast<DHit*>(hits_out_device), ctx->d_counters + 8, d_stats);
 	ctx->launches += 1;
@@ -984,11 +987,11 @@ extern "C" int rzb_trace_closest(rzb_ctx* ctx, const float* origins, const float
 	unsigned long long* d_stats = reinterpret_cast<unsigned long long*>(ctx->d_counters + 10);
 	RZB_CUDA(ctx, cudaMemsetAsync(ctx->d_counters + 8, 0, 40, ctx->stream));
 	if (stats)
-		k_trace_rays<true><<<ctx->rays_grid, kTraceBlock, 0, ctx->stream>>>(ctx->sc,
+		(ctx->own_trees ? k_trace_rays<true, true> : k_trace_rays<true, false>)<<<ctx->rays_grid, kTraceBlock, 0, ctx->stream>>>(ctx->sc,
 			static_cast<const float4*>(ctx->scratch[0].ptr), static_cast<const float4*>(ctx->scratch[1].ptr), n,
 			static_cast<DHit*>(ctx->scratch[2].ptr), ctx->d_counters + 8, d_stats);
 	else
-		k_trace_rays<false><<<ctx->rays_grid, kTraceBlock, 0, ctx->stream>>>(ctx->sc,
+		(ctx->own_trees ? k_trace_rays<false, true> : k_trace_rays<false, false>)<<<ctx->rays_grid, kTraceBlock, 0, ctx->stream>>>(ctx->sc,
 			static_cast<const float4*>(ctx->scratch[0].ptr), static_cast<const float4*>(ctx->scratch[1].ptr), n,
 			static_cast<DHit*>(ctx->scratch[2].ptr), ctx->d_counters + 8, nullptr);
 	k_convert_hits<<<(n + 255) / 256, 256, 0, ctx->stream>>>(ctx->sc, static_cast<const DHit*>(ctx->scratch[2].ptr),
@@ -1018,7 +1021,7 @@ extern "C" int rzb_trace_any(rzb_ctx* ctx, const float* origins, const float* di
 	if ((rc = packRays(ctx, origins, directions, near_far, n))) return rc;
 	if ((rc = ensureScratch(ctx, 2, size_t(n) * 16))) return rc;
 	RZB_CUDA(ctx, cudaMemsetAsync(ctx->d_counters + 8, 0, 4, ctx->stream));
-	k_trace_any_rays<<<ctx->any_grid, kTraceBlock, 0, ctx->stream>>>(ctx->sc,
+	(ctx->own_trees ? k_trace_any_rays<true> : k_trace_any_rays<false>)<<<ctx->any_grid, kTraceBlock, 0, ctx->stream>>>(ctx->sc,
 		static_cast<const float4*>(ctx->scratch[0].ptr), static_cast<const float4*>(ctx->scratch[1].ptr), n,
 		static_cast<float4*>(ctx->scratch[2].ptr), ctx->d_counters + 8);
 	ctx->launches += 1;

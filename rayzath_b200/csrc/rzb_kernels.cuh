@@ -181,7 +181,7 @@ namespace rzb
 		}
 	}
 
-	template <bool STATS>
+	template <bool STATS, bool FAST>
 	__global__ void __launch_bounds__(kTraceBlock, 6) k_trace_paths(DScene sc, DFrame f)
 	{
 		__shared__ uint2 smem_stack[kSmemStack * kTraceBlock];
@@ -215,7 +215,7 @@ namespace rzb
 				}
 			}
 			RayResult r;
-			trace_ray<false, STATS>(sc, active, v3(so.x, so.y, so.z), v3(sd.x, sd.y, sd.z), near_, far_, st, park, cnt, r);
+			trace_ray<false, STATS, false, FAST>(sc, active, v3(so.x, so.y, so.z), v3(sd.x, sd.y, sd.z), near_, far_, st, park, cnt, r);
 			if (STATS) batch_utilisation(active ? r.steps + r.tris : 0u, f.work + 10);
 			if (!active) continue;
 			uint32_t tri_bits = flags | (r.external ? kHitExternalBit : 0u);
@@ -469,7 +469,7 @@ namespace rzb
 	// Measured and dropped: giving finished lanes new rays between rounds (threshold 1..24 idle lanes) raises the share
 	// of busy lane-rounds from 0.44 to 0.70-0.88 on the materials scene but not the speed (1.33 -> 1.28..1.41 ms; 1M
 	// triangles 0.44 -> 0.46..0.62 ms): a round costs what its longest descend / leaf loop costs.
-	template <bool STATS>
+	template <bool STATS, bool FAST>
 	__global__ void __launch_bounds__(kTraceBlock, 6) k_trace_shadow(DScene sc, DFrame f)
 	{
 		__shared__ uint2 smem_stack[kSmemStack * kTraceBlock];
@@ -488,7 +488,7 @@ namespace rzb
 			float4 o = make_float4(0.0f, 0.0f, 0.0f, 0.0f), d = make_float4(0.0f, 0.0f, 1.0f, 0.0f);
 			if (active) { o = f.sh_o[i]; d = f.sh_d[i]; }
 			RayResult r;
-			trace_ray<true, STATS>(sc, active, v3(o.x, o.y, o.z), v3(d.x, d.y, d.z), 0.0f, o.w, st, park, cnt, r);
+			trace_ray<true, STATS, true, FAST>(sc, active, v3(o.x, o.y, o.z), v3(d.x, d.y, d.z), 0.0f, o.w, st, park, cnt, r);
 			if (STATS) batch_utilisation(active ? r.steps + r.tris : 0u, f.work + 12);
 			const float w = r.mask.w;
 			if (!active || w <= 0.0f) continue;
@@ -548,7 +548,7 @@ namespace rzb
 	};
 	static_assert(sizeof(DHit) == 32, "DHit");
 
-	template <bool STATS>
+	template <bool STATS, bool FAST>
 	__global__ void __launch_bounds__(kTraceBlock, 6) k_trace_rays(DScene sc, const float4* __restrict__ ray_o_near,
 		const float4* __restrict__ ray_d_far, uint32_t n, DHit* __restrict__ hits, uint32_t* counter,
 		unsigned long long* stats)
@@ -567,7 +567,7 @@ namespace rzb
 			float4 o = make_float4(0.0f, 0.0f, 0.0f, 0.0f), d = make_float4(0.0f, 0.0f, 1.0f, 0.0f);
 			if (active) { o = __ldg(ray_o_near + i); d = __ldg(ray_d_far + i); }
 			RayResult r;
-			trace_ray<false, STATS>(sc, active, v3(o.x, o.y, o.z), v3(d.x, d.y, d.z), o.w, d.w, st, park, cnt, r);
+			trace_ray<false, STATS, false, FAST>(sc, active, v3(o.x, o.y, o.z), v3(d.x, d.y, d.z), o.w, d.w, st, park, cnt, r);
 			if (!active) continue;
 			const uint32_t tri_bits = (r.tri == kNoIndex ? kHitTriMask : (r.tri & kHitTriMask)) | (r.external ? kHitExternalBit : 0u);
 			float4* dst = reinterpret_cast<float4*>(hits + i);
@@ -599,6 +599,7 @@ namespace rzb
 		out[i] = r;
 	}
 
+	template <bool FAST>
 	__global__ void __launch_bounds__(kTraceBlock, 6) k_trace_any_rays(DScene sc, const float4* __restrict__ ray_o_near,
 		const float4* __restrict__ ray_d_far, uint32_t n, float4* __restrict__ masks, uint32_t* counter)
 	{
@@ -616,7 +617,7 @@ namespace rzb
 			float4 o = make_float4(0.0f, 0.0f, 0.0f, 0.0f), d = make_float4(0.0f, 0.0f, 1.0f, 0.0f);
 			if (active) { o = __ldg(ray_o_near + i); d = __ldg(ray_d_far + i); }
 			RayResult r;
-			trace_ray<true, false>(sc, active, v3(o.x, o.y, o.z), v3(d.x, d.y, d.z), o.w, d.w, st, park, cnt, r);
+			trace_ray<true, false, true, FAST>(sc, active, v3(o.x, o.y, o.z), v3(d.x, d.y, d.z), o.w, d.w, st, park, cnt, r);
 			if (active) masks[i] = r.mask;
 		}
 	}

@@ -51,6 +51,10 @@ namespace rzb
 
 	// Fast slab predicate. Returns true when the box is hit AND its entry distance is within the range; tmin_out is
 	// the (approximate, or exact after the fallback) entry distance.
+	// CONSERVATIVE = true (scenes whose trees are not the reference's, RZB_SCENE_OWN_TREES): no decision has to equal
+	// the reference's, the test only must never reject a box the ray enters -- the interval is widened by 4 ulp
+	// instead of being checked against the error bound (10 instructions per box less, no exact fallback).
+	template <bool CONSERVATIVE>
 	__device__ __forceinline__ bool slab_hit(const float4 n0, const float4 n1, const V3& o, const V3& d, const V3& rcp,
 		const float near_, const float far_, const float margin, float& tmin_out)
 	{
@@ -62,6 +66,13 @@ namespace rzb
 		const float t6 = fmul(fsub(n1.y, o.z), rcp.z);
 		const float tmin = fmaxf(fmaxf(fminf(t1, t2), fminf(t3, t4)), fminf(t5, t6));
 		const float tmax = fminf(fminf(fmaxf(t1, t2), fmaxf(t3, t4)), fmaxf(t5, t6));
+		if (CONSERVATIVE)
+		{
+			// a box that matters has tmax > 0; entry distances that matter for the far test are positive
+			const float lo = tmin * 0.9999995f, hi = tmax * 1.0000005f;
+			tmin_out = lo;
+			return !(hi < near_ || lo > hi || lo > far_);
+		}
 		// closest distance between any two compared quantities versus the error bound of the approximate ones;
 		// infinities (a direction component == 0) are exact in both formulations and never "close"
 		const float gap = fminf(fminf(fabsf(tmax - near_), fabsf(tmin - tmax)), fabsf(tmin - far_));
@@ -119,7 +130,7 @@ namespace rzb
 		uint32_t steps, tris;       // STATS only
 	};
 
-	template <bool ANY, bool STATS>
+	template <bool ANY, bool STATS, bool FAST>
 	__device__ __forceinline__ void trav_begin(const DScene& sc, Trav& t, const bool active, const V3 origin, const V3 direction,
 		const float near_in, const float far_in, Stack& st, ParkedRay& park, TraceCounters& cnt)
 	{
@@ -150,7 +161,7 @@ namespace rzb
 			const float4 n1 = __ldg(sc.nodes + 2 * size_t(sc.top_root) + 1);
 			if (STATS) cnt.top_nodes++;
 			float tmin;
-			t.alive = slab_hit(n0, n1, t.o, t.d, t.rcp, t.near_, t.far_, t.margin, tmin);
+			t.alive = slab_hit<FAST>(n0, n1, t.o, t.d, t.rcp, t.near_, t.far_, t.margin, tmin);
 			t.cur_begin = __float_as_uint(n1.z);
 			t.cur_tc = __float_as_uint(n1.w);
 		}
@@ -158,7 +169,7 @@ namespace rzb
 
 	// One round: descend from the current node to a leaf, intersect it, pop until a node with a passed box is current
 	// (or the ray is finished). Invariant: an alive lane has a current node whose box test has passed.
-	template <bool ANY, bool STATS>
+	template <bool ANY, bool STATS, bool FAST>
 	__device__ __forceinline__ void trav_round(const DScene& sc, Trav& t, Stack& st, ParkedRay& park, TraceCounters& cnt)
 	{
 		const float4* __restrict__ nodes = sc.nodes;
@@ -172,8 +183,8 @@ namespace rzb
 				const float4 p0 = __ldg(pair), p1 = __ldg(pair + 1), p2 = __ldg(pair + 2), p3 = __ldg(pair + 3);
 				if (STATS) { if (t.in_mesh) cnt.mesh_nodes += 2; else cnt.top_nodes += 2; t.steps++; }
 				float tm0, tm1;
-				const bool h0 = slab_hit(p0, p1, t.o, t.d, t.rcp, t.near_, t.far_, t.margin, tm0);
-				const bool h1 = slab_hit(p2, p3, t.o, t.d, t.rcp, t.near_, t.far_, t.margin, tm1);
+				const bool h0 = slab_hit<FAST>(p0, p1, t.o, t.d, t.rcp, t.near_, t.far_, t.margin, tm0);
+				const bool h1 = slab_hit<FAST>(p2, p3, t.o, t.d, t.rcp, t.near_, t.far_, t.margin, tm1);
 				// near child first: `flip` = the second child is the near one
 				const bool flip = !ANY && ((t.sbits >> (t.cur_tc >> 30)) & 1u) != 0u;
 				const bool hit_a = flip ? h1 : h0, hit_b = flip ? h0 : h1;
@@ -278,7 +289,7 @@ namespace rzb
 				const float4 n0 = make_float4(in.bminx, in.bminy, in.bminz, in.bmaxx);
 				const float4 n1 = make_float4(in.bmaxy, in.bmaxz, 0.0f, 0.0f);
 				float tmin;
-				if (!slab_hit(n0, n1, t.o, t.d, t.rcp, t.near_, t.far_, t.margin, tmin)) continue;
+				if (!slab_hit<FAST>(n0, n1, t.o, t.d, t.rcp, t.near_, t.far_, t.margin, tmin)) continue;
 				if (in.mesh_root == kNoIndex) continue;
 				V3 lo, ld;
 				float l;
@@ -289,7 +300,7 @@ namespace rzb
 				const float4 r0 = __ldg(nodes + 2 * size_t(in.mesh_root));
 				const float4 r1 = __ldg(nodes + 2 * size_t(in.mesh_root) + 1);
 				if (STATS) cnt.mesh_nodes++;
-				if (!slab_hit(r0, r1, lo, ld, lrcp, lnear, lfar, lmargin, tmin)) continue;
+				if (!slab_hit<FAST>(r0, r1, lo, ld, lrcp, lnear, lfar, lmargin, tmin)) continue;
 				t.in_mesh = true; t.mesh_hit = false;
 				t.cur_inst = idx;
 				t.mat_offset = in.mat_offset; t.mat_count = in.mat_count;
@@ -301,7 +312,11 @@ namespace rzb
 				break;
 			}
 			// a deferred node of the current level
-			if (!ANY)
+			if (!ANY && FAST)
+			{
+				if (__uint_as_float(e.y) > t.far_) continue; // the stored entry distance is already the conservative one
+			}
+			else if (!ANY)
 			{
 				// late range test (the reference tests the far child after the near subtree has been searched)
 				const float tmin = __uint_as_float(e.y);
@@ -344,14 +359,14 @@ namespace rzb
 	// run its own rounds. Measured on B200 (1M-triangle scene, ms per pass; profiles/): closest hit 1.38 free-running
 	// vs 1.79 synchronised; any hit 0.75 free-running (triangle code at ~2 of 32 lanes) vs 0.43 synchronised -- so the
 	// closest-hit kernels instantiate SYNC = false and the shadow kernels SYNC = true.
-	template <bool ANY, bool STATS, bool SYNC = ANY>
+	template <bool ANY, bool STATS, bool SYNC = ANY, bool FAST = false>
 	__device__ __forceinline__ void trace_ray(const DScene& sc, const bool active, const V3 origin, const V3 direction,
 		const float near_in, const float far_in, Stack& st, ParkedRay& park, TraceCounters& cnt, RayResult& res)
 	{
 		Trav t;
-		trav_begin<ANY, STATS>(sc, t, active, origin, direction, near_in, far_in, st, park, cnt);
+		trav_begin<ANY, STATS, FAST>(sc, t, active, origin, direction, near_in, far_in, st, park, cnt);
 		while (SYNC ? __any_sync(0xFFFFFFFFu, t.alive) != 0 : t.alive)
-			trav_round<ANY, STATS>(sc, t, st, park, cnt);
+			trav_round<ANY, STATS, FAST>(sc, t, st, park, cnt);
 		trav_end(t, active, near_in, far_in, park, res);
 	}
 }

@@ -80,11 +80,17 @@ class Mesh:
     index: int = 0
     normals_input: Optional[np.ndarray] = None  # what was passed to createNormal (written to scene files)
     _bvh: Optional[tuple] = None
+    # "reference" = the reference's own tree (parity mode); ("sah", max_leaf) = the optional SAH builder
+    bvh_builder: object = "reference"
 
     def bvh(self):
-        if self._bvh is None:
-            self._bvh = capi.build_mesh_bvh(self.vertices, self.tris)
-        return self._bvh
+        if self._bvh is None or self._bvh[0] != self.bvh_builder:
+            if self.bvh_builder == "reference":
+                built = capi.build_mesh_bvh(self.vertices, self.tris)
+            else:
+                built = capi.build_mesh_bvh_sah(self.vertices, self.tris, int(self.bvh_builder[1]))
+            self._bvh = (self.bvh_builder, built)
+        return self._bvh[1]
 
 
 @dataclass
@@ -277,6 +283,8 @@ class World:
         out["triangles"] = np.concatenate(all_tris) if all_tris else np.zeros(0, dtype=capi.triangle_dtype)
         out["tri_host_index"] = np.concatenate(all_thi) if all_thi else np.zeros(0, dtype=np.uint32)
         out["meshes"] = np.array(mesh_recs, dtype=capi.mesh_dtype) if mesh_recs else np.zeros(0, dtype=capi.mesh_dtype)
+        if any(m.bvh_builder != "reference" for m in self.meshes):
+            out["scene_flags"] = np.array([capi.SCENE_OWN_TREES], dtype=np.uint32)  # absent = the reference's trees
 
         # lights
         dl = np.zeros(len(self.direct_lights), dtype=capi.direct_light_dtype)
