@@ -399,6 +399,36 @@ def main():
                        "shadow_ms": float(st2["last_shadow_ms"])}
             except Exception as e:  # the headline line must still be printed
                 aux = {"workload": "heightfield_1m_1080p", "error": repr(e)}
+        # the same workload on the optional SAH trees (RZB_SCENE_OWN_TREES; records equal except exact ties)
+        if not args.no_aux and BVH == "reference":
+            own = {}
+            try:
+                BVH = "sah"
+                for wl in (args.workload, "heightfield_1m_1080p"):
+                    w3 = build_world(wl)
+                    ctx.set_scene(w3.flatten())
+                    ctx.set_camera(w3.camera_struct())
+                    ctx.reset()
+                    ctx.render(args.warmup)
+                    torch.cuda.synchronize()
+                    a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    n3 = min(args.steps, 256)
+                    a0.record(stream)
+                    ctx.render(n3)
+                    a1.record(stream)
+                    a1.synchronize()
+                    st3 = ctx.render_stats()
+                    own[wl] = {"value": n3 * n_px / (a0.elapsed_time(a1) * 1e-3) / 1e6, "unit": "Mrays/s", "steps": n3,
+                               "trace_ms": float(st3["last_trace_ms"]), "shade_ms": float(st3["last_shade_ms"]),
+                               "shadow_ms": float(st3["last_shadow_ms"])}
+            except Exception as e:
+                own["error"] = repr(e)
+            finally:
+                BVH = "reference"
+            if aux is not None:
+                aux["own_trees_sah"] = own
+            else:
+                aux = {"own_trees_sah": own}
         if not args.no_cpu_baseline:
             try:
                 r = reference_run(args.workload, 8, 1, budget_s=25.0)

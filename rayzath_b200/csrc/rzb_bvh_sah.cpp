@@ -11,6 +11,11 @@
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
+#include <atomic>
+#include <condition_variable>
+#include <deque>
+#include <mutex>
+#include <thread>
 #include <vector>
 
 namespace
@@ -68,14 +73,18 @@ extern "C" int rzb_build_mesh_bvh_sah(const float* vertices, uint32_t nv, const 
 	std::vector<uint32_t> ids(nt);
 	for (uint32_t i = 0; i < nt; ++i) ids[i] = i;
 
-	std::vector<rzb_node> nodes;
-	nodes.reserve(2 * size_t(nt) / std::max(1u, max_leaf / 2u) + 16);
-	nodes.push_back(rzb_node{});
-	std::vector<Task> stack{{0u, 0u, nt, 0u}};
-	while (!stack.empty())
-	{
-		const Task t = stack.back();
-		stack.pop_back();
+	// nodes are allocated as sibling pairs from an atomic cursor (pairs start at odd indices, as the kernels' 64-byte
+	// pair fetch wants); big ranges go through a shared queue served by all host threads, small ones stay on the
+	// worker's own stack
+	std::vector<rzb_node> nodes(2 * size_t(nt) + 1);
+	std::atomic<uint32_t> cursor{1u};
+	std::mutex mtx;
+	std::condition_variable cv;
+	std::deque<Task> shared{{0u, 0u, nt, 0u}};
+	uint32_t busy = 0;
+	const uint32_t kShareAbove = 8192;
+
+	auto process = [&](const Task& t, std::vector<Task>& local) {
 		const uint32_t n = t.end - t.begin;
 		Box bb, cb;
 		for (uint32_t i = t.begin; i < t.end; ++i) { bb.add(boxes[ids[i]]); cb.add(cent[ids[i]]); }
@@ -133,7 +142,7 @@ extern "C" int rzb_build_mesh_bvh_sah(const float* vertices, uint32_t nv, const 
 			node.begin = t.begin;
 			node.type_count = n; // split type bits unused for leaves
 			nodes[t.node] = node;
-			continue;
+			return;
 		}
 		uint32_t mid;
 		int split_axis = best_axis;
@@ -156,15 +165,79 @@ extern "C" int rzb_build_mesh_bvh_sah(const float* vertices, uint32_t nv, const 
 			split_axis = 0;
 		}
 		if (mid == t.begin || mid == t.end) mid = t.begin + n / 2;
-		const uint32_t child = uint32_t(nodes.size());
-		nodes.push_back(rzb_node{});
-		nodes.push_back(rzb_node{});
+		const uint32_t child = cursor.fetch_add(2u);
+		
 		node.begin = child;
 		// split type in bits 30..31: X = 2, Y = 1, Z = 0 (bvh_tree_node.hpp:21-27); first child = lower side
 		node.type_count = uint32_t(2 - split_axis) << 30;
 		nodes[t.node] = node;
-		stack.push_back({child + 1u, mid, t.end, t.depth + 1u});
-		stack.push_back({child, t.begin, mid, t.depth + 1u});
+		const Task a{child, t.begin, mid, t.depth + 1u}, b{child + 1u, mid, t.end, t.depth + 1u};
+		for (const Task& c : {b, a})
+		{
+			if (c.end - c.begin > kShareAbove)
+			{
+				std::lock_guard<std::mutex> lg(mtx);
+				shared.push_back(c);
+				cv.notify_one();
+			}
+			else local.push_back(c);
+		}
+	};
+	auto worker = [&]() {
+		std::vector<Task> local;
+		for (;;)
+		{
+			Task t;
+			{
+				std::unique_lock<std::mutex> lk(mtx);
+				cv.wait(lk, [&] { return !shared.empty() || busy == 0; });
+				if (shared.empty()) { cv.notify_all(); return; }
+				t = shared.front();
+				shared.pop_front();
+				++busy;
+			}
+			local.push_back(t);
+			while (!local.empty())
+			{
+				const Task c = local.back();
+				local.pop_back();
+				process(c, local);
+			}
+			{
+				std::lock_guard<std::mutex> lg(mtx);
+				--busy;
+			}
+			cv.notify_all();
+		}
+	};
+	const unsigned hw = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+	const unsigned n_threads = nt < 4 * kShareAbove ? 1u : hw;
+	std::vector<std::thread> pool;
+	for (unsigned i = 1; i < n_threads; ++i) pool.emplace_back(worker);
+	worker();
+	for (auto& th : pool) th.join();
+	nodes.resize(cursor.load());
+	{
+		// canonical layout, independent of thread timing: root, then per inner node its sibling pair followed by the
+		// first child's subtree and the second child's (the order Mesh::reconstruct uses, cuda_instance.cu:161-220)
+		std::vector<rzb_node> laid(nodes.size());
+		laid[0] = nodes[0];
+		uint32_t next = 1u;
+		std::vector<uint32_t> todo{0u}; // indices into `laid` whose children still live at old indices
+		while (!todo.empty())
+		{
+			const uint32_t i = todo.back();
+			todo.pop_back();
+			if ((laid[i].type_count & 0x3FFFFFFFu) != 0u) continue;
+			const uint32_t old_child = laid[i].begin;
+			laid[next] = nodes[old_child];
+			laid[next + 1u] = nodes[old_child + 1u];
+			laid[i].begin = next;
+			todo.push_back(next + 1u);
+			todo.push_back(next);
+			next += 2u;
+		}
+		nodes.swap(laid);
 	}
 	if (nodes.size() > node_capacity) return RZB_ERR_NOMEM;
 	std::memcpy(nodes_out, nodes.data(), nodes.size() * sizeof(rzb_node));

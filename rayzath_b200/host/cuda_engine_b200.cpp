@@ -17,7 +17,8 @@
 // the CPU engine (rayzath.cpp:21-28). Behaviour changed (documented in INTEGRATION.md): the call is synchronous
 // for both values of `sync` (the reference pipelines one frame when sync == false); the per-call random seeds of
 // cuda_kernel_data.cu:10-18 become one seed per engine (RZB200_SEED or std::random_device) + the pass counter.
-// Multi-GPU: RZB200_DEVICES="0,1,..." renders one disjoint sample stream per listed device and sums the
+// RZB200_BVH=sah replaces the host World's triangle trees by this repo's SAH trees (RZB_SCENE_OWN_TREES; hit records
+// equal except exact-distance ties). Multi-GPU: RZB200_DEVICES="0,1,..." renders one disjoint sample stream per listed device and sums the
 // accumulators in the fused peer resolve (rzb_resolve_peers) on the first device.
 #include "cuda_engine.cuh"
 #include "cuda_exception.hpp"
@@ -50,6 +51,7 @@ namespace RayZath::Cuda
 		std::map<uint32_t, CameraState> m_cameras; // by camera container index
 		uint64_t m_seed = 0;
 		uint64_t m_scene_version = 0;
+		bool m_own_trees = false; // RZB200_BVH=sah: this repo's SAH triangle trees instead of the host World's
 		rzb_host::FlatScene m_flat;
 		std::string m_timings;
 
@@ -72,6 +74,7 @@ namespace RayZath::Cuda
 					if (!tok.empty()) m_devices.push_back(std::atoi(tok.c_str()));
 			}
 			if (m_devices.empty()) m_devices.push_back(0);
+			if (const char* env = std::getenv("RZB200_BVH")) m_own_trees = std::string(env) == "sah";
 			if (const char* env = std::getenv("RZB200_SEED")) m_seed = std::strtoull(env, nullptr, 0);
 			else
 			{
@@ -108,7 +111,7 @@ namespace RayZath::Cuda
 
 			if (world_update || m_scene_version == 0)
 			{
-				rzb_host::WorldFlattener(hWorld, m_flat).run();
+				rzb_host::WorldFlattener(hWorld, m_flat, m_own_trees).run();
 				++m_scene_version;
 				for (auto& [idx, cam] : m_cameras) cam.scene_current = false;
 				clearFlags(hWorld);

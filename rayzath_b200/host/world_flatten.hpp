@@ -39,6 +39,7 @@ namespace rzb_host
 		std::vector<rzb_spot_light> spot_lights;
 		rzb_material world_material{};
 		uint32_t default_material = 0;
+		uint32_t scene_flags = RZB_SCENE_REFERENCE_TREES;
 
 		rzb_scene view() const
 		{
@@ -57,6 +58,7 @@ namespace rzb_host
 			s.spot_lights = spot_lights.data(); s.spot_light_count = uint32_t(spot_lights.size());
 			s.world_material = world_material;
 			s.default_material = default_material;
+			s.flags = scene_flags;
 			return s;
 		}
 	};
@@ -185,13 +187,40 @@ namespace rzb_host
 			if (!c1.isLeaf()) buildChildren(mesh, c1, node_base, tri_base);
 			if (!c2.isLeaf()) buildChildren(mesh, c2, node_base, tri_base);
 		}
+		// Optional: ignore the host tree and build this repo's SAH tree over the same triangles (rzb_build_mesh_bvh_sah;
+		// RZB_SCENE_OWN_TREES). The triangle records are the same, only their order and the nodes differ.
+		bool flattenMeshOwnTree(const RZ::Mesh& mesh, rzb_mesh& m)
+		{
+			const uint32_t nt = mesh.triangles().count(), nv = mesh.vertices().count();
+			std::vector<float> verts(size_t(nv) * 3);
+			for (uint32_t i = 0; i < nv; ++i) put3(&verts[size_t(i) * 3], mesh.vertices()[i]);
+			std::vector<uint32_t> ids(size_t(nt) * 3);
+			for (uint32_t i = 0; i < nt; ++i)
+			{
+				const RZ::Triangle& t = mesh.triangles()[i];
+				if (!t.areVertsValid()) return false; // keep the host tree for meshes with placeholder triangles
+				for (int k = 0; k < 3; ++k) ids[size_t(i) * 3 + k] = t.vertices[k];
+			}
+			std::vector<rzb_node> nodes(size_t(nt) * 2 + 1);
+			std::vector<uint32_t> order(nt);
+			uint32_t count = 0;
+			if (rzb_build_mesh_bvh_sah(verts.data(), nv, ids.data(), nt, 4, nodes.data(), uint32_t(nodes.size()), &count, order.data()) != RZB_OK)
+				return false;
+			out.mesh_nodes.insert(out.mesh_nodes.end(), nodes.begin(), nodes.begin() + count);
+			for (uint32_t i = 0; i < nt; ++i) addTriangle(mesh, mesh.triangles()[order[i]]);
+			return true;
+		}
 		void flattenMesh(const RZ::Mesh& mesh)
 		{
 			rzb_mesh m{};
 			m.node_offset = uint32_t(out.mesh_nodes.size());
 			m.tri_offset = uint32_t(out.triangles.size());
 			const auto& root = mesh.triangles().getBVH().rootNode();
-			if (mesh.triangles().count() != 0)
+			if (own_trees && mesh.triangles().count() != 0 && flattenMeshOwnTree(mesh, m))
+			{
+				out.scene_flags = RZB_SCENE_OWN_TREES;
+			}
+			else if (mesh.triangles().count() != 0)
 			{
 				if (root.isLeaf()) addLeaf(mesh, root, m.node_offset, m.tri_offset);
 				else
@@ -272,7 +301,9 @@ namespace rzb_host
 		}
 
 	public:
-		WorldFlattener(const RZ::World& w, FlatScene& o) : world(w), out(o) {}
+		// own_trees: build this repo's SAH triangle trees instead of flattening the host's (the reference's) trees
+		bool own_trees = false;
+		WorldFlattener(const RZ::World& w, FlatScene& o, bool own_trees_ = false) : world(w), out(o), own_trees(own_trees_) {}
 
 		// Precondition: world.update() has been called (host BVHs are current), cuda_engine_core.cu:58-60.
 		void run()

@@ -16,13 +16,14 @@ BIN = os.path.join(ROOT, "rayzath_b200", "host", "_build", "rz_b200_headless")
 
 
 @pytest.mark.skipif(not os.path.exists(BIN), reason="drop-in binary not built (needs /root/reference at build time)")
-def test_headless_runner_renders_on_the_b200_path(tmp_path):
+@pytest.mark.parametrize("bvh", ["reference", "sah"])
+def test_headless_runner_renders_on_the_b200_path(tmp_path, bvh):
     w = scenes.materials_scene(resolution=(320, 180), res=24)
     w.save_reference(str(tmp_path), "scene")
     json.dump({"tasks": [{"scene path": "scene.json", "engine": ["CUDAGPU"], "rpp": 200, "timeout": 30.0}]},
               open(tmp_path / "tasks.json", "w"))
     os.makedirs(tmp_path / "report")
-    env = dict(os.environ, RZB200_VERBOSE="1", RZB200_SEED="7")
+    env = dict(os.environ, RZB200_VERBOSE="1", RZB200_SEED="7", RZB200_BVH=bvh)
     r = subprocess.run([BIN, "--headless", "tasks.json", "report", "-r"], cwd=tmp_path, env=env, capture_output=True,
                        text=True, timeout=300)
     assert r.returncode == 0, r.stderr[-2000:]
@@ -33,5 +34,6 @@ def test_headless_runner_renders_on_the_b200_path(tmp_path):
     assert "CUDAGPU" in text
     m = re.search(r"traced\s+([0-9.]+)([kMGT]?)", text)
     assert m, text
-    images = [f for dp, _, fs in os.walk(tmp_path / "report") for f in fs if f.lower().endswith((".png", ".jpg"))]
+    images = [os.path.join(dp, f) for dp, _, fs in os.walk(tmp_path / "report") for f in fs if f.lower().endswith((".png", ".jpg"))]
     assert images, "no rendered image saved"
+    assert os.path.getsize(images[0]) > 1000
