@@ -80,7 +80,7 @@ struct rzb_ctx
 
 	uint64_t passes = 0, launches = 0;
 	float last_render_ms = 0.0f, last_trace_ms = 0.0f, last_shade_ms = 0.0f, last_shadow_ms = 0.0f;
-	int trace_grid = 0, shadow_grid = 0, rays_grid = 0, any_grid = 0;
+	int trace_grid = 0, shadow_grid = 0, rays_grid = 0, any_grid = 0, trace_grid_fast = 0, shadow_grid_fast = 0;
 	bool own_trees = false;        // rzb_scene::flags & RZB_SCENE_OWN_TREES: conservative box tests
 	bool debug_sync = false;       // RZB200_DEBUG_SYNC: synchronise after every kernel of rzb_render and name the one that faulted
 };
@@ -276,6 +276,8 @@ extern "C" int rzb_create(int device, rzb_ctx** out)
 	ctx->debug_sync = std::getenv("RZB200_DEBUG_SYNC") != nullptr;
 	ctx->trace_grid = gridFor(ctx, reinterpret_cast<const void*>(&k_trace_paths<false, false>), kTraceBlock);
 	ctx->shadow_grid = gridFor(ctx, reinterpret_cast<const void*>(&k_trace_shadow<false, false>), kTraceBlock);
+	ctx->trace_grid_fast = gridFor(ctx, reinterpret_cast<const void*>(&k_trace_paths<false, true>), kTraceBlock);
+	ctx->shadow_grid_fast = gridFor(ctx, reinterpret_cast<const void*>(&k_trace_shadow<false, true>), kTraceBlock);
 	ctx->rays_grid = gridFor(ctx, reinterpret_cast<const void*>(&k_trace_rays<false, false>), kTraceBlock);
 	ctx->any_grid = gridFor(ctx, reinterpret_cast<const void*>(&k_trace_any_rays<false>), kTraceBlock);
 	*out = ctx;
@@ -657,8 +659,8 @@ extern "C" int rzb_render(rzb_ctx* ctx, uint32_t passes)
 		cudaEvent_t* ev = timed ? &ctx->ev_stage[size_t(ctx->sampled_passes) * 4] : nullptr;
 		RZB_CUDA(ctx, cudaMemsetAsync(ctx->d_counters, 0, 12, ctx->stream));
 		if (timed) cudaEventRecord(ev[0], ctx->stream);
-		if (count) { if (fast) k_trace_paths<true, true><<<ctx->trace_grid, kTraceBlock, 0, ctx->stream>>>(ctx->sc, f); else k_trace_paths<true, false><<<ctx->trace_grid, kTraceBlock, 0, ctx->stream>>>(ctx->sc, f); }
-		else { if (fast) k_trace_paths<false, true><<<ctx->trace_grid, kTraceBlock, 0, ctx->stream>>>(ctx->sc, f); else k_trace_paths<false, false><<<ctx->trace_grid, kTraceBlock, 0, ctx->stream>>>(ctx->sc, f); }
+		if (count) { if (fast) k_trace_paths<true, true><<<ctx->trace_grid_fast, kTraceBlock, 0, ctx->stream>>>(ctx->sc, f); else k_trace_paths<true, false><<<ctx->trace_grid, kTraceBlock, 0, ctx->stream>>>(ctx->sc, f); }
+		else { if (fast) k_trace_paths<false, true><<<ctx->trace_grid_fast, kTraceBlock, 0, ctx->stream>>>(ctx->sc, f); else k_trace_paths<false, false><<<ctx->trace_grid, kTraceBlock, 0, ctx->stream>>>(ctx->sc, f); }
 		if (ctx->debug_sync)
 		{
 			const cudaError_t e = cudaStreamSynchronize(ctx->stream);
@@ -675,8 +677,8 @@ extern "C" int rzb_render(rzb_ctx* ctx, uint32_t passes)
 		ctx->launches += 2;
 		if (lights)
 		{
-			if (count) { if (fast) k_trace_shadow<true, true><<<ctx->shadow_grid, kTraceBlock, 0, ctx->stream>>>(ctx->sc, f); else k_trace_shadow<true, false><<<ctx->shadow_grid, kTraceBlock, 0, ctx->stream>>>(ctx->sc, f); }
-			else { if (fast) k_trace_shadow<false, true><<<ctx->shadow_grid, kTraceBlock, 0, ctx->stream>>>(ctx->sc, f); else k_trace_shadow<false, false><<<ctx->shadow_grid, kTraceBlock, 0, ctx->stream>>>(ctx->sc, f); }
+			if (count) { if (fast) k_trace_shadow<true, true><<<ctx->shadow_grid_fast, kTraceBlock, 0, ctx->stream>>>(ctx->sc, f); else k_trace_shadow<true, false><<<ctx->shadow_grid, kTraceBlock, 0, ctx->stream>>>(ctx->sc, f); }
+			else { if (fast) k_trace_shadow<false, true><<<ctx->shadow_grid_fast, kTraceBlock, 0, ctx->stream>>>(ctx->sc, f); else k_trace_shadow<false, false><<<ctx->shadow_grid, kTraceBlock, 0, ctx->stream>>>(ctx->sc, f); }
 			ctx->launches += 1;
 			if (ctx->debug_sync)
 			{

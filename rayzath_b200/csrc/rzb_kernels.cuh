@@ -182,7 +182,7 @@ namespace rzb
 	}
 
 	template <bool STATS, bool FAST>
-	__global__ void __launch_bounds__(kTraceBlock, 6) k_trace_paths(DScene sc, DFrame f)
+	__global__ void __launch_bounds__(kTraceBlock, FAST ? 8 : 6) k_trace_paths(DScene sc, DFrame f)
 	{
 		__shared__ uint2 smem_stack[kSmemStack * kTraceBlock];
 		__shared__ ParkedRay smem_park[kTraceBlock];
@@ -470,7 +470,7 @@ namespace rzb
 	// of busy lane-rounds from 0.44 to 0.70-0.88 on the materials scene but not the speed (1.33 -> 1.28..1.41 ms; 1M
 	// triangles 0.44 -> 0.46..0.62 ms): a round costs what its longest descend / leaf loop costs.
 	template <bool STATS, bool FAST>
-	__global__ void __launch_bounds__(kTraceBlock, 6) k_trace_shadow(DScene sc, DFrame f)
+	__global__ void __launch_bounds__(kTraceBlock, FAST ? 8 : 6) k_trace_shadow(DScene sc, DFrame f)
 	{
 		__shared__ uint2 smem_stack[kSmemStack * kTraceBlock];
 		__shared__ ParkedRay smem_park[kTraceBlock];
@@ -488,7 +488,7 @@ namespace rzb
 			float4 o = make_float4(0.0f, 0.0f, 0.0f, 0.0f), d = make_float4(0.0f, 0.0f, 1.0f, 0.0f);
 			if (active) { o = f.sh_o[i]; d = f.sh_d[i]; }
 			RayResult r;
-			trace_ray<true, STATS, true, FAST>(sc, active, v3(o.x, o.y, o.z), v3(d.x, d.y, d.z), 0.0f, o.w, st, park, cnt, r);
+			trace_ray<true, STATS, !FAST, FAST>(sc, active, v3(o.x, o.y, o.z), v3(d.x, d.y, d.z), 0.0f, o.w, st, park, cnt, r);
 			if (STATS) batch_utilisation(active ? r.steps + r.tris : 0u, f.work + 12);
 			const float w = r.mask.w;
 			if (!active || w <= 0.0f) continue;

@@ -186,7 +186,8 @@ namespace rzb
 				const bool h0 = slab_hit<FAST>(p0, p1, t.o, t.d, t.rcp, t.near_, t.far_, t.margin, tm0);
 				const bool h1 = slab_hit<FAST>(p2, p3, t.o, t.d, t.rcp, t.near_, t.far_, t.margin, tm1);
 				// near child first: `flip` = the second child is the near one
-				const bool flip = !ANY && ((t.sbits >> (t.cur_tc >> 30)) & 1u) != 0u;
+				// own trees (FAST): nearer entry first; reference trees: by ray sign on the split axis, as the reference does
+				const bool flip = !ANY && (FAST ? (h0 && h1 && tm1 < tm0) : ((t.sbits >> (t.cur_tc >> 30)) & 1u) != 0u);
 				const bool hit_a = flip ? h1 : h0, hit_b = flip ? h0 : h1;
 				if (hit_a)
 				{
