@@ -43,6 +43,7 @@ WORKLOADS = {
 }
 # reference-layout byte constants for the algorithmic traffic figure (SURVEY.md 8d / DESIGN.md)
 B_NODE, B_TRI, B_STATE, B_HIT = 48, 144, 57, 24
+B_SHADOW_REC, B_SHADOW_ACC = 48, 12  # shadow queue record read, accumulator update
 MAX_DEPTH = 16          # Tracing::maxDepth default, engine_parts.hpp:101
 RPP_E2E = 64            # passes per renderWorld call the headless auto-tuner converges to (headless.cpp:287-295)
 
@@ -322,14 +323,30 @@ def main():
                  "shadow": float(wc["shadow_lane_work"]) / max(int(wc["shadow_batch_work"]), 1),
                  "dropped_non_finite_samples": int(wc["invalid_rays"])}
     bytes_per_seg = B_STATE + nodes_per_seg * B_NODE + tris_per_seg * B_TRI + B_HIT
-    achieved = bytes_per_seg * n_px / (trace_ms * 1e-3) / 1e9 if trace_ms > 0 else None
-    traffic = None
-    prof = os.path.join(ROOT, "profiles", "ncu_summary.json")
-    if os.path.exists(prof):
+    # the shadow kernel in the same currency: per shadow ray the 48-byte queue record, the box and triangle tests of
+    # the any-hit walk (reference layout: 48 B nodes, 144 B triangles) and the 12-byte accumulator update
+    n_shadow = max(int(wc["shadow_rays"]), 1)
+    sh_nodes = float(wc["shadow_top_nodes"] + wc["shadow_mesh_nodes"]) / n_shadow
+    sh_tris = float(wc["shadow_triangles"]) / n_shadow
+    bytes_per_shadow_ray = B_SHADOW_REC + sh_nodes * B_NODE + sh_tris * B_TRI + B_SHADOW_ACC
+    prof = {}
+    prof_path = os.path.join(ROOT, "profiles", "ncu_summary.json")
+    if os.path.exists(prof_path):
         try:
-            traffic = json.load(open(prof)).get(args.workload, {}).get("k_trace_paths_dram_bytes_per_launch")
+            prof = json.load(open(prof_path)).get(args.workload if BVH == "reference" else args.workload + "_sah", {})
         except Exception:
-            traffic = None
+            prof = {}
+    kernels = {
+        "k_trace_paths": {"ms": trace_ms, "units_per_launch": n_px, "algorithmic_bytes_per_unit": bytes_per_seg,
+                          "achieved": bytes_per_seg * n_px / (trace_ms * 1e-3) / 1e9 if trace_ms > 0 else None,
+                          "traffic": prof.get("k_trace_paths_dram_bytes_per_launch")},
+        "k_trace_shadow": {"ms": shadow_ms, "units_per_launch": shadow_per_seg * n_px,
+                           "algorithmic_bytes_per_unit": bytes_per_shadow_ray,
+                           "achieved": bytes_per_shadow_ray * shadow_per_seg * n_px / (shadow_ms * 1e-3) / 1e9 if shadow_ms > 0 else None,
+                           "traffic": prof.get("k_trace_shadow_dram_bytes_per_launch")},
+    }
+    dominant = max(kernels, key=lambda k: kernels[k]["ms"])
+    achieved, traffic = kernels[dominant]["achieved"], kernels[dominant]["traffic"]
     ctx.set_config(1, 1, MAX_DEPTH, capi.FLAG_NONE, seed)
 
     # ---- e2e through the boundary with host buffers (every step = one renderWorld-equivalent frame)
@@ -455,10 +472,13 @@ def main():
                     "frames": e2e_frames},
             "gpu_launches": launches,
             "stage_ms_per_pass": {"k_trace_paths": trace_ms, "k_shade": shade_ms, "k_trace_shadow": shadow_ms},
-            "roofline": {"bound": "hbm", "kernel": "k_trace_paths", "achieved": achieved, "peak": peak, "unit": "GB/s",
+            # top level = the kernel with the largest share of the step (the dominant one); both traversal kernels below
+            "roofline": {"bound": "hbm", "kernel": dominant, "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": (achieved / peak) if achieved else None, "traffic": traffic, "peak_source": peak_src,
+                         "kernels": {k: dict(v, frac=(v["achieved"] / peak) if v["achieved"] else None) for k, v in kernels.items()},
                          "algorithmic_bytes_per_segment": bytes_per_seg, "nodes_per_segment": nodes_per_seg,
                          "triangles_per_segment": tris_per_seg, "shadow_rays_per_segment": shadow_per_seg,
+                         "nodes_per_shadow_ray": sh_nodes, "triangles_per_shadow_ray": sh_tris,
                          "segments_per_launch": n_px, "batch_lane_utilisation": lane_util},
             "cpu_baseline": cpu, "aux": aux,
         })

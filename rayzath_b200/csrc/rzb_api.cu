@@ -80,7 +80,7 @@ struct rzb_ctx
 
 	uint64_t passes = 0, launches = 0;
 	float last_render_ms = 0.0f, last_trace_ms = 0.0f, last_shade_ms = 0.0f, last_shadow_ms = 0.0f;
-	int trace_grid = 0, shadow_grid = 0, rays_grid = 0, any_grid = 0, trace_grid_fast = 0, shadow_grid_fast = 0;
+	int trace_grid = 0, shadow_grid = 0, rays_grid = 0, any_grid = 0, trace_grid_fast = 0;
 	bool own_trees = false;        // rzb_scene::flags & RZB_SCENE_OWN_TREES: conservative box tests
 	bool debug_sync = false;       // RZB200_DEBUG_SYNC: synchronise after every kernel of rzb_render and name the one that faulted
 };
@@ -275,11 +275,10 @@ extern "C" int rzb_create(int device, rzb_ctx** out)
 	cudaMemsetAsync(ctx->d_counters, 0, 256, ctx->stream);
 	ctx->debug_sync = std::getenv("RZB200_DEBUG_SYNC") != nullptr;
 	ctx->trace_grid = gridFor(ctx, reinterpret_cast<const void*>(&k_trace_paths<false, false>), kTraceBlock);
-	ctx->shadow_grid = gridFor(ctx, reinterpret_cast<const void*>(&k_trace_shadow<false, false>), kTraceBlock);
+	ctx->shadow_grid = gridFor(ctx, reinterpret_cast<const void*>(&k_trace_shadow<false>), kTraceBlock);
 	ctx->trace_grid_fast = gridFor(ctx, reinterpret_cast<const void*>(&k_trace_paths<false, true>), kTraceBlock);
-	ctx->shadow_grid_fast = gridFor(ctx, reinterpret_cast<const void*>(&k_trace_shadow<false, true>), kTraceBlock);
 	ctx->rays_grid = gridFor(ctx, reinterpret_cast<const void*>(&k_trace_rays<false, false>), kTraceBlock);
-	ctx->any_grid = gridFor(ctx, reinterpret_cast<const void*>(&k_trace_any_rays<false>), kTraceBlock);
+	ctx->any_grid = gridFor(ctx, reinterpret_cast<const void*>(&k_trace_any_rays), kTraceBlock);
 	*out = ctx;
 	return RZB_OK;
 }
@@ -677,8 +676,8 @@ extern "C" int rzb_render(rzb_ctx* ctx, uint32_t passes)
 		ctx->launches += 2;
 		if (lights)
 		{
-			if (count) { if (fast) k_trace_shadow<true, true><<<ctx->shadow_grid_fast, kTraceBlock, 0, ctx->stream>>>(ctx->sc, f); else k_trace_shadow<true, false><<<ctx->shadow_grid, kTraceBlock, 0, ctx->stream>>>(ctx->sc, f); }
-			else { if (fast) k_trace_shadow<false, true><<<ctx->shadow_grid_fast, kTraceBlock, 0, ctx->stream>>>(ctx->sc, f); else k_trace_shadow<false, false><<<ctx->shadow_grid, kTraceBlock, 0, ctx->stream>>>(ctx->sc, f); }
+			if (count) k_trace_shadow<true><<<ctx->shadow_grid, kTraceBlock, 0, ctx->stream>>>(ctx->sc, f);
+			else k_trace_shadow<false><<<ctx->shadow_grid, kTraceBlock, 0, ctx->stream>>>(ctx->sc, f);
 			ctx->launches += 1;
 			if (ctx->debug_sync)
 			{
@@ -1023,7 +1022,7 @@ extern "C" int rzb_trace_any(rzb_ctx* ctx, const float* origins, const float* di
 	if ((rc = packRays(ctx, origins, directions, near_far, n))) return rc;
 	if ((rc = ensureScratch(ctx, 2, size_t(n) * 16))) return rc;
 	RZB_CUDA(ctx, cudaMemsetAsync(ctx->d_counters + 8, 0, 4, ctx->stream));
-	(ctx->own_trees ? k_trace_any_rays<true> : k_trace_any_rays<false>)<<<ctx->any_grid, kTraceBlock, 0, ctx->stream>>>(ctx->sc,
+	k_trace_any_rays<<<ctx->any_grid, kTraceBlock, 0, ctx->stream>>>(ctx->sc,
 		static_cast<const float4*>(ctx->scratch[0].ptr), static_cast<const float4*>(ctx->scratch[1].ptr), n,
 		static_cast<float4*>(ctx->scratch[2].ptr), ctx->d_counters + 8);
 	ctx->launches += 1;

@@ -465,12 +465,18 @@ namespace rzb
 	}
 
 	// ---------------------------------------------------------------- k_trace_shadow
-	// Any-hit queries over the shadow queue, whole-warp batches of 32 entries in warp-synchronised rounds.
-	// Measured and dropped: giving finished lanes new rays between rounds (threshold 1..24 idle lanes) raises the share
-	// of busy lane-rounds from 0.44 to 0.70-0.88 on the materials scene but not the speed (1.33 -> 1.28..1.41 ms; 1M
-	// triangles 0.44 -> 0.46..0.62 ms): a round costs what its longest descend / leaf loop costs.
-	template <bool STATS, bool FAST>
-	__global__ void __launch_bounds__(kTraceBlock, FAST ? 8 : 6) k_trace_shadow(DScene sc, DFrame f)
+	// Any-hit queries over the shadow queue, whole-warp batches of 32 entries, free-running lanes, CONSERVATIVE box
+	// test on every tree (64 registers, 8 blocks per SM). The result of a shadow query is the product of the opacities
+	// of all triangles the ray crosses -- independent of visiting order and of which boxes were opened, as long as no
+	// box the ray enters is skipped; the widened interval only ever opens more boxes than the reference's exact test.
+	// (A triangle in a box that the reference's own test rejects by rounding while the ray grazes it within 4 ulp
+	// is counted here and not there; none on the golden shadow rays, tests/test_gpu_parity.py.)
+	// Measured, ms per pass, reference trees (materials / 1M triangles): exact decisions + synchronised rounds 1.30 /
+	// 0.43; conservative + synchronised 1.12 / 0.35; conservative + free-running 0.77 / 0.25 (kept).
+	// Dropped: giving finished lanes new rays between synchronised rounds (threshold 1..24 idle lanes) raised the
+	// share of busy lane-rounds from 0.44 to 0.70-0.88 but not the speed (1.28..1.41 ms).
+	template <bool STATS>
+	__global__ void __launch_bounds__(kTraceBlock, 8) k_trace_shadow(DScene sc, DFrame f)
 	{
 		__shared__ uint2 smem_stack[kSmemStack * kTraceBlock];
 		__shared__ ParkedRay smem_park[kTraceBlock];
@@ -488,7 +494,7 @@ namespace rzb
 			float4 o = make_float4(0.0f, 0.0f, 0.0f, 0.0f), d = make_float4(0.0f, 0.0f, 1.0f, 0.0f);
 			if (active) { o = f.sh_o[i]; d = f.sh_d[i]; }
 			RayResult r;
-			trace_ray<true, STATS, !FAST, FAST>(sc, active, v3(o.x, o.y, o.z), v3(d.x, d.y, d.z), 0.0f, o.w, st, park, cnt, r);
+			trace_ray<true, STATS, false, true>(sc, active, v3(o.x, o.y, o.z), v3(d.x, d.y, d.z), 0.0f, o.w, st, park, cnt, r);
 			if (STATS) batch_utilisation(active ? r.steps + r.tris : 0u, f.work + 12);
 			const float w = r.mask.w;
 			if (!active || w <= 0.0f) continue;
@@ -599,8 +605,8 @@ namespace rzb
 		out[i] = r;
 	}
 
-	template <bool FAST>
-	__global__ void __launch_bounds__(kTraceBlock, 6) k_trace_any_rays(DScene sc, const float4* __restrict__ ray_o_near,
+	// the shadow kernel's traversal flavour (conservative boxes, free-running) over a caller's ray set
+	__global__ void __launch_bounds__(kTraceBlock, 8) k_trace_any_rays(DScene sc, const float4* __restrict__ ray_o_near,
 		const float4* __restrict__ ray_d_far, uint32_t n, float4* __restrict__ masks, uint32_t* counter)
 	{
 		__shared__ uint2 smem_stack[kSmemStack * kTraceBlock];
@@ -617,7 +623,7 @@ namespace rzb
 			float4 o = make_float4(0.0f, 0.0f, 0.0f, 0.0f), d = make_float4(0.0f, 0.0f, 1.0f, 0.0f);
 			if (active) { o = __ldg(ray_o_near + i); d = __ldg(ray_d_far + i); }
 			RayResult r;
-			trace_ray<true, false, true, FAST>(sc, active, v3(o.x, o.y, o.z), v3(d.x, d.y, d.z), o.w, d.w, st, park, cnt, r);
+			trace_ray<true, false, false, true>(sc, active, v3(o.x, o.y, o.z), v3(d.x, d.y, d.z), o.w, d.w, st, park, cnt, r);
 			if (active) masks[i] = r.mask;
 		}
 	}

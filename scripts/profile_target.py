@@ -9,8 +9,10 @@ import bench
 ap = argparse.ArgumentParser()
 ap.add_argument("--workload", default="heightfield_1m_1080p")
 ap.add_argument("--passes", type=int, default=12)
+ap.add_argument("--bvh", default="reference", choices=["reference", "sah"])
 ap.add_argument("--primary", type=int, default=0, help="also run the ray-set entry point on the primary rays N times")
 a = ap.parse_args()
+bench.BVH = a.bvh
 w = bench.build_world(a.workload)
 with capi.Context(0) as ctx:
     ctx.set_scene(w.flatten())
