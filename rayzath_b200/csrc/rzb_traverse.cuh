@@ -19,6 +19,7 @@
 //     distance, so the reference's late range test is a compare at pop time instead of a second box test;
 //   * one flat while-while loop serves both levels; the world ray and the committed hit live in shared memory while a
 //     mesh is being walked (they are only touched at instance transitions), which keeps the loop at <= 80 registers.
+// Scenes with own trees (RZB_SCENE_OWN_TREES) and all shadow queries use a conservative box test instead (FAST).
 // What was measured and dropped (B200, 1M-triangle scene): per-lane ray refill (startup = root test +
 // instance transform is too expensive to run for single lanes), warp-private work chunks, vote-scheduled phases and a
 // camera-ray / bounce-ray queue split -- none beat whole-warp batches of 32 neighbouring slots.
@@ -358,8 +359,10 @@ namespace rzb
 	// SYNC = true makes the outer loop warp-uniform (one __any_sync per round): in every round the lanes descend
 	// together, then intersect their leaves together, then pop / change level together. SYNC = false lets every lane
 	// run its own rounds. Measured on B200 (1M-triangle scene, ms per pass; profiles/): closest hit 1.38 free-running
-	// vs 1.79 synchronised; any hit 0.75 free-running (triangle code at ~2 of 32 lanes) vs 0.43 synchronised -- so the
-	// closest-hit kernels instantiate SYNC = false and the shadow kernels SYNC = true.
+	// vs 1.79 synchronised. Any hit with the exact box test (80 registers): 0.75 free-running vs 0.43 synchronised;
+	// with the conservative test (64 registers, 8 blocks per SM): 0.25 free-running vs 0.35 synchronised -- every
+	// render kernel now instantiates SYNC = false, only the one-warp k_raycast keeps SYNC = true.
+	// FAST = true selects the conservative box test (slab_hit) and nearer-entry-first child order.
 	template <bool ANY, bool STATS, bool SYNC = ANY, bool FAST = false>
 	__device__ __forceinline__ void trace_ray(const DScene& sc, const bool active, const V3 origin, const V3 direction,
 		const float near_in, const float far_in, Stack& st, ParkedRay& park, TraceCounters& cnt, RayResult& res)
