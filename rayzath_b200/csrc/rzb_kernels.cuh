@@ -302,13 +302,17 @@ namespace rzb
 			analyze_intersection(sc, hinst, tri_bits & kHitTriMask, ha.y, ha.z, (tri_bits & kHitExternalBit) != 0u, s);
 			any_hit = true;
 		}
-		else
-		{
-			// sky sphere coordinates (cuda_world.cuh:121-126)
-			s.u = -(0.5f + atan2f(rd.z, rd.x) * (1.0f / 6.2831853f));
-			s.v = 0.5f + asinf(fminf(fmaxf(rd.y, -1.0f), 1.0f)) * (1.0f / 3.14159265f);
-		}
 		const rzb_material& smat = sc.materials[s.surface_material];
+		if (!(valid && hinst != kNoIndex))
+		{
+			// sky sphere coordinates (cuda_world.cuh:121-126); only read by map fetches
+			const bool mapped = (smat.texture & smat.emission_map & smat.metalness_map & smat.roughness_map) != kNoIndex;
+			if (mapped)
+			{
+				s.u = -(0.5f + atan2f(rd.z, rd.x) * (1.0f / 6.2831853f));
+				s.v = 0.5f + asinf(fminf(fmaxf(rd.y, -1.0f), 1.0f)) * (1.0f / 3.14159265f);
+			}
+		}
 		{
 			const float4 oc = material_opacity_color(sc, smat, s.u, s.v);
 			s.color = f3(oc.x, oc.y, oc.z);
