@@ -2,7 +2,7 @@
 // /root/reference/RayZath by oracle/Makefile) for parity vectors and the CPU baseline.
 //
 // TEST INFRASTRUCTURE ONLY: nothing in the product path links or executes this. It is used by
-// tests/, scripts/make_golden.py and bench.py's reference arm / cpu_baseline leg.
+// tests/, tests/tools/make_golden.py and bench.py's reference arm / cpu_baseline leg.
 //
 // commands
 //   dumpscene <scene.json> <out.rzs>            flattened world (C-ABI arrays) + camera 0 + reference pixel-centre rays

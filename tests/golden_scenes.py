@@ -1,5 +1,5 @@
-"""Small instances of BASELINE.json's configurations shared by scripts/make_golden.py and the tests.
-Changing anything here invalidates tests/golden/*.rzs (regenerate with scripts/make_golden.py)."""
+"""Small instances of BASELINE.json's configurations shared by tests/tools/make_golden.py and the tests.
+Changing anything here invalidates tests/golden/*.rzs (regenerate with tests/tools/make_golden.py)."""
 import hashlib
 
 import numpy as np

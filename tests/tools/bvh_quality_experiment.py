@@ -2,7 +2,7 @@
 """CPU experiment (oracle work counters): nodes visited / triangles tested per ray on the reference's tree versus
 the optional SAH tree, for primary rays and for diffuse bounce rays leaving the primary hit points."""
 import os, sys, time, json
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "oracle"))
 import numpy as np
 import rz_oracle as O

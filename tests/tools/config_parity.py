@@ -2,7 +2,7 @@
 """Converged-image parity of BASELINE.json's configurations at their real resolutions: the B200 path (CPU
 semantics flag) against the reference's own CPU engine (oracle/_ref/rz_ref_tool render) at EQUAL passes, with the
 Monte-Carlo noise floor taken from two independent reference renders. Writes one JSON object per configuration.
-Run on the GPU box:  python scripts/config_parity.py > gpurun_out/config_parity.jsonl"""
+Run on the GPU box:  python tests/tools/config_parity.py > gpurun_out/config_parity.jsonl"""
 import json
 import os
 import sys
@@ -11,7 +11,7 @@ import time
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "oracle"))
 import rz_oracle as O  # noqa: E402

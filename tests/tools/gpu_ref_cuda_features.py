@@ -3,7 +3,7 @@
 (CUDA-engine semantics): mean RGB8 per variant of the materials scene."""
 import json, os, subprocess, sys, tempfile
 import numpy as np
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 from rayzath_b200 import capi, rzs, scenes
 TOOL = os.path.join(ROOT, "oracle", "_ref", "rz_ref_tool_cuda")

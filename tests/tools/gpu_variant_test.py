@@ -1,5 +1,5 @@
 import os, subprocess, sys
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 code = r'''
 import os, sys
 sys.path.insert(0, %r); sys.path.insert(0, os.path.join(%r, "oracle"))
