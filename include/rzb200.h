@@ -197,8 +197,16 @@ enum
 	RZB_FLAG_NONE = 0,
 	RZB_FLAG_CPU_SEMANTICS = 1, /* follow cpu_engine_kernel.cpp where it differs from the CUDA kernel:
 	                               no medium scattering / Beer-Lambert, opaque shadows, texture replaces colour */
-	RZB_FLAG_COUNT_WORK = 2     /* rzb_render counts box tests / triangle tests / shadow rays (rzb_work_counters);
+	RZB_FLAG_COUNT_WORK = 2,    /* rzb_render counts box tests / triangle tests / shadow rays (rzb_work_counters);
 	                               measurement aid, slower kernels */
+	RZB_FLAG_TEMPORAL_REPROJECTION = 4 /* Camera::reproject + spacialReprojection (cuda_camera.cuh:390-426,
+	                               cuda_postprocess_kernel.cu:5-16): when accumulation restarts (rzb_reset after at least one
+	                               rendered pass at the same resolution), the first pass projects every pixel's hit point
+	                               into the camera of the frame that is being replaced and, where that frame's depth agrees
+	                               within 1 %, adds its accumulator value (rgb sum and sample count) times
+	                               rzb_camera::temporal_blend. The reference always does this; here it is opt-in so that
+	                               "reset" alone means a clean restart (the C++ drop-in switches it on). The first frame has
+	                               no history (the reference reads uninitialised memory there). */
 };
 
 /* Closest-hit record (TraversalResult, cuda_render_parts.cuh:946-952), 24 B. */

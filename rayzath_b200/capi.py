@@ -21,6 +21,7 @@ NO_INDEX = 0xFFFFFFFF
 FLAG_NONE = 0
 FLAG_CPU_SEMANTICS = 1
 FLAG_COUNT_WORK = 2
+FLAG_TEMPORAL_REPROJECTION = 4
 SCENE_REFERENCE_TREES, SCENE_OWN_TREES = 0, 1
 MAP_RGBA8, MAP_R8, MAP_R32F = 0, 1, 2
 FILTER_POINT, FILTER_LINEAR = 0, 1

@@ -81,6 +81,12 @@ struct rzb_ctx
 	uint64_t passes = 0, launches = 0;
 	float last_render_ms = 0.0f, last_trace_ms = 0.0f, last_shade_ms = 0.0f, last_shadow_ms = 0.0f;
 	int trace_grid = 0, shadow_grid = 0, rays_grid = 0, any_grid = 0, trace_grid_fast = 0;
+	// temporal reprojection history (RZB_FLAG_TEMPORAL_REPROJECTION)
+	float4* d_prev_accum = nullptr;
+	float* d_prev_depth = nullptr;
+	size_t prev_pixels = 0;
+	bool has_prev = false;
+	rzb_camera frame_cam{}, prev_cam{};
 	bool own_trees = false;        // rzb_scene::flags & RZB_SCENE_OWN_TREES: conservative box tests
 	bool debug_sync = false;       // RZB200_DEBUG_SYNC: synchronise after every kernel of rzb_render and name the one that faulted
 };
@@ -191,6 +197,8 @@ namespace
 		RZB_CUDA(ctx, cudaMemsetAsync(f.accum, 0, n_pixels * 16, ctx->stream));
 		RZB_CUDA(ctx, cudaMemsetAsync(f.depth, 0, n_pixels * 4, ctx->stream));
 		ctx->frame_ready = false;
+		ctx->passes = 0;       // new buffers: nothing rendered, no reprojection history
+		ctx->has_prev = false;
 		return RZB_OK;
 	}
 
@@ -295,6 +303,8 @@ extern "C" void rzb_destroy(rzb_ctx* ctx)
 	for (auto& b : ctx->scratch) if (b.ptr) cudaFree(b.ptr);
 	if (ctx->d_counters) cudaFree(ctx->d_counters);
 	if (ctx->d_work) cudaFree(ctx->d_work);
+	if (ctx->d_prev_accum) cudaFree(ctx->d_prev_accum);
+	if (ctx->d_prev_depth) cudaFree(ctx->d_prev_depth);
 	for (auto& h : ctx->ipc_open) cudaIpcCloseMemHandle(h.second);
 	cudaEventDestroy(ctx->ev_begin);
 	cudaEventDestroy(ctx->ev_end);
@@ -602,6 +612,26 @@ extern "C" int rzb_reset(rzb_ctx* ctx)
 	f.counters = ctx->d_counters;
 	applyRows(ctx);
 	const size_t n_pixels = size_t(ctx->cam.width) * ctx->cam.height;
+	// temporal reprojection: keep the frame that is being replaced (Camera::swapHistoryIdx, cuda_camera.cuh:152)
+	const bool reproject = (ctx->cfg.flags & RZB_FLAG_TEMPORAL_REPROJECTION) != 0u && ctx->cam.temporal_blend > 0.0f;
+	if (reproject && ctx->passes > 0 && ctx->frame_cam.width == ctx->cam.width && ctx->frame_cam.height == ctx->cam.height)
+	{
+		if (ctx->prev_pixels != n_pixels)
+		{
+			if (ctx->d_prev_accum) cudaFree(ctx->d_prev_accum);
+			if (ctx->d_prev_depth) cudaFree(ctx->d_prev_depth);
+			ctx->d_prev_accum = nullptr; ctx->d_prev_depth = nullptr; ctx->prev_pixels = 0;
+			RZB_CUDA(ctx, cudaMalloc(reinterpret_cast<void**>(&ctx->d_prev_accum), n_pixels * 16));
+			RZB_CUDA(ctx, cudaMalloc(reinterpret_cast<void**>(&ctx->d_prev_depth), n_pixels * 4));
+			ctx->prev_pixels = n_pixels;
+		}
+		RZB_CUDA(ctx, cudaMemcpyAsync(ctx->d_prev_accum, f.accum, n_pixels * 16, cudaMemcpyDeviceToDevice, ctx->stream));
+		RZB_CUDA(ctx, cudaMemcpyAsync(ctx->d_prev_depth, f.depth, n_pixels * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+		ctx->prev_cam = ctx->frame_cam;
+		ctx->has_prev = true;
+	}
+	else ctx->has_prev = false;
+	ctx->frame_cam = ctx->cam;
 	RZB_CUDA(ctx, cudaMemsetAsync(f.accum, 0, n_pixels * 16, ctx->stream)); // rows outside the band stay zero
 	RZB_CUDA(ctx, cudaMemsetAsync(f.depth, 0, n_pixels * 4, ctx->stream));
 	RZB_CUDA(ctx, cudaMemsetAsync(ctx->d_counters, 0, 256, ctx->stream));
@@ -639,6 +669,10 @@ extern "C" int rzb_render(rzb_ctx* ctx, uint32_t passes)
 	const bool count = (ctx->cfg.flags & RZB_FLAG_COUNT_WORK) != 0u;
 	const bool fast = ctx->own_trees;
 	f.work = ctx->d_work;
+	f.prev_accum = ctx->d_prev_accum;
+	f.prev_depth = ctx->d_prev_depth;
+	f.prev_cam = makeDeviceCamera(ctx->prev_cam);
+	f.reproject_blend = ctx->has_prev ? ctx->cam.temporal_blend : 0.0f;
 	// per-stage device timing: up to 256 passes of this call are bracketed by events (4 per sampled pass)
 	const uint32_t stride = (passes + 255u) / 256u;
 	const uint32_t n_sampled = passes ? (passes + stride - 1u) / stride : 0u;
@@ -664,6 +698,11 @@ extern "C" int rzb_render(rzb_ctx* ctx, uint32_t passes)
 		{
 			const cudaError_t e = cudaStreamSynchronize(ctx->stream);
 			if (e != cudaSuccess) return cudaFail(ctx, e, ("k_trace_paths, pass " + std::to_string(ctx->passes)).c_str());
+		}
+		if (f.pass_index == 0u && f.reproject_blend > 0.0f)
+		{
+			k_reproject<<<(f.slot_end - f.slot_begin + 127) / 128, 128, 0, ctx->stream>>>(f);
+			ctx->launches += 1;
 		}
 		if (timed) cudaEventRecord(ev[1], ctx->stream);
 		k_shade<<<(f.slot_end - f.slot_begin + 127) / 128, 128, 0, ctx->stream>>>(ctx->sc, f);

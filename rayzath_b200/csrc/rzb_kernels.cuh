@@ -49,6 +49,11 @@ namespace rzb
 		unsigned long long* work; // RZB_FLAG_COUNT_WORK: [0..3] closest top/inst/mesh/tri, [4..7] shadow, [8] shadow rays
 		uint32_t shadow_capacity;
 		uint32_t pass_index;
+		// temporal reprojection (RZB_FLAG_TEMPORAL_REPROJECTION): the frame that the current one replaces
+		const float4* prev_accum;
+		const float* prev_depth;
+		DCamera prev_cam;
+		float reproject_blend; // 0 = off
 
 		uint32_t max_depth, direct_samples, spot_samples;
 		uint64_t seed;
@@ -466,6 +471,38 @@ namespace rzb
 			f.st_d[slot] = make_float4(next_d.x, next_d.y, next_d.z, thr.x);
 			f.st_c[slot] = make_float2(thr.y, thr.z);
 		}
+	}
+
+	// ---------------------------------------------------------------- k_reproject
+	// Camera::reproject + spacialReprojection (cuda_camera.cuh:390-426, cuda_postprocess_kernel.cu:5-16). Runs once per
+	// restarted frame, between k_trace_paths and k_shade of pass 0 (the slot still holds the first ray and its hit
+	// distance): the hit point is projected into the camera of the frame being replaced and, where that frame's depth
+	// agrees within 1 %, its accumulator value times temporal_blend is added.
+	__global__ void __launch_bounds__(128) k_reproject(DFrame f)
+	{
+		const uint32_t slot = f.slot_begin + blockIdx.x * blockDim.x + threadIdx.x;
+		uint32_t x = 0, y = 0;
+		if (slot >= f.slot_end || !slot_to_pixel(f, slot, x, y)) return;
+		const float4 so = f.st_o[slot], sd = f.st_d[slot];
+		const float far_ = f.hit_a[slot].x;
+		const float3 sp = f3(so.x, so.y, so.z) + f3(sd.x, sd.y, sd.z) * far_;
+		const float3 rel = sp - f3(f.prev_cam.px, f.prev_cam.py, f.prev_cam.pz);
+		const float lx = f.prev_cam.xx * rel.x + f.prev_cam.xy * rel.y + f.prev_cam.xz * rel.z;
+		const float ly = f.prev_cam.yx * rel.x + f.prev_cam.yy * rel.y + f.prev_cam.yz * rel.z;
+		const float lz = f.prev_cam.zx * rel.x + f.prev_cam.zy * rel.y + f.prev_cam.zz * rel.z;
+		if (!(lz > 0.0f)) return; // behind the previous camera
+		const float fx = ((lx / lz) / f.prev_cam.tana + 0.5f) * float(f.cam.width);
+		const float fy = ((ly / lz) / (-f.prev_cam.tana / f.cam.aspect) + 0.5f) * float(f.cam.height);
+		if (!(fx >= 0.0f && fx < float(f.cam.width) && fy >= 0.0f && fy < float(f.cam.height))) return;
+		const size_t q = size_t(uint32_t(fy)) * f.cam.width + uint32_t(fx);
+		const float point_dist = length(rel);
+		if (!(fabsf(point_dist - f.prev_depth[q]) < 0.01f * point_dist)) return;
+		const float4 h = f.prev_accum[q];
+		const size_t p = size_t(y) * f.cam.width + x;
+		float4 acc = f.accum[p];
+		acc.x += h.x * f.reproject_blend; acc.y += h.y * f.reproject_blend;
+		acc.z += h.z * f.reproject_blend; acc.w += h.w * f.reproject_blend;
+		f.accum[p] = acc;
 	}
 
 	// ---------------------------------------------------------------- k_trace_shadow

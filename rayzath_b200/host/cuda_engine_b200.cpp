@@ -139,6 +139,7 @@ namespace RayZath::Cuda
 					if (!cs.scene_current) check(c, rzb_set_scene(c, &scene), "rzb_set_scene");
 					// one disjoint sample stream per device
 					rzb_config cfg = rzb_host::flattenConfig(config, m_seed + 0x9E3779B97F4A7C15ull * (uint64_t(ci) * 64 + d));
+					cfg.flags |= RZB_FLAG_TEMPORAL_REPROJECTION; // as the reference: every restart blends the replaced frame in
 					check(c, rzb_set_config(c, &cfg), "rzb_set_config");
 					if (camera_update)
 					{

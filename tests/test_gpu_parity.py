@@ -500,3 +500,60 @@ def test_non_finite_samples_are_dropped():
     assert np.isfinite(acc).all()
     assert int(wc["invalid_rays"]) >= 1
     assert acc[929, :, 3].min() > 0 and (acc[:929] == 0).all() and (acc[930:] == 0).all()
+
+
+def test_temporal_reprojection(worlds, flats):
+    """Camera::reproject (cuda_camera.cuh:390-426) behind RZB_FLAG_TEMPORAL_REPROJECTION: after a restart the first pass
+    adds temporal_blend x the replaced frame's accumulator value at the pixel the hit point projects to (depth within
+    1 %). The RNG is counter-based, so the same restart without the flag isolates the history term exactly."""
+    w = worlds["materials"]
+    cam = w.camera_struct().copy()
+    h, wd = int(cam[0]["height"]), int(cam[0]["width"])
+
+    def frame_pair(cam2, flags):
+        with capi.Context(0) as c:
+            c.set_scene(flats["materials"])
+            c.set_camera(cam)
+            c.set_config(max_depth=6, flags=flags, seed=31)
+            c.reset()
+            c.render(24)
+            a = c.read_accum()
+            c.set_camera(cam2)
+            c.reset()
+            c.render(1)
+            return a, c.read_accum()
+
+    a, with_history = frame_pair(cam, capi.FLAG_TEMPORAL_REPROJECTION)
+    a2, clean = frame_pair(cam, capi.FLAG_NONE)
+    assert np.allclose(a, a2, rtol=1e-5, atol=1e-5)  # equal up to the order of the shadow kernel's atomic adds
+    d = with_history - clean
+    blend = np.float32(cam[0]["temporal_blend"])
+    assert blend > 0 and (d >= -1e-3).all()
+    assert (d[..., 3] > 0).mean() > 0.9
+    assert abs(d[..., :3].sum() / (blend * a[..., :3].sum()) - 1.0) < 0.1
+    # every history term is blend x the old value of a pixel at most one pixel away (anti-aliasing jitter)
+    pad = np.pad(a * blend, ((1, 1), (1, 1), (0, 0)))
+    neigh = np.stack([pad[1 + dy:1 + dy + h, 1 + dx:1 + dx + wd] for dy in (-1, 0, 1) for dx in (-1, 0, 1)])
+    hit = d[..., 3] > 0
+    match = (np.isclose(neigh[..., 3], d[None, ..., 3], rtol=1e-5, atol=1e-6) &
+             np.isclose(neigh[..., 0], d[None, ..., 0], rtol=1e-3, atol=1e-3)).any(axis=0)
+    assert match[hit].mean() > 0.999, match[hit].mean()
+
+    # a camera looking the other way sees nothing the old one saw; blend 0 switches the term off
+    away = cam.copy()
+    away[0]["axis_x"] = -cam[0]["axis_x"]
+    away[0]["axis_z"] = -cam[0]["axis_z"]
+    _, b1 = frame_pair(away, capi.FLAG_TEMPORAL_REPROJECTION)
+    _, b0 = frame_pair(away, capi.FLAG_NONE)
+    assert np.allclose(b1, b0, rtol=1e-5, atol=1e-5)
+    off = cam.copy()
+    off[0]["temporal_blend"] = 0.0
+    with capi.Context(0) as c:
+        c.set_scene(flats["materials"])
+        c.set_camera(off)
+        c.set_config(max_depth=6, flags=capi.FLAG_TEMPORAL_REPROJECTION, seed=31)
+        c.reset()
+        c.render(24)
+        c.reset()
+        c.render(1)
+        assert np.allclose(c.read_accum(), clean, rtol=1e-5, atol=1e-5)
