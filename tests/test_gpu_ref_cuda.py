@@ -32,6 +32,30 @@ VARIANTS = {
 W, H, PASSES, DEPTH = 320, 180, 256, 16
 
 
+def _maps_world(linear):
+    """Config-3 geometry in small: texture x base colour, normal map in tangent space, roughness map, DoF camera."""
+    w = scenes.heightfield_scene(resolution=(W, H), nx=120, nz=120, map_size=128)
+    if linear:
+        for kind in w.maps:
+            for m in w.maps[kind]:
+                m.filter = capi.FILTER_LINEAR
+    return w
+
+
+def _instancing_world():
+    """Config-4 geometry in small: rotated, non-uniformly scaled instances of one mesh (normal transformation)."""
+    w = scenes.instancing_scene(resolution=(W, H), n_instances=16, nx=24, nz=24)
+    w.cameras[0].aperture = 0.05  # the bench camera's pinhole aperture tone-maps to black
+    return w
+
+
+OTHER_SCENES = {
+    "heightfield_maps_point": lambda: _maps_world(False),
+    "heightfield_maps_linear": lambda: _maps_world(True),
+    "instancing": _instancing_world,
+}
+
+
 def _variant(keep, lights):
     w = scenes.materials_scene(resolution=(W, H), res=24)
     w.instances = [i for i in w.instances if i.name in keep]
@@ -50,12 +74,15 @@ def _blocks(img, k=16):
 
 
 @pytest.mark.skipif(not os.path.exists(TOOL), reason="oracle/_ref/rz_ref_tool_cuda not built (make -C oracle ref_cuda)")
-@pytest.mark.parametrize("name", list(VARIANTS))
+@pytest.mark.parametrize("name", list(VARIANTS) + list(OTHER_SCENES))
 def test_image_vs_reference_cuda_engine(name, tmp_path):
     """Tolerance (stated): image mean of the tone-mapped RGB within 1 %, RMS difference of 16x16-block means within
     2 % of the image mean (both renders: 256 passes, depth 16)."""
-    keep, lights = VARIANTS[name]
-    w = _variant(keep, lights)
+    if name in VARIANTS:
+        keep, lights = VARIANTS[name]
+        w = _variant(keep, lights)
+    else:
+        w = OTHER_SCENES[name]()
     path = w.save_reference(str(tmp_path / name))
     out = str(tmp_path / "cuda.rzs")
     r = subprocess.run([TOOL, "rendercuda", path, str(PASSES), "1", out, str(DEPTH), "1", "1", "1"],
