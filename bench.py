@@ -11,7 +11,8 @@ One JSON line is printed by rank 0:
   e2e        the same metric through the reference-facing boundary with HOST buffers: every e2e step is one
              Engine::renderWorld-equivalent frame = rzb_set_scene (host arrays -> device) + rzb_set_camera + rzb_reset
              + rzb_render(rpp passes) + rzb_resolve (tone map, RGBA8 + depth -> pinned host buffers)
-  roofline   HBM roofline of the dominant kernel (k_trace_paths) from ALGORITHMIC bytes
+  roofline   HBM roofline from ALGORITHMIC bytes of both traversal kernels; the one with the larger share of
+             the step is reported at the top level
   cpu_baseline  the reference's own CPU engine (oracle/_ref/rz_ref_tool, built from /root/reference) on this box's
              host cores on a bounded sample of the same workload
 `--impl reference` times that CPU engine alone and prints the same line with "impl": "reference".
@@ -211,7 +212,9 @@ def main():
         r = reference_run(args.workload, args.steps, args.warmup)
         line = dict(base)
         line.update({"impl": "reference", "value": r["value"], "ms_per_step": r["ms_per_step"],
-                     "config": {"workload": args.workload, "max_depth": MAX_DEPTH, "light_samples": [1, 1]},
+                     "config": {"workload": args.workload, "resolution": list(WORKLOADS[args.workload][1]["resolution"]),
+                                "max_depth": MAX_DEPTH, "light_samples": [1, 1],
+                                "bvh": "reference trees (built by the reference itself)", "sharding": "host threads"},
                      "cpu_baseline": {"value": r["value"], "unit": "Mrays/s", "cores": r["cores"], "kind": r["kind"],
                                       "sample": r["sample"]},
                      "e2e": {"value": r["value"], "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
