@@ -288,6 +288,17 @@ int rzb_render(rzb_ctx* ctx, uint32_t passes);
 int rzb_resolve(rzb_ctx* ctx, uint8_t* rgba8, float* depth, uint64_t* ray_count);
 /* raw float accumulator (rgb sum, alpha = completed paths), width*height*4 floats, HOST buffer. */
 int rzb_read_accum(rzb_ctx* ctx, float* rgba_f32);
+/* Pipelined hosts (the reference's sync == false: the caller gets the PREVIOUS frame while this one renders,
+ * cuda_engine_core.cu:111-121). rzb_resolve_async enqueues the tone map, the copies into the caller's PINNED buffers
+ * (rzb_host_alloc; either may be NULL) and the ray-cast pick behind the rendering already enqueued on the context's
+ * stream and returns at once; `slot` (0 or 1) names the completion event, so a host can have one frame in flight while
+ * it reads the other. ray_count is known on the host and returned immediately. rzb_resolve_wait blocks until that
+ * slot's resolve has finished (later work keeps running) and hands back its pick (RZB_NO_INDEX = nothing hit). */
+int rzb_resolve_async(rzb_ctx* ctx, uint32_t slot, uint8_t* rgba8_pinned, float* depth_pinned, uint64_t* ray_count);
+int rzb_resolve_wait(rzb_ctx* ctx, uint32_t slot, uint32_t* instance, uint32_t* material_slot);
+/* page-locked host memory for the asynchronous copies */
+int rzb_host_alloc(size_t bytes, void** out);
+int rzb_host_free(void* p);
 /* device pointer of the linear float4 accumulator (for NCCL reduction by the caller) and its size. */
 int rzb_accum_device_ptr(rzb_ctx* ctx, void** device_ptr, size_t* bytes);
 /* add `count` float4 pixels from a DEVICE buffer into the accumulator (after a reduce-scatter or P2P read). */

@@ -122,6 +122,10 @@ SYMBOLS = {
     "rzb_trace_closest_device_counted": (C.c_int, [_P, _P, _P, C.c_uint32, _P]),
     "rzb_trace_any": (C.c_int, [_P, _P, _P, _P, C.c_uint32, _P]),
     "rzb_generate_camera_rays": (C.c_int, [_P, _P, _P, _P]),
+    "rzb_resolve_async": (C.c_int, [_P, C.c_uint32, _P, _P, C.POINTER(C.c_uint64)]),
+    "rzb_resolve_wait": (C.c_int, [_P, C.c_uint32, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),
+    "rzb_host_alloc": (C.c_int, [C.c_size_t, C.POINTER(C.c_void_p)]),
+    "rzb_host_free": (C.c_int, [_P]),
     "rzb_build_mesh_bvh": (C.c_int, [_P, C.c_uint32, _P, C.c_uint32, _P, C.c_uint32, C.POINTER(C.c_uint32), _P]),
     "rzb_build_mesh_bvh_sah": (C.c_int, [_P, C.c_uint32, _P, C.c_uint32, C.c_uint32, _P, C.c_uint32, C.POINTER(C.c_uint32), _P]),
     "rzb_build_instance_bvh": (C.c_int, [_P, C.c_uint32, _P, C.c_uint32, C.POINTER(C.c_uint32), _P]),
@@ -162,6 +166,32 @@ def _ptr(a: Optional[np.ndarray]):
 
 def _c(a, dtype) -> np.ndarray:
     return np.ascontiguousarray(a, dtype=dtype)
+
+
+class PinnedArray:
+    """numpy view of page-locked host memory from rzb_host_alloc (for rzb_resolve_async); free() or use as a context."""
+
+    def __init__(self, shape, dtype):
+        dtype = np.dtype(dtype)
+        nbytes = int(np.prod(shape)) * dtype.itemsize
+        p = C.c_void_p(0)
+        rc = lib().rzb_host_alloc(nbytes, C.byref(p))
+        if rc:
+            raise RzbError(rc, "rzb_host_alloc failed")
+        self._p = p
+        self.array = np.frombuffer((C.c_uint8 * nbytes).from_address(p.value), dtype=dtype).reshape(shape)
+
+    def free(self):
+        if self._p is not None:
+            self.array = None
+            lib().rzb_host_free(self._p)
+            self._p = None
+
+    def __enter__(self):
+        return self.array
+
+    def __exit__(self, *exc):
+        self.free()
 
 
 # ---------------------------------------------------------------- host utilities (no device needed)
@@ -372,6 +402,19 @@ class Context:
         self._check(self._l.rzb_resolve(self._h, rgba8.ctypes.data, _ptr(depth), C.byref(rays)))
         assert rgba8.size == n * 4
         return rgba8, depth, rays.value
+
+    def resolve_async(self, slot: int, rgba8_pinned: Optional[np.ndarray], depth_pinned: Optional[np.ndarray] = None) -> int:
+        """rzb_resolve_async: enqueue tone map + copies into PINNED arrays (pinned_array) + the ray-cast pick; returns the
+        ray count at once. The arrays are valid after resolve_wait(slot)."""
+        rays = C.c_uint64(0)
+        self._check(self._l.rzb_resolve_async(self._h, int(slot), _ptr(rgba8_pinned), _ptr(depth_pinned), C.byref(rays)))
+        return rays.value
+
+    def resolve_wait(self, slot: int):
+        """rzb_resolve_wait: block until the asynchronous resolve of `slot` is done; returns its (instance, material slot) pick."""
+        inst, mat = C.c_uint32(0), C.c_uint32(0)
+        self._check(self._l.rzb_resolve_wait(self._h, int(slot), C.byref(inst), C.byref(mat)))
+        return inst.value, mat.value
 
     def resolve_peers(self, peers, want_depth=False):
         rgba8 = np.empty((self.height, self.width, 4), dtype=np.uint8)

@@ -47,6 +47,8 @@ struct rzb_ctx
 	cudaStream_t stream = nullptr;     // the stream everything runs on (own_stream unless rzb_set_stream gave another)
 	cudaStream_t own_stream = nullptr;
 	cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
+	cudaEvent_t ev_resolve[2] = {nullptr, nullptr}; // rzb_resolve_async completion, per slot
+	uint32_t* h_pick = nullptr;                     // pinned: ray-cast pick of the two slots
 	std::vector<cudaEvent_t> ev_stage; // 4 per sampled pass of the last rzb_render call
 	uint32_t sampled_passes = 0;
 	bool last_had_shadow = false;
@@ -277,6 +279,9 @@ extern "C" int rzb_create(int device, rzb_ctx** out)
 	ctx->stream = ctx->own_stream;
 	cudaEventCreate(&ctx->ev_begin);
 	cudaEventCreate(&ctx->ev_end);
+	cudaEventCreateWithFlags(&ctx->ev_resolve[0], cudaEventDisableTiming);
+	cudaEventCreateWithFlags(&ctx->ev_resolve[1], cudaEventDisableTiming);
+	if (cudaMallocHost(reinterpret_cast<void**>(&ctx->h_pick), 16) != cudaSuccess) ctx->h_pick = nullptr;
 	if ((e = cudaMalloc(reinterpret_cast<void**>(&ctx->d_work), 128)) != cudaSuccess) { delete ctx; return cudaFail(nullptr, e, "cudaMalloc(work)"); }
 	cudaMemsetAsync(ctx->d_work, 0, 128, ctx->stream);
 	if ((e = cudaMalloc(reinterpret_cast<void**>(&ctx->d_counters), 256)) != cudaSuccess) { delete ctx; return cudaFail(nullptr, e, "cudaMalloc(counters)"); }
@@ -308,6 +313,9 @@ extern "C" void rzb_destroy(rzb_ctx* ctx)
 	for (auto& h : ctx->ipc_open) cudaIpcCloseMemHandle(h.second);
 	cudaEventDestroy(ctx->ev_begin);
 	cudaEventDestroy(ctx->ev_end);
+	cudaEventDestroy(ctx->ev_resolve[0]);
+	cudaEventDestroy(ctx->ev_resolve[1]);
+	if (ctx->h_pick) cudaFreeHost(ctx->h_pick);
 	for (auto& ev : ctx->ev_stage) cudaEventDestroy(ev);
 	cudaStreamDestroy(ctx->own_stream);
 	delete ctx;
@@ -747,7 +755,7 @@ extern "C" int rzb_synchronize(rzb_ctx* ctx)
 
 namespace
 {
-	int tonemapAndCopy(rzb_ctx* ctx, const PeerList& peers, uint8_t* rgba8, float* depth)
+	int tonemapAndCopy(rzb_ctx* ctx, const PeerList& peers, uint8_t* rgba8, float* depth, bool sync = true)
 	{
 		const uint32_t n = ctx->cam.width * ctx->cam.height;
 		if (rgba8)
@@ -760,7 +768,7 @@ namespace
 			RZB_CUDA(ctx, cudaMemcpyAsync(rgba8, ctx->d_rgba, size_t(n) * 4, cudaMemcpyDeviceToHost, ctx->stream));
 		}
 		if (depth) RZB_CUDA(ctx, cudaMemcpyAsync(depth, ctx->frame.depth, size_t(n) * 4, cudaMemcpyDeviceToHost, ctx->stream));
-		RZB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+		if (sync) RZB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
 		return RZB_OK;
 	}
 }
@@ -775,6 +783,50 @@ extern "C" int rzb_resolve(rzb_ctx* ctx, uint8_t* rgba8, float* depth, uint64_t*
 	if (rc) return rc;
 	if (ray_count) *ray_count = ctx->passes * bandPixels(ctx);
 	return RZB_OK;
+}
+
+extern "C" int rzb_resolve_async(rzb_ctx* ctx, uint32_t slot, uint8_t* rgba8_pinned, float* depth_pinned, uint64_t* ray_count)
+{
+	if (!ctx || slot > 1u) return fail(ctx, RZB_ERR_INVALID, "rzb_resolve_async: bad argument");
+	if (!ctx->has_camera || !ctx->has_scene) return fail(ctx, RZB_ERR_STATE, "rzb_resolve_async: scene and camera must be set first");
+	DeviceGuard guard(ctx->device);
+	PeerList peers{};
+	const int rc = tonemapAndCopy(ctx, peers, rgba8_pinned, depth_pinned, false);
+	if (rc) return rc;
+	// the ray-cast pick travels with the frame (rayCast kernel, cuda_render_kernel.cu:130-144)
+	const uint32_t px = std::min(ctx->cam.raycast_pixel[0], ctx->cam.width - 1u);
+	const uint32_t py = std::min(ctx->cam.raycast_pixel[1], ctx->cam.height - 1u);
+	uint32_t* d_out = ctx->d_counters + 44 + 2 * slot;
+	k_raycast<<<1, 32, 0, ctx->stream>>>(ctx->sc, makeDeviceCamera(ctx->cam), ctx->frame.depth, px, py, d_out);
+	ctx->launches += 1;
+	RZB_CUDA(ctx, cudaGetLastError());
+	RZB_CUDA(ctx, cudaMemcpyAsync(ctx->h_pick + 2 * slot, d_out, 8, cudaMemcpyDeviceToHost, ctx->stream));
+	RZB_CUDA(ctx, cudaEventRecord(ctx->ev_resolve[slot], ctx->stream));
+	if (ray_count) *ray_count = ctx->passes * bandPixels(ctx);
+	return RZB_OK;
+}
+
+extern "C" int rzb_resolve_wait(rzb_ctx* ctx, uint32_t slot, uint32_t* instance, uint32_t* material_slot)
+{
+	if (!ctx || slot > 1u) return fail(ctx, RZB_ERR_INVALID, "rzb_resolve_wait: bad argument");
+	DeviceGuard guard(ctx->device);
+	RZB_CUDA(ctx, cudaEventSynchronize(ctx->ev_resolve[slot]));
+	if (instance) *instance = ctx->h_pick[2 * slot];
+	if (material_slot) *material_slot = ctx->h_pick[2 * slot + 1];
+	return RZB_OK;
+}
+
+extern "C" int rzb_host_alloc(size_t bytes, void** out)
+{
+	if (!out || bytes == 0) return RZB_ERR_INVALID;
+	*out = nullptr;
+	return cudaMallocHost(out, bytes) == cudaSuccess ? RZB_OK : RZB_ERR_NOMEM;
+}
+
+extern "C" int rzb_host_free(void* p)
+{
+	if (!p) return RZB_OK;
+	return cudaFreeHost(p) == cudaSuccess ? RZB_OK : RZB_ERR_CUDA;
 }
 
 extern "C" int rzb_resolve_peers(rzb_ctx* ctx, rzb_ctx* const* peers_in, uint32_t n_peers,

@@ -14,8 +14,8 @@
 // Behaviour kept: dirty-flag protocol (world modified -> re-mirror, camera modified -> restart accumulation,
 // flags cleared afterwards), `rpp` passes per call, results written to Camera::m_image_buffer / m_depth_buffer /
 // m_ray_count / m_raycasted_*, errors as RayZath::Cuda::Exception, CUDA init failure -> the facade falls back to
-// the CPU engine (rayzath.cpp:21-28). Behaviour changed (documented in INTEGRATION.md): the call is synchronous
-// for both values of `sync` (the reference pipelines one frame when sync == false); the per-call random seeds of
+// the CPU engine (rayzath.cpp:21-28); sync == false pipelines one frame as the reference does (the caller gets the
+// previous frame while this one renders; single device only). Behaviour changed: the per-call random seeds of
 // cuda_kernel_data.cu:10-18 become one seed per engine (RZB200_SEED or std::random_device) + the pass counter.
 // RZB200_BVH=sah replaces the host World's triangle trees by this repo's SAH trees (RZB_SCENE_OWN_TREES; hit records
 // equal except exact-distance ties). Multi-GPU: RZB200_DEVICES="0,1,..." renders one disjoint sample stream per listed device and sums the
@@ -45,6 +45,13 @@ namespace RayZath::Cuda
 			bool scene_current = false;
 			std::vector<uint8_t> rgba;
 			std::vector<float> depth;
+			// sync == false: one frame in flight (pinned double buffer), the caller gets the previous one
+			void* pin_rgba[2] = {nullptr, nullptr};
+			void* pin_depth[2] = {nullptr, nullptr};
+			size_t pin_pixels = 0;
+			int pending = -1;          // slot whose asynchronous resolve has not been handed back yet
+			uint64_t pending_rays = 0;
+			uint64_t frame_no = 0;
 		};
 		std::mutex m_mtx;
 		std::vector<int> m_devices;
@@ -93,10 +100,13 @@ namespace RayZath::Cuda
 			if (std::getenv("RZB200_VERBOSE") && !m_timings.empty())
 				std::fprintf(stderr, "[rzb200] %zu device(s), seed %llu\n%s", m_devices.size(), (unsigned long long)m_seed, m_timings.c_str());
 			for (auto& [idx, cam] : m_cameras)
-				for (rzb_ctx* c : cam.ctxs) rzb_destroy(c);
+			{
+				for (rzb_ctx* c : cam.ctxs) rzb_destroy(c); // synchronises the stream: nothing is in flight afterwards
+				for (int k = 0; k < 2; ++k) { rzb_host_free(cam.pin_rgba[k]); rzb_host_free(cam.pin_depth[k]); }
+			}
 		}
 
-		void renderWorld(RZ::World& hWorld, const RZ::RenderConfig& config)
+		void renderWorld(RZ::World& hWorld, const RZ::RenderConfig& config, const bool sync)
 		{
 			std::lock_guard<std::mutex> lg(m_mtx);
 
@@ -157,18 +167,58 @@ namespace RayZath::Cuda
 
 				// copy-back (CopyRenderToHost, cuda_engine_core.cu:163-240)
 				const size_t n = size_t(cs.width) * cs.height;
-				cs.rgba.resize(n * 4);
-				cs.depth.resize(n);
 				uint64_t rays = 0;
 				rzb_ctx* root = cs.ctxs[0];
-				check(root, rzb_resolve_peers(root, cs.ctxs.data() + 1, uint32_t(cs.ctxs.size() - 1), cs.rgba.data(),
-					cs.depth.data(), &rays), "rzb_resolve_peers");
-				hCamera->m_ray_count = rays;
-				hCamera->m_image_buffer.CopyFromMemory(cs.rgba.data(), n * 4, 0, 0);
-				hCamera->m_depth_buffer.CopyFromMemory(cs.depth.data(), n * sizeof(float), 0, 0);
-
 				uint32_t inst = RZB_NO_INDEX, slot = RZB_NO_INDEX;
-				check(root, rzb_raycast(root, &inst, &slot), "rzb_raycast");
+				const uint8_t* rgba_src = nullptr;
+				const float* depth_src = nullptr;
+				if (sync || cs.ctxs.size() > 1)
+				{
+					// synchronous: finish and hand back THIS frame (also drains a frame still in flight)
+					cs.pending = -1;
+					cs.rgba.resize(n * 4);
+					cs.depth.resize(n);
+					check(root, rzb_resolve_peers(root, cs.ctxs.data() + 1, uint32_t(cs.ctxs.size() - 1), cs.rgba.data(),
+						cs.depth.data(), &rays), "rzb_resolve_peers");
+					check(root, rzb_raycast(root, &inst, &slot), "rzb_raycast");
+					rgba_src = cs.rgba.data();
+					depth_src = cs.depth.data();
+				}
+				else
+				{
+					// pipelined, as the reference with sync == false (cuda_engine_core.cu:111-121): this frame's tone map,
+					// copies and pick are enqueued behind its passes; the caller gets the previous frame, whose copies
+					// finished while the host was busy. The very first frame has no predecessor and is waited for.
+					if (cs.pin_pixels != n)
+					{
+						if (cs.pending >= 0) check(root, rzb_resolve_wait(root, uint32_t(cs.pending), nullptr, nullptr), "rzb_resolve_wait");
+						cs.pending = -1;
+						for (int k = 0; k < 2; ++k)
+						{
+							rzb_host_free(cs.pin_rgba[k]); rzb_host_free(cs.pin_depth[k]);
+							cs.pin_rgba[k] = cs.pin_depth[k] = nullptr;
+							if (rzb_host_alloc(n * 4, &cs.pin_rgba[k]) != RZB_OK || rzb_host_alloc(n * 4, &cs.pin_depth[k]) != RZB_OK)
+								fail(root, "rzb_host_alloc");
+						}
+						cs.pin_pixels = n;
+					}
+					const int k = int(cs.frame_no & 1u);
+					uint64_t rays_k = 0;
+					check(root, rzb_resolve_async(root, uint32_t(k), static_cast<uint8_t*>(cs.pin_rgba[k]),
+						static_cast<float*>(cs.pin_depth[k]), &rays_k), "rzb_resolve_async");
+					const int give = cs.pending >= 0 ? cs.pending : k;
+					check(root, rzb_resolve_wait(root, uint32_t(give), &inst, &slot), "rzb_resolve_wait");
+					rays = cs.pending >= 0 ? cs.pending_rays : rays_k;
+					rgba_src = static_cast<const uint8_t*>(cs.pin_rgba[give]);
+					depth_src = static_cast<const float*>(cs.pin_depth[give]);
+					cs.pending = k;
+					cs.pending_rays = rays_k;
+					++cs.frame_no;
+				}
+				hCamera->m_ray_count = rays;
+				hCamera->m_image_buffer.CopyFromMemory(rgba_src, n * 4, 0, 0);
+				hCamera->m_depth_buffer.CopyFromMemory(depth_src, n * sizeof(float), 0, 0);
+
 				auto& hInstances = hWorld.container<RZ::ObjectType::Instance>();
 				if (inst < hInstances.count() && hInstances[inst])
 				{
@@ -221,9 +271,9 @@ namespace RayZath::Cuda
 	Engine::~Engine() = default;
 
 	void Engine::renderWorld(RayZath::Engine::World& hWorld, const RayZath::Engine::RenderConfig& render_config,
-		const bool /*block*/, const bool /*sync*/)
+		const bool /*block*/, const bool sync)
 	{
-		m_engine_core->renderWorld(hWorld, render_config);
+		m_engine_core->renderWorld(hWorld, render_config, sync);
 		m_timing_string = m_engine_core->timings();
 	}
 	std::string Engine::timingsString() { return m_timing_string; }

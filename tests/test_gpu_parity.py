@@ -557,3 +557,32 @@ def test_temporal_reprojection(worlds, flats):
         c.reset()
         c.render(1)
         assert np.allclose(c.read_accum(), clean, rtol=1e-5, atol=1e-5)
+
+
+def test_async_resolve_matches_resolve_and_overlaps(contexts, worlds):
+    """rzb_resolve_async / rzb_resolve_wait (the reference's sync == false pipeline): same image, depth, ray count and
+    pick as the blocking calls; a second frame can be enqueued while the first slot is still being read."""
+    c = contexts["materials"]
+    cam = worlds["materials"].camera_struct()[0]
+    h, w = int(cam["height"]), int(cam["width"])
+    c.set_config(max_depth=6, seed=9)
+    c.reset()
+    c.render(8)
+    rgba, depth, rays = c.resolve(want_depth=True)
+    pick = c.raycast()
+    bufs = [(capi.PinnedArray((h, w, 4), np.uint8), capi.PinnedArray((h, w), np.float32)) for _ in range(2)]
+    try:
+        rays0 = c.resolve_async(0, bufs[0][0].array, bufs[0][1].array)
+        c.render(8)                                   # frame 2 is enqueued behind the resolve of frame 1
+        rays1 = c.resolve_async(1, bufs[1][0].array, bufs[1][1].array)
+        assert c.resolve_wait(0) == pick
+        assert rays0 == rays and rays1 == 2 * rays
+        assert np.array_equal(bufs[0][0].array, rgba) and np.array_equal(bufs[0][1].array, depth)
+        c.resolve_wait(1)
+        rgba2, depth2, rays2 = c.resolve(want_depth=True)
+        assert rays2 == rays1 and np.array_equal(bufs[1][0].array, rgba2) and np.array_equal(bufs[1][1].array, depth2)
+    finally:
+        for a, b in bufs:
+            a.free()
+            b.free()
+        c.set_config()
