@@ -162,6 +162,12 @@ enum
 {
 	RZB_SCENE_REFERENCE_TREES = 0, /* the trees are the reference's own (rzb_build_mesh_bvh or the host World's): every box
 	                                  test decides exactly as the reference's arithmetic does -- the parity mode */
+	RZB_SCENE_KEEP_GEOMETRY = 2,   /* incremental update: meshes, mesh_nodes, triangles and tri_host_index
+	                                  are unchanged since the last full rzb_set_scene on this context -- their fields are
+	                                  ignored (may be NULL / 0) and the device copies are reused; instances, the instance tree,
+	                                  materials, maps and lights are replaced. Instances may only reference the meshes of that
+	                                  upload. Fails with RZB_ERR_STATE when there is no previous full upload or the instance
+	                                  tree outgrew the space reserved for it (then upload the whole scene). */
 	RZB_SCENE_OWN_TREES = 1        /* the mesh trees come from another builder (rzb_build_mesh_bvh_sah): nothing has to
 	                                  follow the reference's box decisions, so the kernels use a cheaper conservative
 	                                  box test; closest-hit records still equal the reference's except on exact ties */

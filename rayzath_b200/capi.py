@@ -22,7 +22,7 @@ FLAG_NONE = 0
 FLAG_CPU_SEMANTICS = 1
 FLAG_COUNT_WORK = 2
 FLAG_TEMPORAL_REPROJECTION = 4
-SCENE_REFERENCE_TREES, SCENE_OWN_TREES = 0, 1
+SCENE_REFERENCE_TREES, SCENE_OWN_TREES, SCENE_KEEP_GEOMETRY = 0, 1, 2
 MAP_RGBA8, MAP_R8, MAP_R32F = 0, 1, 2
 FILTER_POINT, FILTER_LINEAR = 0, 1
 ADDRESS_WRAP, ADDRESS_CLAMP, ADDRESS_MIRROR, ADDRESS_BORDER = 0, 1, 2, 3
@@ -361,6 +361,14 @@ class Context:
         s.flags = int(np.asarray(scene.get("scene_flags", 0)).reshape(-1)[0])
         self._check(self._l.rzb_set_scene(self._h, C.byref(s)))
         self._keep = None
+
+    def update_scene(self, scene: Dict[str, np.ndarray]):
+        """Incremental update (RZB_SCENE_KEEP_GEOMETRY): instances, instance tree, materials, maps and lights are replaced,
+        the geometry of the last full set_scene stays on the device."""
+        s2 = {k: v for k, v in scene.items() if k not in ("mesh_nodes", "triangles", "tri_host_index", "meshes")}
+        flags = int(np.asarray(scene.get("scene_flags", 0)).reshape(-1)[0]) | SCENE_KEEP_GEOMETRY
+        s2["scene_flags"] = np.array([flags], dtype=np.uint32)
+        self.set_scene(s2)
 
     def set_camera(self, camera: np.ndarray):
         cam = np.ascontiguousarray(camera).view(camera_dtype).reshape(-1)[:1].copy()

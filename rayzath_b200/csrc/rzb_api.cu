@@ -89,6 +89,11 @@ struct rzb_ctx
 	size_t prev_pixels = 0;
 	bool has_prev = false;
 	rzb_camera frame_cam{}, prev_cam{};
+	// geometry of the last full rzb_set_scene (RZB_SCENE_KEEP_GEOMETRY)
+	bool geom_valid = false;
+	std::vector<uint32_t> geom_mesh_base;
+	uint32_t geom_top_base = 0, geom_top_capacity = 0, geom_triangle_count = 0;
+	bool geom_own_trees = false;
 	bool own_trees = false;        // rzb_scene::flags & RZB_SCENE_OWN_TREES: conservative box tests
 	bool debug_sync = false;       // RZB200_DEBUG_SYNC: synchronise after every kernel of rzb_render and name the one that faulted
 };
@@ -364,8 +369,18 @@ extern "C" int rzb_set_scene(rzb_ctx* ctx, const rzb_scene* s)
 	ctx->has_scene = false;
 	ctx->frame_ready = false;
 
+	const bool keep_geometry = (s->flags & RZB_SCENE_KEEP_GEOMETRY) != 0u;
+	if (keep_geometry)
+	{
+		if (!ctx->geom_valid) return fail(ctx, RZB_ERR_STATE, "rzb_set_scene: RZB_SCENE_KEEP_GEOMETRY without a previous full upload");
+		if (s->instance_node_count > ctx->geom_top_capacity)
+			return fail(ctx, RZB_ERR_STATE, "rzb_set_scene: the instance tree outgrew its reserved space, upload the whole scene");
+	}
+	const uint32_t mesh_count = keep_geometry ? uint32_t(ctx->geom_mesh_base.size()) : s->mesh_count;
+	const uint32_t triangle_count = keep_geometry ? ctx->geom_triangle_count : s->triangle_count;
+
 	// ---- validate (host reads of the caller's arrays; everything heavy happens on the device below)
-	if (s->triangle_count > kHitTriMask - 1u) return fail(ctx, RZB_ERR_INVALID, "rzb_set_scene: too many triangles");
+	if (triangle_count > kHitTriMask - 1u) return fail(ctx, RZB_ERR_INVALID, "rzb_set_scene: too many triangles");
 	if (s->default_material >= s->material_count) return fail(ctx, RZB_ERR_INVALID, "rzb_set_scene: default material out of range");
 	for (uint32_t i = 0; i < s->instance_material_count; ++i)
 		if (s->instance_materials[i] >= s->material_count)
@@ -376,45 +391,60 @@ extern "C" int rzb_set_scene(rzb_ctx* ctx, const rzb_scene* s)
 	// ---- node placement: every tree is placed so that its root sits at an odd global index; sibling pairs (odd
 	// local index, next even) then start at even global indices = 64-byte aligned
 	std::vector<MeshEntry> table; // non-empty meshes only, ascending node_offset
-	table.reserve(s->mesh_count);
-	std::vector<uint32_t> mesh_base(s->mesh_count, kNoIndex);
-	size_t cursor = 1;
-	uint64_t expect_node = 0;
-	for (uint32_t m = 0; m < s->mesh_count; ++m)
+	std::vector<uint32_t> mesh_base(mesh_count, kNoIndex);
+	uint32_t top_base = 0;
+	size_t total_nodes = 0;
+	uint32_t top_capacity = 0;
+	if (keep_geometry)
 	{
-		const rzb_mesh& mesh = s->meshes[m];
-		if (uint64_t(mesh.node_offset) + mesh.node_count > s->mesh_node_count ||
-			uint64_t(mesh.tri_offset) + mesh.tri_count > s->triangle_count)
-			return fail(ctx, RZB_ERR_INVALID, "rzb_set_scene: mesh range outside node/triangle arrays");
-		if (mesh.node_count != 0 && mesh.node_offset < expect_node)
-			return fail(ctx, RZB_ERR_INVALID, "rzb_set_scene: mesh node ranges must be disjoint and ascending");
-		if (mesh.node_count != 0)
-		{
-			expect_node = uint64_t(mesh.node_offset) + mesh.node_count;
-			if ((cursor & 1u) == 0) ++cursor;
-			mesh_base[m] = uint32_t(cursor);
-			cursor += mesh.node_count;
-			table.push_back(MeshEntry{mesh.node_offset, mesh.node_count, mesh.tri_offset, mesh_base[m]});
-		}
+		mesh_base = ctx->geom_mesh_base;
+		top_base = ctx->geom_top_base;
+		top_capacity = ctx->geom_top_capacity;
 	}
-	if ((cursor & 1u) == 0) ++cursor;
-	const uint32_t top_base = uint32_t(cursor);
-	cursor += s->instance_node_count;
-	if (cursor >= (1u << 30)) return fail(ctx, RZB_ERR_INVALID, "rzb_set_scene: too many nodes");
-	const size_t total_nodes = cursor + 1;
-	for (uint32_t m = 0; m < s->mesh_count; ++m)
+	else
 	{
-		const rzb_mesh& mesh = s->meshes[m];
-		for (uint32_t i = 0; i < mesh.node_count; ++i)
+		ctx->geom_valid = false; // until this upload has succeeded
+		table.reserve(s->mesh_count);
+		size_t cursor = 1;
+		uint64_t expect_node = 0;
+		for (uint32_t m = 0; m < s->mesh_count; ++m)
 		{
-			const rzb_node& n = s->mesh_nodes[mesh.node_offset + i];
-			const uint32_t count = n.type_count & 0x3FFFFFFFu;
-			if (count != 0)
+			const rzb_mesh& mesh = s->meshes[m];
+			if (uint64_t(mesh.node_offset) + mesh.node_count > s->mesh_node_count ||
+				uint64_t(mesh.tri_offset) + mesh.tri_count > s->triangle_count)
+				return fail(ctx, RZB_ERR_INVALID, "rzb_set_scene: mesh range outside node/triangle arrays");
+			if (mesh.node_count != 0 && mesh.node_offset < expect_node)
+				return fail(ctx, RZB_ERR_INVALID, "rzb_set_scene: mesh node ranges must be disjoint and ascending");
+			if (mesh.node_count != 0)
 			{
-				if (uint64_t(n.begin) + count > mesh.tri_count) return fail(ctx, RZB_ERR_INVALID, "rzb_set_scene: leaf outside mesh triangles");
+				expect_node = uint64_t(mesh.node_offset) + mesh.node_count;
+				if ((cursor & 1u) == 0) ++cursor;
+				mesh_base[m] = uint32_t(cursor);
+				cursor += mesh.node_count;
+				table.push_back(MeshEntry{mesh.node_offset, mesh.node_count, mesh.tri_offset, mesh_base[m]});
 			}
-			else if (uint64_t(n.begin) + 1 >= mesh.node_count || (n.begin & 1u) == 0)
-				return fail(ctx, RZB_ERR_INVALID, "rzb_set_scene: bad child index in mesh tree");
+		}
+		if ((cursor & 1u) == 0) ++cursor;
+		top_base = uint32_t(cursor);
+		// room for the instance tree to grow under RZB_SCENE_KEEP_GEOMETRY updates
+		top_capacity = std::max<uint32_t>(2u * s->instance_node_count, 1024u);
+		cursor += top_capacity;
+		if (cursor >= (1u << 30)) return fail(ctx, RZB_ERR_INVALID, "rzb_set_scene: too many nodes");
+		total_nodes = cursor + 1;
+		for (uint32_t m = 0; m < s->mesh_count; ++m)
+		{
+			const rzb_mesh& mesh = s->meshes[m];
+			for (uint32_t i = 0; i < mesh.node_count; ++i)
+			{
+				const rzb_node& n = s->mesh_nodes[mesh.node_offset + i];
+				const uint32_t count = n.type_count & 0x3FFFFFFFu;
+				if (count != 0)
+				{
+					if (uint64_t(n.begin) + count > mesh.tri_count) return fail(ctx, RZB_ERR_INVALID, "rzb_set_scene: leaf outside mesh triangles");
+				}
+				else if (uint64_t(n.begin) + 1 >= mesh.node_count || (n.begin & 1u) == 0)
+					return fail(ctx, RZB_ERR_INVALID, "rzb_set_scene: bad child index in mesh tree");
+			}
 		}
 	}
 	// instance tree (small): fixed up on the host
@@ -453,7 +483,7 @@ extern "C" int rzb_set_scene(rzb_ctx* ctx, const rzb_scene* s)
 		d.mesh_root = kNoIndex;
 		if (h.mesh != RZB_NO_INDEX)
 		{
-			if (h.mesh >= s->mesh_count) return fail(ctx, RZB_ERR_INVALID, "rzb_set_scene: instance mesh id out of range");
+			if (h.mesh >= mesh_count) return fail(ctx, RZB_ERR_INVALID, "rzb_set_scene: instance mesh id out of range");
 			d.mesh_root = mesh_base[h.mesh];
 		}
 		if (uint64_t(h.material_offset) + h.material_count > s->instance_material_count ||
@@ -498,48 +528,58 @@ extern "C" int rzb_set_scene(rzb_ctx* ctx, const rzb_scene* s)
 	// ---- uploads straight from the caller's arrays, then device-side repacking into the traversal layout
 	DScene sc{};
 	DeviceBuffer* B = ctx->scene_buf;
-	const rzb_triangle* d_tri_raw = nullptr;
-	const rzb_node* d_mesh_nodes_raw = nullptr;
-	const MeshEntry* d_table = nullptr;
-	if ((rc = uploadTo(ctx, B[rzb_ctx::kBufTriRaw], s->triangles, s->triangle_count, &d_tri_raw))) return rc;
-	if ((rc = uploadTo(ctx, B[rzb_ctx::kBufMeshNodesRaw], s->mesh_nodes, s->mesh_node_count, &d_mesh_nodes_raw))) return rc;
-	if ((rc = uploadTo(ctx, B[rzb_ctx::kBufMeshTable], table.data(), table.size(), &d_table))) return rc;
-	if ((rc = ensureBuf(ctx, B[rzb_ctx::kBufNodes], total_nodes * 32))) return rc;
-	if ((rc = ensureBuf(ctx, B[rzb_ctx::kBufHot], size_t(s->triangle_count) * 48))) return rc;
-	if ((rc = ensureBuf(ctx, B[rzb_ctx::kBufCold], size_t(s->triangle_count) * 80))) return rc;
-	float4* d_nodes = static_cast<float4*>(B[rzb_ctx::kBufNodes].ptr);
-	RZB_CUDA(ctx, cudaMemsetAsync(d_nodes, 0, total_nodes * 32, ctx->stream));
+	float4* d_nodes = nullptr;
+	if (keep_geometry)
+	{
+		// reuse the packed geometry; only the instance-tree region of the node array is rewritten
+		d_nodes = static_cast<float4*>(B[rzb_ctx::kBufNodes].ptr);
+		RZB_CUDA(ctx, cudaMemsetAsync(d_nodes + 2 * size_t(top_base), 0, size_t(top_capacity) * 32, ctx->stream));
+	}
+	else
+	{
+		const rzb_triangle* d_tri_raw = nullptr;
+		const rzb_node* d_mesh_nodes_raw = nullptr;
+		const MeshEntry* d_table = nullptr;
+		if ((rc = uploadTo(ctx, B[rzb_ctx::kBufTriRaw], s->triangles, s->triangle_count, &d_tri_raw))) return rc;
+		if ((rc = uploadTo(ctx, B[rzb_ctx::kBufMeshNodesRaw], s->mesh_nodes, s->mesh_node_count, &d_mesh_nodes_raw))) return rc;
+		if ((rc = uploadTo(ctx, B[rzb_ctx::kBufMeshTable], table.data(), table.size(), &d_table))) return rc;
+		if ((rc = ensureBuf(ctx, B[rzb_ctx::kBufNodes], total_nodes * 32))) return rc;
+		if ((rc = ensureBuf(ctx, B[rzb_ctx::kBufHot], size_t(s->triangle_count) * 48))) return rc;
+		if ((rc = ensureBuf(ctx, B[rzb_ctx::kBufCold], size_t(s->triangle_count) * 80))) return rc;
+		d_nodes = static_cast<float4*>(B[rzb_ctx::kBufNodes].ptr);
+		RZB_CUDA(ctx, cudaMemsetAsync(d_nodes, 0, total_nodes * 32, ctx->stream));
+		if (s->mesh_node_count)
+		{
+			k_pack_mesh_nodes<<<(s->mesh_node_count + 255) / 256, 256, 0, ctx->stream>>>(d_mesh_nodes_raw, s->mesh_node_count,
+				d_table, uint32_t(table.size()), d_nodes);
+			ctx->launches += 1;
+		}
+		if (s->triangle_count)
+		{
+			k_pack_triangles<<<(s->triangle_count + 127) / 128, 128, 0, ctx->stream>>>(d_tri_raw, s->triangle_count,
+				static_cast<float4*>(B[rzb_ctx::kBufHot].ptr), static_cast<float4*>(B[rzb_ctx::kBufCold].ptr));
+			ctx->launches += 1;
+		}
+		if (s->tri_host_index)
+		{
+			if ((rc = uploadTo(ctx, B[rzb_ctx::kBufTriHost], s->tri_host_index, s->triangle_count, static_cast<const uint32_t**>(nullptr)))) return rc;
+		}
+		else
+		{
+			if ((rc = ensureBuf(ctx, B[rzb_ctx::kBufTriHost], size_t(s->triangle_count) * 4))) return rc;
+			if (s->triangle_count)
+				k_iota<<<(s->triangle_count + 255) / 256, 256, 0, ctx->stream>>>(static_cast<uint32_t*>(B[rzb_ctx::kBufTriHost].ptr), s->triangle_count);
+		}
+	}
 	if (s->instance_node_count)
 		RZB_CUDA(ctx, cudaMemcpyAsync(d_nodes + 2 * size_t(top_base), top_nodes.data(), top_nodes.size() * 32, cudaMemcpyHostToDevice, ctx->stream));
-	if (s->mesh_node_count)
-	{
-		k_pack_mesh_nodes<<<(s->mesh_node_count + 255) / 256, 256, 0, ctx->stream>>>(d_mesh_nodes_raw, s->mesh_node_count,
-			d_table, uint32_t(table.size()), d_nodes);
-		ctx->launches += 1;
-	}
-	if (s->triangle_count)
-	{
-		k_pack_triangles<<<(s->triangle_count + 127) / 128, 128, 0, ctx->stream>>>(d_tri_raw, s->triangle_count,
-			static_cast<float4*>(B[rzb_ctx::kBufHot].ptr), static_cast<float4*>(B[rzb_ctx::kBufCold].ptr));
-		ctx->launches += 1;
-	}
 	RZB_CUDA(ctx, cudaGetLastError());
 	sc.nodes = d_nodes;
 	sc.tri_hot = static_cast<const float4*>(B[rzb_ctx::kBufHot].ptr);
 	sc.tri_cold = static_cast<const float4*>(B[rzb_ctx::kBufCold].ptr);
+	sc.tri_host_index = static_cast<const uint32_t*>(B[rzb_ctx::kBufTriHost].ptr);
 	if ((rc = uploadTo(ctx, B[rzb_ctx::kBufInstances], insts.data(), insts.size(), &sc.instances))) return rc;
 	if ((rc = uploadTo(ctx, B[rzb_ctx::kBufInstHost], inst_host.data(), inst_host.size(), &sc.inst_host_index))) return rc;
-	if (s->tri_host_index)
-	{
-		if ((rc = uploadTo(ctx, B[rzb_ctx::kBufTriHost], s->tri_host_index, s->triangle_count, &sc.tri_host_index))) return rc;
-	}
-	else
-	{
-		if ((rc = ensureBuf(ctx, B[rzb_ctx::kBufTriHost], size_t(s->triangle_count) * 4))) return rc;
-		if (s->triangle_count)
-			k_iota<<<(s->triangle_count + 255) / 256, 256, 0, ctx->stream>>>(static_cast<uint32_t*>(B[rzb_ctx::kBufTriHost].ptr), s->triangle_count);
-		sc.tri_host_index = static_cast<const uint32_t*>(B[rzb_ctx::kBufTriHost].ptr);
-	}
 	if ((rc = uploadTo(ctx, B[rzb_ctx::kBufInstMats], s->instance_materials, s->instance_material_count, &sc.inst_materials))) return rc;
 	if ((rc = uploadTo(ctx, B[rzb_ctx::kBufMaterials], mats.data(), mats.size(), &sc.materials))) return rc;
 	if ((rc = uploadTo(ctx, B[rzb_ctx::kBufMaps], maps.data(), maps.size(), &sc.maps))) return rc;
@@ -555,7 +595,16 @@ extern "C" int rzb_set_scene(rzb_ctx* ctx, const rzb_scene* s)
 	sc.flags = ctx->cfg.flags;
 	RZB_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); // host staging vectors die at return; the caller may reuse its arrays
 	ctx->sc = sc;
-	ctx->own_trees = (s->flags & RZB_SCENE_OWN_TREES) != 0u;
+	if (!keep_geometry)
+	{
+		ctx->geom_valid = true;
+		ctx->geom_mesh_base = mesh_base;
+		ctx->geom_top_base = top_base;
+		ctx->geom_top_capacity = top_capacity;
+		ctx->geom_triangle_count = s->triangle_count;
+		ctx->geom_own_trees = (s->flags & RZB_SCENE_OWN_TREES) != 0u;
+	}
+	ctx->own_trees = ctx->geom_own_trees;
 	ctx->has_scene = true;
 	return RZB_OK;
 }

@@ -43,6 +43,7 @@ namespace RayZath::Cuda
 			std::vector<rzb_ctx*> ctxs; // one per device
 			uint32_t width = 0, height = 0;
 			bool scene_current = false;
+			uint64_t geometry_version = 0; // m_geometry_version of the last full upload into these contexts
 			std::vector<uint8_t> rgba;
 			std::vector<float> depth;
 			// sync == false: one frame in flight (pinned double buffer), the caller gets the previous one
@@ -58,6 +59,8 @@ namespace RayZath::Cuda
 		std::map<uint32_t, CameraState> m_cameras; // by camera container index
 		uint64_t m_seed = 0;
 		uint64_t m_scene_version = 0;
+		uint64_t m_geometry_version = 0; // bumped when the Mesh container changed: everything else updates incrementally
+		bool m_full_upload = false; // RZB200_FULL_UPLOAD=1: re-upload the geometry on every world change (test aid)
 		bool m_own_trees = false; // RZB200_BVH=sah: this repo's SAH triangle trees instead of the host World's
 		rzb_host::FlatScene m_flat;
 		std::string m_timings;
@@ -82,6 +85,7 @@ namespace RayZath::Cuda
 			}
 			if (m_devices.empty()) m_devices.push_back(0);
 			if (const char* env = std::getenv("RZB200_BVH")) m_own_trees = std::string(env) == "sah";
+			if (const char* env = std::getenv("RZB200_FULL_UPLOAD")) m_full_upload = std::string(env) == "1";
 			if (const char* env = std::getenv("RZB200_SEED")) m_seed = std::strtoull(env, nullptr, 0);
 			else
 			{
@@ -121,12 +125,18 @@ namespace RayZath::Cuda
 
 			if (world_update || m_scene_version == 0)
 			{
-				rzb_host::WorldFlattener(hWorld, m_flat, m_own_trees).run();
+				// incremental by dirty flags: triangles and mesh trees are re-flattened and re-uploaded only when the Mesh
+				// container changed (the reference re-mirrors per container too, cuda_world.cu:40-76)
+				const bool geometry_dirty = m_scene_version == 0 || m_full_upload || containerModified<RZ::ObjectType::Mesh>(hWorld);
+				rzb_host::WorldFlattener(hWorld, m_flat, m_own_trees).run(!geometry_dirty);
+				if (geometry_dirty) ++m_geometry_version;
 				++m_scene_version;
 				for (auto& [idx, cam] : m_cameras) cam.scene_current = false;
 				clearFlags(hWorld);
 			}
 			const rzb_scene scene = m_flat.view();
+			rzb_scene scene_update = scene; // same arrays, geometry kept on the device
+			scene_update.flags |= RZB_SCENE_KEEP_GEOMETRY;
 
 			for (uint32_t ci = 0; ci < hCameras.count(); ++ci)
 			{
@@ -146,7 +156,8 @@ namespace RayZath::Cuda
 				for (size_t d = 0; d < cs.ctxs.size(); ++d)
 				{
 					rzb_ctx* c = cs.ctxs[d];
-					if (!cs.scene_current) check(c, rzb_set_scene(c, &scene), "rzb_set_scene");
+					if (!cs.scene_current)
+						check(c, rzb_set_scene(c, cs.geometry_version == m_geometry_version ? &scene_update : &scene), "rzb_set_scene");
 					// one disjoint sample stream per device
 					rzb_config cfg = rzb_host::flattenConfig(config, m_seed + 0x9E3779B97F4A7C15ull * (uint64_t(ci) * 64 + d));
 					cfg.flags |= RZB_FLAG_TEMPORAL_REPROJECTION; // as the reference: every restart blends the replaced frame in
@@ -161,6 +172,7 @@ namespace RayZath::Cuda
 					check(c, rzb_render(c, std::max<uint32_t>(config.tracing().rpp(), 1u)), "rzb_render");
 				}
 				cs.scene_current = true;
+				cs.geometry_version = m_geometry_version;
 				cs.width = hCamera->width();
 				cs.height = hCamera->height();
 				hCamera->stateRegister().MakeUnmodified();
@@ -242,6 +254,15 @@ namespace RayZath::Cuda
 	private:
 		// every reconstruct() of the reference ends with MakeUnmodified() on what it mirrored (e.g. cuda_instance.cu:225,
 		// 281, cuda_world.cu:69-76); the GUI and the CPU engine read the same flags
+		template <RZ::ObjectType T>
+		static bool containerModified(RZ::World& w)
+		{
+			auto& c = w.container<T>();
+			if (c.stateRegister().IsModified()) return true;
+			for (uint32_t i = 0; i < c.count(); ++i)
+				if (c[i] && c[i]->stateRegister().IsModified()) return true;
+			return false;
+		}
 		template <RZ::ObjectType T>
 		static void clearContainer(RZ::World& w)
 		{

@@ -306,9 +306,22 @@ namespace rzb_host
 		WorldFlattener(const RZ::World& w, FlatScene& o, bool own_trees_ = false) : world(w), out(o), own_trees(own_trees_) {}
 
 		// Precondition: world.update() has been called (host BVHs are current), cuda_engine_core.cu:58-60.
-		void run()
+		// keep_geometry: the Mesh container has not changed since the previous run into the same FlatScene -- its
+		// mesh_nodes / triangles / tri_host_index / meshes stay as they are (RZB_SCENE_KEEP_GEOMETRY), everything else is
+		// flattened again.
+		void run(const bool keep_geometry = false)
 		{
-			out = FlatScene{};
+			if (keep_geometry)
+			{
+				FlatScene kept;
+				kept.mesh_nodes.swap(out.mesh_nodes);
+				kept.triangles.swap(out.triangles);
+				kept.tri_host_index.swap(out.tri_host_index);
+				kept.meshes.swap(out.meshes);
+				kept.scene_flags = out.scene_flags;
+				out = std::move(kept);
+			}
+			else out = FlatScene{};
 			flattenMaps<RZ::ObjectType::Texture, Graphics::Color>(tex_ids, RZB_MAP_RGBA8);
 			flattenMaps<RZ::ObjectType::NormalMap, Graphics::Color>(nrm_ids, RZB_MAP_RGBA8);
 			flattenMaps<RZ::ObjectType::MetalnessMap, uint8_t>(met_ids, RZB_MAP_R8);
@@ -329,11 +342,12 @@ namespace rzb_host
 
 			const auto& meshes = world.container<RZ::ObjectType::Mesh>();
 			std::vector<uint32_t> mesh_ids(meshes.count(), RZB_NO_INDEX);
+			uint32_t next_mesh = 0;
 			for (uint32_t i = 0; i < meshes.count(); ++i)
 			{
 				if (!meshes[i]) continue;
-				mesh_ids[i] = uint32_t(out.meshes.size());
-				flattenMesh(*meshes[i]);
+				mesh_ids[i] = next_mesh++;
+				if (!keep_geometry) flattenMesh(*meshes[i]);
 			}
 
 			const auto& dls = world.container<RZ::ObjectType::DirectLight>();

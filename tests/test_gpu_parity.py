@@ -586,3 +586,36 @@ def test_async_resolve_matches_resolve_and_overlaps(contexts, worlds):
             a.free()
             b.free()
         c.set_config()
+
+
+def test_incremental_scene_update_keeps_geometry():
+    """RZB_SCENE_KEEP_GEOMETRY: moving instances / changing materials re-uploads only the small arrays; the result is
+    byte-equal to a full upload of the changed scene."""
+    w = GOLDEN_SCENES["instancing"]()
+    flat0 = w.flatten()
+    for k, inst in enumerate(w.instances):
+        inst.position = (inst.position[0] + 0.3 * (k % 3), inst.position[1] + 0.1, inst.position[2] - 0.2 * (k % 2))
+    w.materials[0].color = (10, 200, 30, 255)
+    flat1 = w.flatten()
+    assert np.array_equal(flat0["triangles"].view(np.uint8), flat1["triangles"].view(np.uint8))
+    assert not np.array_equal(flat0["instances"].view(np.uint8), flat1["instances"].view(np.uint8))
+    cam = w.camera_struct()
+    with capi.Context(0) as a, capi.Context(0) as b:
+        with pytest.raises(capi.RzbError):
+            a.update_scene(flat1)             # nothing to keep yet
+        a.set_scene(flat0)
+        a.update_scene(flat1)
+        b.set_scene(flat1)
+        for c in (a, b):
+            c.set_camera(cam)
+        o, d, nf = a.generate_camera_rays()
+        ha, hb = a.trace_closest(o, d, nf), b.trace_closest(o, d, nf)
+        assert np.array_equal(ha.view(np.uint8), hb.view(np.uint8))
+        assert (ha["instance"] != capi.NO_INDEX).mean() > 0.15
+        ref = O.trace_closest(O.Scene(flat1), o, d, nf, order=O.ORDER_CUDA, minmax=O.MINMAX_FMINF)
+        assert np.array_equal(ha.view(np.uint8), ref.view(np.uint8))
+        for c in (a, b):
+            c.set_config(max_depth=4, seed=3)
+            c.reset()
+            c.render(4)
+        assert np.allclose(a.read_accum(), b.read_accum(), rtol=1e-5, atol=1e-5)
