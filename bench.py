@@ -121,7 +121,7 @@ def build_world(workload):
     w = scenes.CONFIGS[name](**kw)
     if BVH != "reference":
         for m in w.meshes:
-            m.bvh_builder = ("sah", int(os.environ.get("RZB200_SAH_MAX_LEAF", "4")))
+            m.bvh_builder = (BVH, int(os.environ.get("RZB200_SAH_MAX_LEAF", "4")))
     return w
 
 
@@ -189,8 +189,9 @@ def main():
     ap.add_argument("--split", default="samples", choices=["samples", "tiles", "hybrid"],
                     help="N>1: samples = every rank renders the whole frame with its own RNG stream (weak scaling, default); "
                          "tiles = rank r renders row band r of N (strong scaling); hybrid = N/2 bands x 2 streams")
-    ap.add_argument("--bvh", default="reference", choices=["reference", "sah"],
-                    help="triangle trees: the reference's own (parity mode, default) or the optional SAH builder")
+    ap.add_argument("--bvh", default="reference", choices=["reference", "sah", "lbvh"],
+                    help="triangle trees: the reference's own (parity mode, default), the optional SAH builder (host) or the "
+                         "optional linear-BVH builder (GPU)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-aux", action="store_true")
     args = ap.parse_args()
@@ -463,7 +464,8 @@ def main():
             "value": value, "ms_per_step": ms_max / args.steps,
             "config": {"workload": args.workload, "resolution": [W, H], "triangles": int(flat["triangles"].shape[0]),
                        "instances": int(flat["instances"].shape[0]), "max_depth": MAX_DEPTH, "light_samples": [1, 1],
-                       "bvh": "reference trees" if BVH == "reference" else "optional SAH builder (leaf <= 4)",
+                       "bvh": {"reference": "reference trees", "sah": "optional SAH builder (leaf <= 4)",
+                               "lbvh": "optional GPU linear-BVH builder (leaf <= 4)"}[BVH],
                        "sharding": ("%d row band(s) x %d sample stream(s)" % (bands, streams)) if world > 1 else "single GPU",
                        "reduce": args.reduce if world > 1 else None,
                        "l2": "no flush: per-pass working set %.0f MB (path state + queues + accumulator + scene) > 126 MB L2"

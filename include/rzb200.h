@@ -360,6 +360,14 @@ int rzb_build_mesh_bvh(const float* vertices, uint32_t nv, const uint32_t* tris,
  * on it unchanged. Closest-hit records equal the reference tree's except on exact-distance ties. */
 int rzb_build_mesh_bvh_sah(const float* vertices, uint32_t nv, const uint32_t* tris, uint32_t nt, uint32_t max_leaf,
 	rzb_node* nodes_out, uint32_t node_capacity, uint32_t* node_count_out, uint32_t* order_out);
+/* OPTIONAL GPU builder: linear BVH built on `device` (Morton codes, radix sort, Karras' parallel
+ * radix tree, bottom-up boxes, leaves of at most max_leaf triangles), same output format and guarantees as
+ * rzb_build_mesh_bvh_sah. For rebuild speed (1M triangles: milliseconds of device time, reported through device_ms_out,
+ * may be NULL); the SAH tree traces faster. Inputs whose radix tree is deeper than the traversal stack allows are handed
+ * to rzb_build_mesh_bvh_sah. */
+int rzb_build_mesh_bvh_lbvh(int device, const float* vertices, uint32_t nv, const uint32_t* tris, uint32_t nt,
+	uint32_t max_leaf, rzb_node* nodes_out, uint32_t node_capacity, uint32_t* node_count_out, uint32_t* order_out,
+	float* device_ms_out);
 /* Instance BVH (bvh_tree_node.hpp:117-215 + cuda_bvh.cuh:86-111): boxes[n][6] = min xyz, max xyz. */
 int rzb_build_instance_bvh(const float* boxes, uint32_t n,
 	rzb_node* nodes_out, uint32_t node_capacity, uint32_t* node_count_out, uint32_t* order_out);

@@ -127,6 +127,8 @@ SYMBOLS = {
     "rzb_host_alloc": (C.c_int, [C.c_size_t, C.POINTER(C.c_void_p)]),
     "rzb_host_free": (C.c_int, [_P]),
     "rzb_build_mesh_bvh": (C.c_int, [_P, C.c_uint32, _P, C.c_uint32, _P, C.c_uint32, C.POINTER(C.c_uint32), _P]),
+    "rzb_build_mesh_bvh_lbvh": (C.c_int, [C.c_int, _P, C.c_uint32, _P, C.c_uint32, C.c_uint32, _P, C.c_uint32, C.POINTER(C.c_uint32), _P,
+                                          C.POINTER(C.c_float)]),
     "rzb_build_mesh_bvh_sah": (C.c_int, [_P, C.c_uint32, _P, C.c_uint32, C.c_uint32, _P, C.c_uint32, C.POINTER(C.c_uint32), _P]),
     "rzb_build_instance_bvh": (C.c_int, [_P, C.c_uint32, _P, C.c_uint32, C.POINTER(C.c_uint32), _P]),
     "rzb_rotation_axes": (C.c_int, [_P, C.c_int, _P]),
@@ -223,6 +225,22 @@ def build_mesh_bvh_sah(vertices: np.ndarray, tris: np.ndarray, max_leaf: int = 8
     if rc:
         raise RzbError(rc, "rzb_build_mesh_bvh_sah failed")
     return nodes[:count.value].copy(), order
+
+
+def build_mesh_bvh_lbvh(vertices: np.ndarray, tris: np.ndarray, max_leaf: int = 4, device: int = 0, timing=False):
+    """rzb_build_mesh_bvh_lbvh: the optional GPU linear-BVH builder. Returns (nodes, order[, device ms])."""
+    v = _c(vertices, f4).reshape(-1, 3)
+    t = _c(tris, u4).reshape(-1, 3)
+    nt = t.shape[0]
+    nodes = np.zeros(2 * nt + 1, dtype=node_dtype)
+    order = np.zeros(nt, dtype=u4)
+    count, ms = C.c_uint32(0), C.c_float(0.0)
+    rc = lib().rzb_build_mesh_bvh_lbvh(int(device), v.ctypes.data, v.shape[0], t.ctypes.data, nt, int(max_leaf),
+                                       nodes.ctypes.data, nodes.shape[0], C.byref(count), order.ctypes.data, C.byref(ms))
+    if rc:
+        raise RzbError(rc, "rzb_build_mesh_bvh_lbvh failed")
+    out = (nodes[:count.value].copy(), order)
+    return out + (ms.value,) if timing else out
 
 
 def build_instance_bvh(boxes: np.ndarray):

@@ -80,13 +80,16 @@ class Mesh:
     index: int = 0
     normals_input: Optional[np.ndarray] = None  # what was passed to createNormal (written to scene files)
     _bvh: Optional[tuple] = None
-    # "reference" = the reference's own tree (parity mode); ("sah", max_leaf) = the optional SAH builder
+    # "reference" = the reference's own tree (parity mode); ("sah", max_leaf) = the optional SAH builder;
+    # ("lbvh", max_leaf) = the optional GPU linear-BVH builder
     bvh_builder: object = "reference"
 
     def bvh(self):
         if self._bvh is None or self._bvh[0] != self.bvh_builder:
             if self.bvh_builder == "reference":
                 built = capi.build_mesh_bvh(self.vertices, self.tris)
+            elif self.bvh_builder[0] == "lbvh":
+                built = capi.build_mesh_bvh_lbvh(self.vertices, self.tris, int(self.bvh_builder[1]))
             else:
                 built = capi.build_mesh_bvh_sah(self.vertices, self.tris, int(self.bvh_builder[1]))
             self._bvh = (self.bvh_builder, built)

@@ -163,3 +163,65 @@ def test_gpu_sah_tree_same_image():
     close = np.isclose(a[..., :3], b[..., :3], rtol=1e-4, atol=1e-6).all(axis=2)
     assert close.mean() > 0.999, close.mean()
     assert abs(a[..., :3].mean() - b[..., :3].mean()) / a[..., :3].mean() < 1e-3
+
+
+# ---------------------------------------------------------------------------------------------- GPU builder (linear BVH)
+def _check_tree(nodes, order, v, t, max_leaf):
+    assert sorted(order.tolist()) == list(range(t.shape[0]))
+    count = nodes["type_count"] & 0x3FFFFFFF
+    leaf = count != 0
+    assert count[leaf].sum() == t.shape[0] and count.max() <= max_leaf
+    inner = np.flatnonzero(~leaf)
+    assert (nodes["begin"][inner] % 2 == 1).all()
+    refs = np.concatenate([nodes["begin"][inner], nodes["begin"][inner] + 1])
+    assert sorted(refs.tolist()) == list(range(1, nodes.shape[0]))
+    lb = np.sort(nodes["begin"][leaf])
+    assert lb[0] == 0 and (np.diff(lb) > 0).all()
+    tri_v = v[t[order]]
+    for i in np.flatnonzero(leaf)[::max(1, int(leaf.sum()) // 300)]:
+        pts = tri_v[nodes["begin"][i]:nodes["begin"][i] + count[i]].reshape(-1, 3)
+        assert (pts >= nodes["bb_min"][i]).all() and (pts <= nodes["bb_max"][i]).all()
+    for i in inner[::max(1, inner.size // 300)]:
+        for ch in (nodes["begin"][i], nodes["begin"][i] + 1):
+            assert (nodes["bb_min"][ch] >= nodes["bb_min"][i]).all() and (nodes["bb_max"][ch] <= nodes["bb_max"][i]).all()
+
+
+@pytest.mark.gpu
+def test_gpu_lbvh_builder_structure_and_speed():
+    v, t, uv, n = scenes.heightfield_mesh(300, 300)
+    for max_leaf in (1, 4, 8):
+        nodes, order = capi.build_mesh_bvh_lbvh(v, t, max_leaf)
+        _check_tree(nodes, order, v, t, max_leaf)
+    # degenerate inputs: a single triangle, fewer triangles than a leaf holds, coincident triangles (-> SAH fallback)
+    v1 = np.array([[0, 0, 0], [1, 0, 0], [0, 0, 1]], np.float32)
+    nodes, order = capi.build_mesh_bvh_lbvh(v1, np.array([[0, 1, 2]], np.uint32), 4)
+    assert nodes.shape[0] == 1 and (nodes["type_count"][0] & 0x3FFFFFFF) == 1
+    same = np.tile(np.array([[0, 1, 2]], np.uint32), (4096, 1))
+    nodes, order = capi.build_mesh_bvh_lbvh(v1, same, 4)
+    _check_tree(nodes, order, v1, same, 4)
+    with pytest.raises(capi.RzbError):
+        capi.build_mesh_bvh_lbvh(v1, np.array([[0, 1, 9]], np.uint32), 4)
+    # 1M triangles: device time of the build (keys, sort, radix tree, boxes, collapse, emission)
+    v, t, uv, n = scenes.heightfield_mesh(708, 707)
+    capi.build_mesh_bvh_lbvh(v, t, 4)
+    nodes, order, ms = capi.build_mesh_bvh_lbvh(v, t, 4, timing=True)
+    print("LBVH 1,001,112 triangles: %d nodes, %.2f ms on the device" % (nodes.shape[0], ms))
+    assert 0.0 < ms < 100.0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", NAMES)
+def test_gpu_lbvh_tree_hits_vs_oracle_on_reference_tree(name, golden, flats):
+    g = golden[name]
+    w = GOLDEN_SCENES[name]()
+    for m in w.meshes:
+        m.bvh_builder = ("lbvh", 4)
+    flat = w.flatten()
+    assert int(flat["scene_flags"][0]) == capi.SCENE_OWN_TREES
+    with capi.Context(0) as c:
+        c.set_scene(flat)
+        c.set_camera(w.camera_struct())
+        for rays in ((g["ray_origins"], g["ray_directions"], g["ray_near_far"]), _incoherent_rays()):
+            hits = c.trace_closest(*rays)
+            ref = O.trace_closest(O.Scene(flats[name]), *rays, order=O.ORDER_CUDA, minmax=O.MINMAX_FMINF)
+            _assert_equal_except_ties(hits, ref)
