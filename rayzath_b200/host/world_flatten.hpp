@@ -189,8 +189,14 @@ namespace rzb_host
 		}
 		// Optional: ignore the host tree and build this repo's SAH tree over the same triangles (rzb_build_mesh_bvh_sah;
 		// RZB_SCENE_OWN_TREES). The triangle records are the same, only their order and the nodes differ.
+		// Compiled only where librzb200.so is linked (the drop-in build defines RZB_FLATTEN_WITH_OWN_TREES); the oracle's
+		// rz_ref_tool includes this header for the reference trees alone and must not depend on the product library.
 		bool flattenMeshOwnTree(const RZ::Mesh& mesh, rzb_mesh& m)
 		{
+#ifndef RZB_FLATTEN_WITH_OWN_TREES
+			(void)mesh; (void)m;
+			return false;
+#else
 			const uint32_t nt = mesh.triangles().count(), nv = mesh.vertices().count();
 			std::vector<float> verts(size_t(nv) * 3);
 			for (uint32_t i = 0; i < nv; ++i) put3(&verts[size_t(i) * 3], mesh.vertices()[i]);
@@ -209,6 +215,7 @@ namespace rzb_host
 			out.mesh_nodes.insert(out.mesh_nodes.end(), nodes.begin(), nodes.begin() + count);
 			for (uint32_t i = 0; i < nt; ++i) addTriangle(mesh, mesh.triangles()[order[i]]);
 			return true;
+#endif
 		}
 		void flattenMesh(const RZ::Mesh& mesh)
 		{
