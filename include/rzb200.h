@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define RZB_ABI_VERSION 1u
+#define RZB_ABI_VERSION 2u /* 2: rzb_scene::flags, own trees, async resolve, incremental update, work counters grew */
 #define RZB_NO_INDEX 0xFFFFFFFFu
 #define RZB_MAX_MATERIALS_PER_INSTANCE 64u /* Instance::materialCapacity(), instance.hpp */
 

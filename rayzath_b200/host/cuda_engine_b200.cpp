@@ -92,6 +92,8 @@ namespace RayZath::Cuda
 				std::random_device rd;
 				m_seed = (uint64_t(rd()) << 32) | rd();
 			}
+			if (rzb_abi_version() != int(RZB_ABI_VERSION))
+				throw Exception("librzb200.so has ABI version " + std::to_string(rzb_abi_version()) + ", this engine was built for " + std::to_string(RZB_ABI_VERSION));
 			// probe the first device now: a missing GPU must surface from the constructor so that
 			// RayZath::Engine::Engine falls back to the CPU engine
 			rzb_ctx* probe = nullptr;
