@@ -49,10 +49,20 @@ def _instancing_world():
     return w
 
 
+def _world_fog():
+    """Scattering and absorbing WORLD medium: free flight in applyScattering (cuda_material.cuh:141-159) on every segment,
+    isotropic in-scattering with NEE (BRDF = 1), exp(-d sigma) on the spot lights, Beer-Lambert on every segment."""
+    w = _variant(["ground", "mirror ball", "gold ball"], ["sun", "spots"])
+    w.world_material.scattering = 0.08
+    w.world_material.color = (245, 250, 255, 3)
+    return w
+
+
 OTHER_SCENES = {
     "heightfield_maps_point": lambda: _maps_world(False),
     "heightfield_maps_linear": lambda: _maps_world(True),
     "instancing": _instancing_world,
+    "world_fog": _world_fog,
 }
 
 
