@@ -119,8 +119,12 @@ namespace rzb
 	// ---- short stack: first kSmemStack entries per thread in shared memory (interleaved by thread so a
 	// warp's pushes hit 32 consecutive 8-byte words), the rest in local memory. Depth bound: two trees of
 	// depth <= 33 (max_depth 31 in both builders) plus one instance-range entry.
-	constexpr int kSmemStack = 20;
-	constexpr int kLocalStack = 52;
+	// Shared memory taken here is L1 taken from the node / triangle fetches (one 256 KB array per SM): measured on B200
+	// at 1080p, entries in shared memory 20 / 12 / 8 / 4 / 2 -> materials scene 1058 / 1100 / 1108 / 1103 / 1088 Mrays/s,
+	// 1M triangles 1140 / 1159 / 1161 / 1153 / 1135 (at 8 blocks per SM the 20-entry stack left the shadow kernel
+	// almost no L1).
+	constexpr int kSmemStack = 8;
+	constexpr int kLocalStack = 64;
 	constexpr int kTraceBlock = 128;
 
 	enum : uint32_t
