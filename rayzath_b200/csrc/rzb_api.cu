@@ -94,6 +94,7 @@ struct rzb_ctx
 	std::vector<uint32_t> geom_mesh_base;
 	uint32_t geom_top_base = 0, geom_top_capacity = 0, geom_triangle_count = 0;
 	bool geom_own_trees = false;
+	bool set_carveout = true;      // RZB200_CARVEOUT=0 disables the shared-memory carve-out hint
 	bool own_trees = false;        // rzb_scene::flags & RZB_SCENE_OWN_TREES: conservative box tests
 	bool debug_sync = false;       // RZB200_DEBUG_SYNC: synchronise after every kernel of rzb_render and name the one that faulted
 };
@@ -170,6 +171,21 @@ namespace
 	{
 		int per_sm = 0;
 		if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, block, 0) != cudaSuccess || per_sm < 1) per_sm = 1;
+		// shared memory and L1 share one array per SM: ask for no more shared memory than the resident blocks use, the
+		// rest serves the node / triangle fetches (RZB200_CARVEOUT=0 leaves the driver's default)
+		cudaFuncAttributes attr{};
+		if (ctx->set_carveout && cudaFuncGetAttributes(&attr, kernel) == cudaSuccess && attr.sharedSizeBytes > 0)
+		{
+			int max_smem = 0;
+			cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerMultiprocessor, ctx->device);
+			const size_t need = size_t(per_sm) * (attr.sharedSizeBytes + 1024);
+			if (max_smem > 0)
+			{
+				const int pct = int(std::min<size_t>(100, (need * 100 + size_t(max_smem) - 1) / size_t(max_smem)));
+				cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+				if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, block, 0) != cudaSuccess || per_sm < 1) per_sm = 1;
+			}
+		}
 		return ctx->sm_count * per_sm;
 	}
 
@@ -292,6 +308,7 @@ extern "C" int rzb_create(int device, rzb_ctx** out)
 	if ((e = cudaMalloc(reinterpret_cast<void**>(&ctx->d_counters), 256)) != cudaSuccess) { delete ctx; return cudaFail(nullptr, e, "cudaMalloc(counters)"); }
 	cudaMemsetAsync(ctx->d_counters, 0, 256, ctx->stream);
 	ctx->debug_sync = std::getenv("RZB200_DEBUG_SYNC") != nullptr;
+	if (const char* env = std::getenv("RZB200_CARVEOUT")) ctx->set_carveout = std::atoi(env) != 0;
 	ctx->trace_grid = gridFor(ctx, reinterpret_cast<const void*>(&k_trace_paths<false, false>), kTraceBlock);
 	ctx->shadow_grid = gridFor(ctx, reinterpret_cast<const void*>(&k_trace_shadow<false>), kTraceBlock);
 	ctx->trace_grid_fast = gridFor(ctx, reinterpret_cast<const void*>(&k_trace_paths<false, true>), kTraceBlock);
