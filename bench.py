@@ -33,10 +33,11 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 WORKLOADS = {
-    # BASELINE.json configs[1]: the configuration the metric is quoted on (fits one GPU)
-    "materials_1080p": ("materials", dict(resolution=(1920, 1080), res=64)),
-    # configs[2] geometry (1M triangles, maps, DoF), kept as a secondary line in "aux"
+    # BASELINE.json configs[2] geometry: the 1M-triangle scene (texture / normal / roughness maps, depth of field) that
+    # north_star's target (">= 1 Grays/s per B200 on a 1M-triangle scene") is stated on -- the headline workload
     "heightfield_1m_1080p": ("heightfield_1m", dict(resolution=(1920, 1080))),
+    # configs[1]: materials + lights scene (23k triangles), kept as a secondary line in "aux"
+    "materials_1080p": ("materials", dict(resolution=(1920, 1080), res=64)),
     "instancing_10m_1080p": ("instancing_10m", dict(resolution=(1920, 1080))),
     "cornell_512": ("cornell", dict(resolution=(512, 512))),
     # configs[4]: the 1M-triangle scene at 3840x2160 (use with --split hybrid on 8 GPUs: 4 row bands x 2 sample streams)
@@ -46,6 +47,9 @@ WORKLOADS = {
 B_NODE, B_TRI, B_STATE, B_HIT = 48, 144, 57, 24
 B_SHADOW_REC, B_SHADOW_ACC = 48, 12  # shadow queue record read, accumulator update
 MAX_DEPTH = 16          # Tracing::maxDepth default, engine_parts.hpp:101
+PREROLL = 2 * MAX_DEPTH  # untimed passes after a reset before anything is timed: paths of all depths are in flight
+DEFAULT_WORKLOAD = "heightfield_1m_1080p"
+SECONDARY_WORKLOAD = "materials_1080p"
 RPP_E2E = 64            # passes per renderWorld call the headless auto-tuner converges to (headless.cpp:287-295)
 
 
@@ -168,6 +172,52 @@ def reference_run(workload, steps, warmup, budget_s=240.0):
     }
 
 
+# ---------------------------------------------------------------------------------------------- drop-in leg
+def dropin_run(workload, budget_s=20.0):
+    """e2e through the REFERENCE-FACING host: the reference's own headless runner (Application/headless.cpp, compiled
+    in place) with RayZath::Cuda::Engine implemented by rayzath_b200/host/cuda_engine_b200.cpp -- scene file loaded by
+    the reference's json_loader, World flattened by world_flatten.hpp, frames through Engine::renderWorld. The number
+    is the reference's own report line (`traced N rays (N rps)`, headless.cpp:317-320). None when the binary was not
+    built (it needs /root/reference at build time and travels to the GPU box prebuilt)."""
+    binary = os.path.join(ROOT, "rayzath_b200", "host", "_build", "rz_b200_headless")
+    if not os.path.exists(binary):
+        return None
+    import re
+    from rayzath_b200 import scenes
+    name, kw = WORKLOADS[workload]
+    tmp = tempfile.mkdtemp(prefix="rzb_bench_dropin_")
+    try:
+        w = scenes.CONFIGS[name](**kw)
+        w.save_reference(tmp, "scene")
+        json.dump({"tasks": [{"scene path": "scene.json", "engine": ["CUDAGPU"], "rpp": 1000000, "timeout": budget_s,
+                              "max depth": MAX_DEPTH}]}, open(os.path.join(tmp, "tasks.json"), "w"))
+        os.makedirs(os.path.join(tmp, "report"))
+        t0 = time.perf_counter()
+        r = subprocess.run([binary, "--headless", "tasks.json", "report", "-r"], cwd=tmp, capture_output=True, text=True,
+                           timeout=budget_s * 6 + 240, env=dict(os.environ, RZB200_SEED="20261018"))
+        wall = time.perf_counter() - t0
+        if r.returncode != 0:
+            return {"error": (r.stderr or r.stdout)[-400:]}
+        text = ""
+        for dp, _, fs in os.walk(os.path.join(tmp, "report")):
+            for f in fs:
+                if f == "report.txt":
+                    text = open(os.path.join(dp, f)).read()
+        m = re.search(r"traced\s+([0-9.]+)\s*([kMGT]?)\s*rays\s*\(([0-9.]+)\s*([kMGT]?)\s*rps\)", text)
+        if not m:
+            return {"error": "no report line: " + text[-300:]}
+        mult = {"": 1.0, "k": 1e3, "M": 1e6, "G": 1e9, "T": 1e12}
+        return {"value": float(m.group(3)) * mult[m.group(4)] / 1e6, "unit": "Mrays/s",
+                "rays": float(m.group(1)) * mult[m.group(2)], "wall_s": wall,
+                "step": "rz_b200_headless (reference headless.cpp + json_loader + World flatten + renderWorld on the B200 path), "
+                        "task: engine CUDAGPU, timeout %.0f s, max depth %d; number = the reference's own report.txt rps" % (budget_s, MAX_DEPTH)}
+    except Exception as e:
+        return {"error": repr(e)}
+    finally:
+        import shutil
+        shutil.rmtree(tmp, ignore_errors=True)
+
+
 # ---------------------------------------------------------------------------------------------- our arm
 def pin(arrays):
     """Page-lock the host arrays the boundary reads from (cudaHostRegister through torch)."""
@@ -178,12 +228,122 @@ def pin(arrays):
             rt.cudaHostRegister(a.ctypes.data, a.nbytes, 0)
 
 
+def describe_config(workload, world_obj, n_px_state):
+    """`config` of the JSON line: the workload only, identical (keys AND values) in both arms so that the driver's
+    same-config check compares like with like; arm-specific facts (sharding, reduce, spp/s) are under "run"."""
+    tris = int(sum(m.tris.shape[0] for m in world_obj.meshes))
+    nodes_est = 0.33 * tris
+    W, H = (int(x) for x in world_obj.cameras[0].resolution)
+    working_set = (tris * 128 + nodes_est * 32 + n_px_state * (40 + 20 + 16 + 48)) / 1e6
+    return {"workload": workload, "resolution": [W, H], "triangles": tris, "instances": len(world_obj.instances),
+            "max_depth": MAX_DEPTH, "light_samples": [1, 1], "bvh": "reference trees",
+            "preroll_passes": PREROLL,
+            "l2": "no flush: per-pass working set ~%.0f MB (path state + queues + accumulator + scene) > 126 MB L2"
+                  % working_set}
+
+
+def load_profile(key):
+    prof_path = os.path.join(ROOT, "profiles", "ncu_summary.json")
+    if os.path.exists(prof_path):
+        try:
+            return json.load(open(prof_path)).get(key, {})
+        except Exception:
+            pass
+    return {}
+
+
+def work_and_roofline(ctx, capi, steps, warm, seed, n_px, stage_ms, profile_key, peak, clocks, sm_count):
+    """Replays the timed passes with the counting kernels (the RNG is counter-based on (seed, slot, pass): after a
+    reset the same pass indices retrace the same rays) and turns the counters into the two roofs of DESIGN.md:
+      hbm    ALGORITHMIC bytes in reference-layout constants / measured kernel time / measured HBM peak.
+             A throughput normalisation: the hot scene is L2-resident, `traffic` (ncu DRAM bytes) is far smaller.
+      issue  the roof that binds: warp instructions per launch (ncu smsp__inst_executed of the same command,
+             profiles/ncu_summary.json) / measured kernel time, against SMs x 4 schedulers x SM clock; `lane_frac`
+             multiplies by the active threads per instruction / 32 (SIMT efficiency)."""
+    trace_ms, shade_ms, shadow_ms = stage_ms
+    ctx.reset()
+    ctx.render(warm)
+    ctx.set_config(1, 1, MAX_DEPTH, capi.FLAG_COUNT_WORK, seed)
+    ctx.render(steps)
+    wc = ctx.work_counters()
+    ctx.set_config(1, 1, MAX_DEPTH, capi.FLAG_NONE, seed)
+    seg = max(int(wc["segments"]), 1)
+    nodes_per_seg = float(wc["closest_top_nodes"] + wc["closest_mesh_nodes"]) / seg
+    tris_per_seg = float(wc["closest_triangles"]) / seg
+    shadow_per_seg = float(wc["shadow_rays"]) / seg
+    lane_util = {"closest": float(wc["closest_lane_work"]) / max(int(wc["closest_batch_work"]), 1),
+                 "shadow": float(wc["shadow_lane_work"]) / max(int(wc["shadow_batch_work"]), 1),
+                 "dropped_non_finite_samples": int(wc["invalid_rays"])}
+    bytes_per_seg = B_STATE + nodes_per_seg * B_NODE + tris_per_seg * B_TRI + B_HIT
+    n_shadow = max(int(wc["shadow_rays"]), 1)
+    sh_nodes = float(wc["shadow_top_nodes"] + wc["shadow_mesh_nodes"]) / n_shadow
+    sh_tris = float(wc["shadow_triangles"]) / n_shadow
+    bytes_per_shadow_ray = B_SHADOW_REC + sh_nodes * B_NODE + sh_tris * B_TRI + B_SHADOW_ACC
+    prof = load_profile(profile_key)
+    f_mhz = float((clocks or {}).get("sm_mhz") or (clocks or {}).get("sm_max_mhz") or 1965.0)
+    warp_peak = sm_count * 4 * f_mhz * 1e6  # warp instructions per second the chip can issue at the sampled clock
+
+    def issue(kernel, ms):
+        wi, tpi = prof.get(kernel + "_warp_inst_per_launch"), prof.get(kernel + "_threads_per_inst")
+        if not wi or not ms:
+            return None
+        rate = float(wi) / (ms * 1e-3)
+        out = {"warp_inst_per_launch": float(wi), "threads_per_inst": tpi, "warp_inst_per_s": rate,
+               "peak_warp_inst_per_s": warp_peak, "frac": rate / warp_peak,
+               "source": "ncu smsp__inst_executed.sum of the same workload (profiles/ncu_summary.json) / live kernel time; "
+                         "peak = %d SMs x 4 x %.0f MHz" % (sm_count, f_mhz)}
+        if tpi:
+            out["thread_inst_per_s"] = rate * float(tpi)
+            out["lane_frac"] = rate * float(tpi) / (warp_peak * 32.0)
+        return out
+
+    kernels = {
+        "k_trace_paths": {"ms": trace_ms, "units_per_launch": n_px, "algorithmic_bytes_per_unit": bytes_per_seg,
+                          "achieved": bytes_per_seg * n_px / (trace_ms * 1e-3) / 1e9 if trace_ms > 0 else None,
+                          "traffic": prof.get("k_trace_paths_dram_bytes_per_launch"), "issue": issue("k_trace_paths", trace_ms)},
+        "k_trace_shadow": {"ms": shadow_ms, "units_per_launch": shadow_per_seg * n_px,
+                           "algorithmic_bytes_per_unit": bytes_per_shadow_ray,
+                           "achieved": bytes_per_shadow_ray * shadow_per_seg * n_px / (shadow_ms * 1e-3) / 1e9 if shadow_ms > 0 else None,
+                           "traffic": prof.get("k_trace_shadow_dram_bytes_per_launch"), "issue": issue("k_trace_shadow", shadow_ms)},
+    }
+    dominant = max(kernels, key=lambda k: kernels[k]["ms"])
+    achieved = kernels[dominant]["achieved"]
+    return {
+        # `bound` names the roof that binds the dominant kernel: instruction issue under low SIMT efficiency (ncu: DRAM
+        # ~1 % of peak, issue slots 65-70 %). achieved / peak / frac keep the contract's HBM form in algorithmic bytes.
+        "bound": "issue", "kernel": dominant, "achieved": achieved, "peak": peak, "unit": "GB/s",
+        "frac": (achieved / peak) if achieved else None, "traffic": kernels[dominant]["traffic"],
+        "hbm_note": "achieved = algorithmic bytes (reference layout: 48 B nodes, 144 B triangles) / kernel time; the hot "
+                    "scene is L2-resident so `traffic` (ncu DRAM bytes per launch) is far below it -- a normalisation, not the binding roof",
+        "issue": kernels[dominant]["issue"],
+        "kernels": {k: dict(v, frac=(v["achieved"] / peak) if v["achieved"] else None) for k, v in kernels.items()},
+        "algorithmic_bytes_per_segment": bytes_per_seg, "nodes_per_segment": nodes_per_seg,
+        "triangles_per_segment": tris_per_seg, "shadow_rays_per_segment": shadow_per_seg,
+        "nodes_per_shadow_ray": sh_nodes, "triangles_per_shadow_ray": sh_tris,
+        "segments_per_launch": n_px, "batch_lane_utilisation": lane_util,
+    }
+
+
+def timed_passes(ctx, torch, stream, steps, warm):
+    """reset + `warm` untimed passes + `steps` passes between CUDA events on the launching stream"""
+    ctx.reset()
+    ctx.render(warm)
+    torch.cuda.synchronize()
+    a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a0.record(stream)
+    ctx.render(steps)
+    a1.record(stream)
+    a1.synchronize()
+    st = ctx.render_stats()
+    return a0.elapsed_time(a1), (float(st["last_trace_ms"]), float(st["last_shade_ms"]), float(st["last_shadow_ms"]))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=512)
     ap.add_argument("--warmup", type=int, default=16)
-    ap.add_argument("--workload", default="materials_1080p", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--reduce", default="ipc", choices=["ipc", "nccl"])
     ap.add_argument("--split", default="samples", choices=["samples", "tiles", "hybrid"],
@@ -194,6 +354,7 @@ def main():
                          "optional linear-BVH builder (GPU)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-aux", action="store_true")
+    ap.add_argument("--no-dropin", action="store_true", help="skip the e2e_dropin leg (the C++ drop-in's headless run)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     global BVH
@@ -211,11 +372,12 @@ def main():
         if rank != 0:
             return 0
         r = reference_run(args.workload, args.steps, args.warmup)
+        wobj = build_world(args.workload)
+        W0, H0 = (int(x) for x in wobj.cameras[0].resolution)
         line = dict(base)
         line.update({"impl": "reference", "value": r["value"], "ms_per_step": r["ms_per_step"],
-                     "config": {"workload": args.workload, "resolution": list(WORKLOADS[args.workload][1]["resolution"]),
-                                "max_depth": MAX_DEPTH, "light_samples": [1, 1],
-                                "bvh": "reference trees (built by the reference itself)", "sharding": "host threads"},
+                     "config": describe_config(args.workload, wobj, ((W0 + 15) // 16) * ((H0 + 15) // 16) * 256),
+                     "run": {"sharding": "host threads", "engine": "reference CPU engine (oracle/_ref/rz_ref_tool render)"},
                      "cpu_baseline": {"value": r["value"], "unit": "Mrays/s", "cores": r["cores"], "kind": r["kind"],
                                       "sample": r["sample"]},
                      "e2e": {"value": r["value"], "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -230,6 +392,7 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device -- the render path has no CPU fallback")
     torch.cuda.set_device(local_rank)
+    sm_count = torch.cuda.get_device_properties(local_rank).multi_processor_count
     dist = None
     if world > 1:
         dist = parallel.init_process_group("nccl")
@@ -267,19 +430,25 @@ def main():
     rgba_host = torch.empty((H, W, 4), dtype=torch.uint8, pin_memory=True).numpy()
     depth_host = torch.empty((H, W), dtype=torch.float32, pin_memory=True).numpy()
 
-    fused = parallel.FusedResolve(ctx) if (world > 1 and args.reduce == "ipc") else None
+    resolver = None
+    if world > 1 and args.reduce == "ipc":
+        resolver = parallel.SlicedResolve(ctx, rgba_host, depth_host)
 
     def combine():
-        """the one exchange step of the N>1 path: sum the accumulators onto rank 0 (and tone-map there)"""
+        """the one exchange step of the N>1 path: every rank sums and tone-maps its slice of the frame over NVLink
+        (parallel.SlicedResolve), or an NCCL reduce onto rank 0 with --reduce nccl"""
         if world == 1:
             return
-        if fused is not None:
-            fused(want_depth=True)
+        if resolver is not None:
+            resolver()
         else:
             parallel.reduce_accum(ctx.accum_tensor().clone(), dst=0)  # a copy: rendering continues on the original
 
-    # ---- warm-up, then the timed region: K passes (+ the exchange step), device-timed on the launching stream
-    ctx.render(args.warmup)
+    # ---- pre-roll + warm-up (untimed), then the timed region: K passes (+ the exchange step), device-timed on the
+    # launching stream. The pre-roll (2 x max depth passes) puts paths of every depth in flight: the first passes after
+    # a reset trace only coherent camera rays and would flatter the number.
+    warm = PREROLL + args.warmup
+    ctx.render(warm)
     combine()
     barrier()
     alpha0 = float(ctx.read_accum()[..., 3].mean())
@@ -298,8 +467,10 @@ def main():
     ms = ev0.elapsed_time(ev1)
     # per-kernel device time per launch: CUDA events recorded around each stage of (up to 256 of) the timed passes
     st = ctx.render_stats()
-    trace_ms, shade_ms, shadow_ms = float(st["last_trace_ms"]), float(st["last_shade_ms"]), float(st["last_shadow_ms"])
+    stage_ms = (float(st["last_trace_ms"]), float(st["last_shade_ms"]), float(st["last_shadow_ms"]))
     launches = int(st["kernel_launches"]) - launches0
+    if resolver is not None:
+        resolver.wait()
     t_all = torch.tensor([ms, (float(ctx.read_accum()[..., 3].mean()) - alpha0), float(args.steps) * n_px],
                          dtype=torch.float64, device="cuda")
     ms_max, spp_sum, rays_sum = float(t_all[0].item()), float(t_all[1].item()), float(t_all[2].item())
@@ -311,47 +482,10 @@ def main():
     value = rays_sum / (ms_max * 1e-3) / 1e6
     spp_per_s = spp_sum / (ms_max * 1e-3)  # completed camera paths per pixel per second, whole job
 
-    # ---- algorithmic bytes of the dominant kernel: replay the same passes with the counting kernels
-    # (the RNG is counter-based on (seed, pixel, pass): after a reset the same pass indices retrace the same rays)
-    ctx.reset()
-    ctx.render(args.warmup)
-    ctx.set_config(1, 1, MAX_DEPTH, capi.FLAG_COUNT_WORK, seed)
-    ctx.render(args.steps)
-    wc = ctx.work_counters()
-    seg = max(int(wc["segments"]), 1)
-    nodes_per_seg = float(wc["closest_top_nodes"] + wc["closest_mesh_nodes"]) / seg
-    tris_per_seg = float(wc["closest_triangles"]) / seg
-    shadow_per_seg = float(wc["shadow_rays"]) / seg
-    # share of lane-time the whole-warp batches keep busy (work of a ray = pair steps + triangle tests)
-    lane_util = {"closest": float(wc["closest_lane_work"]) / max(int(wc["closest_batch_work"]), 1),
-                 "shadow": float(wc["shadow_lane_work"]) / max(int(wc["shadow_batch_work"]), 1),
-                 "dropped_non_finite_samples": int(wc["invalid_rays"])}
-    bytes_per_seg = B_STATE + nodes_per_seg * B_NODE + tris_per_seg * B_TRI + B_HIT
-    # the shadow kernel in the same currency: per shadow ray the 48-byte queue record, the box and triangle tests of
-    # the any-hit walk (reference layout: 48 B nodes, 144 B triangles) and the 12-byte accumulator update
-    n_shadow = max(int(wc["shadow_rays"]), 1)
-    sh_nodes = float(wc["shadow_top_nodes"] + wc["shadow_mesh_nodes"]) / n_shadow
-    sh_tris = float(wc["shadow_triangles"]) / n_shadow
-    bytes_per_shadow_ray = B_SHADOW_REC + sh_nodes * B_NODE + sh_tris * B_TRI + B_SHADOW_ACC
-    prof = {}
-    prof_path = os.path.join(ROOT, "profiles", "ncu_summary.json")
-    if os.path.exists(prof_path):
-        try:
-            prof = json.load(open(prof_path)).get(args.workload if BVH == "reference" else args.workload + "_sah", {})
-        except Exception:
-            prof = {}
-    kernels = {
-        "k_trace_paths": {"ms": trace_ms, "units_per_launch": n_px, "algorithmic_bytes_per_unit": bytes_per_seg,
-                          "achieved": bytes_per_seg * n_px / (trace_ms * 1e-3) / 1e9 if trace_ms > 0 else None,
-                          "traffic": prof.get("k_trace_paths_dram_bytes_per_launch")},
-        "k_trace_shadow": {"ms": shadow_ms, "units_per_launch": shadow_per_seg * n_px,
-                           "algorithmic_bytes_per_unit": bytes_per_shadow_ray,
-                           "achieved": bytes_per_shadow_ray * shadow_per_seg * n_px / (shadow_ms * 1e-3) / 1e9 if shadow_ms > 0 else None,
-                           "traffic": prof.get("k_trace_shadow_dram_bytes_per_launch")},
-    }
-    dominant = max(kernels, key=lambda k: kernels[k]["ms"])
-    achieved, traffic = kernels[dominant]["achieved"], kernels[dominant]["traffic"]
-    ctx.set_config(1, 1, MAX_DEPTH, capi.FLAG_NONE, seed)
+    # ---- both roofs of the dominant kernel (replay of the same passes with the counting kernels)
+    roofline = work_and_roofline(ctx, capi, args.steps, warm, seed, n_px, stage_ms,
+                                 args.workload if BVH == "reference" else args.workload + "_" + BVH, peak, clocks, sm_count)
+    roofline["peak_source"] = peak_src
 
     # ---- e2e through the boundary with host buffers (every step = one renderWorld-equivalent frame)
     host_arrays = [np.ascontiguousarray(v) for v in flat.values()]
@@ -371,8 +505,9 @@ def main():
         ctx.reset()
         ctx.render(RPP_E2E)
         if world > 1:
-            if fused is not None:
-                fused(want_depth=True)
+            if resolver is not None:
+                resolver()
+                resolver.wait()
             else:
                 parallel.reduce_accum(ctx.accum_tensor(), dst=0)
                 if rank == 0:
@@ -395,61 +530,46 @@ def main():
         dist.all_reduce(e2e_rays, op=dist.ReduceOp.SUM)
     e2e_value = float(e2e_rays.item()) / float(e2e_t.item()) / 1e6
 
-    # ---- secondary workload (config 3 geometry) and the CPU baseline: rank 0, N=1 only
+    # ---- secondary workload, own-tree variants, the drop-in's headless run and the CPU baseline: rank 0, N=1 only
     aux = None
     cpu = None
+    dropin = None
     if rank == 0 and world == 1:
-        if not args.no_aux and args.workload != "heightfield_1m_1080p":
+        n2 = min(args.steps, 256)
+        secondary = SECONDARY_WORKLOAD if args.workload != SECONDARY_WORKLOAD else DEFAULT_WORKLOAD
+        if not args.no_aux:
+            aux = {}
             try:
-                w2 = build_world("heightfield_1m_1080p")
-                ctx.set_scene(w2.flatten())
+                w2 = build_world(secondary)
+                f2 = w2.flatten()
+                ctx.set_scene(f2)
                 ctx.set_camera(w2.camera_struct())
-                ctx.reset()
-                ctx.render(args.warmup)
-                torch.cuda.synchronize()
-                a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                n2 = min(args.steps, 256)
-                a0.record(stream)
-                ctx.render(n2)
-                a1.record(stream)
-                a1.synchronize()
-                st2 = ctx.render_stats()
-                aux = {"workload": "heightfield_1m_1080p", "triangles": int(w2.flatten()["triangles"].shape[0]),
-                       "value": n2 * n_px / (a0.elapsed_time(a1) * 1e-3) / 1e6, "unit": "Mrays/s", "steps": n2,
-                       "trace_ms": float(st2["last_trace_ms"]), "shade_ms": float(st2["last_shade_ms"]),
-                       "shadow_ms": float(st2["last_shadow_ms"])}
+                ms2, stage2 = timed_passes(ctx, torch, stream, n2, warm)
+                aux[secondary] = {"triangles": int(f2["triangles"].shape[0]), "instances": int(f2["instances"].shape[0]),
+                                  "value": n2 * n_px / (ms2 * 1e-3) / 1e6, "unit": "Mrays/s", "steps": n2,
+                                  "stage_ms_per_pass": {"k_trace_paths": stage2[0], "k_shade": stage2[1], "k_trace_shadow": stage2[2]},
+                                  "roofline": work_and_roofline(ctx, capi, n2, warm, seed, n_px, stage2, secondary, peak, clocks, sm_count)}
             except Exception as e:  # the headline line must still be printed
-                aux = {"workload": "heightfield_1m_1080p", "error": repr(e)}
-        # the same workload on the optional SAH trees (RZB_SCENE_OWN_TREES; records equal except exact ties)
-        if not args.no_aux and BVH == "reference":
-            own = {}
-            try:
-                BVH = "sah"
-                for wl in (args.workload, "heightfield_1m_1080p"):
-                    w3 = build_world(wl)
-                    ctx.set_scene(w3.flatten())
-                    ctx.set_camera(w3.camera_struct())
-                    ctx.reset()
-                    ctx.render(args.warmup)
-                    torch.cuda.synchronize()
-                    a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                    n3 = min(args.steps, 256)
-                    a0.record(stream)
-                    ctx.render(n3)
-                    a1.record(stream)
-                    a1.synchronize()
-                    st3 = ctx.render_stats()
-                    own[wl] = {"value": n3 * n_px / (a0.elapsed_time(a1) * 1e-3) / 1e6, "unit": "Mrays/s", "steps": n3,
-                               "trace_ms": float(st3["last_trace_ms"]), "shade_ms": float(st3["last_shade_ms"]),
-                               "shadow_ms": float(st3["last_shadow_ms"])}
-            except Exception as e:
-                own["error"] = repr(e)
-            finally:
-                BVH = "reference"
-            if aux is not None:
+                aux[secondary] = {"error": repr(e)}
+            # the same workloads on the optional SAH trees (RZB_SCENE_OWN_TREES; records equal except exact ties)
+            if BVH == "reference":
+                own = {}
+                try:
+                    BVH = "sah"
+                    for wl in (args.workload, secondary):
+                        w3 = build_world(wl)
+                        ctx.set_scene(w3.flatten())
+                        ctx.set_camera(w3.camera_struct())
+                        ms3, stage3 = timed_passes(ctx, torch, stream, n2, warm)
+                        own[wl] = {"value": n2 * n_px / (ms3 * 1e-3) / 1e6, "unit": "Mrays/s", "steps": n2,
+                                   "stage_ms_per_pass": {"k_trace_paths": stage3[0], "k_shade": stage3[1], "k_trace_shadow": stage3[2]}}
+                except Exception as e:
+                    own["error"] = repr(e)
+                finally:
+                    BVH = "reference"
                 aux["own_trees_sah"] = own
-            else:
-                aux = {"own_trees_sah": own}
+        if not args.no_dropin:
+            dropin = dropin_run(args.workload)
         if not args.no_cpu_baseline:
             try:
                 r = reference_run(args.workload, 8, 1, budget_s=25.0)
@@ -458,33 +578,23 @@ def main():
                 cpu = {"value": None, "unit": "Mrays/s", "cores": os.cpu_count(), "kind": "reference", "sample": "failed: %r" % e}
 
     if rank == 0:
-        working_set = (flat["triangles"].shape[0] * 128 + flat["mesh_nodes"].shape[0] * 32 + n_px * (40 + 20 + 16 + 48)) / 1e6
         line = dict(base)
         line.update({
             "value": value, "ms_per_step": ms_max / args.steps,
-            "config": {"workload": args.workload, "resolution": [W, H], "triangles": int(flat["triangles"].shape[0]),
-                       "instances": int(flat["instances"].shape[0]), "max_depth": MAX_DEPTH, "light_samples": [1, 1],
-                       "bvh": {"reference": "reference trees", "sah": "optional SAH builder (leaf <= 4)",
-                               "lbvh": "optional GPU linear-BVH builder (leaf <= 4)"}[BVH],
-                       "sharding": ("%d row band(s) x %d sample stream(s)" % (bands, streams)) if world > 1 else "single GPU",
-                       "reduce": args.reduce if world > 1 else None,
-                       "l2": "no flush: per-pass working set %.0f MB (path state + queues + accumulator + scene) > 126 MB L2"
-                             % working_set,
-                       "spp_per_s": spp_per_s},
+            "config": describe_config(args.workload, world_obj, ((W + 15) // 16) * ((H + 15) // 16) * 256),
+            "run": {"bvh": {"reference": "reference trees", "sah": "optional SAH builder (leaf <= 4)",
+                            "lbvh": "optional GPU linear-BVH builder (leaf <= 4)"}[BVH],
+                    "sharding": ("%d row band(s) x %d sample stream(s)" % (bands, streams)) if world > 1 else "single GPU",
+                    "reduce": args.reduce if world > 1 else None, "spp_per_s": spp_per_s,
+                    "resolve_ms": resolver.last_ms() if resolver is not None else None},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "step": "set_scene + set_camera + reset + render(%d passes) + resolve to pinned host buffers" % RPP_E2E,
                     "frames": e2e_frames},
+            "e2e_dropin": dropin,
             "gpu_launches": launches,
-            "stage_ms_per_pass": {"k_trace_paths": trace_ms, "k_shade": shade_ms, "k_trace_shadow": shadow_ms},
-            # top level = the kernel with the largest share of the step (the dominant one); both traversal kernels below
-            "roofline": {"bound": "hbm", "kernel": dominant, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": (achieved / peak) if achieved else None, "traffic": traffic, "peak_source": peak_src,
-                         "kernels": {k: dict(v, frac=(v["achieved"] / peak) if v["achieved"] else None) for k, v in kernels.items()},
-                         "algorithmic_bytes_per_segment": bytes_per_seg, "nodes_per_segment": nodes_per_seg,
-                         "triangles_per_segment": tris_per_seg, "shadow_rays_per_segment": shadow_per_seg,
-                         "nodes_per_shadow_ray": sh_nodes, "triangles_per_shadow_ray": sh_tris,
-                         "segments_per_launch": n_px, "batch_lane_utilisation": lane_util},
+            "stage_ms_per_pass": {"k_trace_paths": stage_ms[0], "k_shade": stage_ms[1], "k_trace_shadow": stage_ms[2]},
+            "roofline": roofline,
             "cpu_baseline": cpu, "aux": aux,
         })
         print(json.dumps(line), flush=True)

@@ -26,7 +26,8 @@
 extern "C" {
 #endif
 
-#define RZB_ABI_VERSION 2u /* 2: rzb_scene::flags, own trees, async resolve, incremental update, work counters grew */
+#define RZB_ABI_VERSION 3u /* 2: rzb_scene::flags, own trees, async resolve, incremental update, work counters grew
+                              3: sliced multi-process resolve, mesh-tree refit, tree validation (depth / acyclic) */
 #define RZB_NO_INDEX 0xFFFFFFFFu
 #define RZB_MAX_MATERIALS_PER_INSTANCE 64u /* Instance::materialCapacity(), instance.hpp */
 
@@ -241,6 +242,8 @@ typedef struct rzb_render_stats
 	float last_render_ms;      /* device time of the last rzb_render call (CUDA events on the context stream) */
 	/* per-stage device time of the last rzb_render call, averaged over its sampled passes (ms per launch) */
 	float last_trace_ms, last_shade_ms, last_shadow_ms;
+	float last_sort_ms;        /* ray-order pass between shade and the next trace (0 when ray sorting is off) */
+	float last_exchange_ms;    /* device time of the last rzb_resolve_sliced kernel (includes waiting for the slowest rank) */
 } rzb_render_stats;
 
 /* Work done by rzb_render since the last rzb_reset while RZB_FLAG_COUNT_WORK was set. */
@@ -320,6 +323,21 @@ int rzb_accum_ipc_handle(rzb_ctx* ctx, void* handle_out_64_bytes);
  * kernel. handles = n_peers * 64 bytes. The peers must have finished rendering (barrier) before the call. */
 int rzb_resolve_ipc(rzb_ctx* ctx, const void* handles, uint32_t n_peers,
 	uint8_t* rgba8, float* depth);
+/* Sliced resolve for one process per GPU (no NCCL call, no host round trip; the exchange step of the multi-GPU path):
+ * every rank calls rzb_resolve_sliced with the same `world` and its own `rank`; ONE kernel per rank (1) tells all peers
+ * through flags in peer memory that its passes are done and waits for theirs, (2) sums slice `rank` of ALL ranks'
+ * accumulators over NVLink peer loads, tone-maps it and stores the RGBA8 pixels into rank 0's staging image, (3) tells
+ * all peers it is done and waits for theirs -- so when it ends the peers may render into their accumulators again.
+ * rzb_exchange_ipc_handle exports the context's exchange buffer (flags + staging image; allocated for the current
+ * resolution) as a 64-byte CUDA IPC handle; accum_handles / exchange_handles are world * 64 bytes in rank order
+ * (entry [rank] is ignored). Asynchronous: rank 0's copies into its PINNED buffers (either may be NULL; depth is rank
+ * 0's own first-pass depth) are enqueued behind the kernel; rzb_resolve_sliced_wait blocks until they are done and
+ * reports the device time of the exchange kernel (includes waiting for the slowest rank). Fails with RZB_ERR_STATE when
+ * a peer never arrived (the kernel gives up after a spin limit instead of hanging the GPU). */
+int rzb_exchange_ipc_handle(rzb_ctx* ctx, void* handle_out_64_bytes);
+int rzb_resolve_sliced(rzb_ctx* ctx, uint32_t rank, uint32_t world, const void* accum_handles,
+	const void* exchange_handles, uint8_t* rgba8_pinned, float* depth_pinned);
+int rzb_resolve_sliced_wait(rzb_ctx* ctx, float* exchange_ms_or_null);
 /* pick ray (rayCast kernel, cuda_render_kernel.cu:130-144): instance host index + material slot. */
 int rzb_raycast(rzb_ctx* ctx, uint32_t* instance, uint32_t* material_slot);
 int rzb_synchronize(rzb_ctx* ctx);

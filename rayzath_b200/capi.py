@@ -55,7 +55,7 @@ trace_stats_dtype = np.dtype([("rays", u8), ("top_nodes", u8), ("instances_enter
                               ("triangles", u8)])
 render_stats_dtype = np.dtype([("passes", u8), ("ray_count", u8), ("shadow_rays", u8), ("kernel_launches", u8),
                                ("last_render_ms", f4), ("last_trace_ms", f4), ("last_shade_ms", f4),
-                               ("last_shadow_ms", f4)])
+                               ("last_shadow_ms", f4), ("last_sort_ms", f4), ("last_exchange_ms", f4)])
 
 work_counters_dtype = np.dtype([(n, u8) for n in (
     "closest_top_nodes", "closest_instances", "closest_mesh_nodes", "closest_triangles",
@@ -112,6 +112,9 @@ SYMBOLS = {
     "rzb_resolve_peers": (C.c_int, [_P, C.POINTER(_P), C.c_uint32, _P, _P, C.POINTER(C.c_uint64)]),
     "rzb_accum_ipc_handle": (C.c_int, [_P, _P]),
     "rzb_resolve_ipc": (C.c_int, [_P, _P, C.c_uint32, _P, _P]),
+    "rzb_exchange_ipc_handle": (C.c_int, [_P, _P]),
+    "rzb_resolve_sliced": (C.c_int, [_P, C.c_uint32, C.c_uint32, _P, _P, _P, _P]),
+    "rzb_resolve_sliced_wait": (C.c_int, [_P, C.POINTER(C.c_float)]),
     "rzb_get_work_counters": (C.c_int, [_P, _P]),
     "rzb_raycast": (C.c_int, [_P, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),
     "rzb_synchronize": (C.c_int, [_P]),
@@ -300,6 +303,7 @@ class Context:
         self.device = device
         self.width = self.height = 0
         self._keep = None
+        self.caller_stream = None  # the CUDA stream handed to set_stream (None = the context's private stream)
 
     def close(self):
         if getattr(self, "_h", None):
@@ -329,6 +333,7 @@ class Context:
             self._check(self._l.rzb_set_stream(self._h, None, 0))
         else:
             self._check(self._l.rzb_set_stream(self._h, cuda_stream if cuda_stream else None, 1))
+        self.caller_stream = cuda_stream
 
     # -- world mirror
     def set_scene(self, scene: Dict[str, np.ndarray]):
@@ -475,6 +480,23 @@ class Context:
         blob = b"".join(handles)
         self._check(self._l.rzb_resolve_ipc(self._h, blob if blob else None, len(handles), rgba8.ctypes.data, _ptr(depth)))
         return rgba8, depth
+
+    def exchange_ipc_handle(self) -> bytes:
+        buf = C.create_string_buffer(64)
+        self._check(self._l.rzb_exchange_ipc_handle(self._h, buf))
+        return buf.raw
+
+    def resolve_sliced(self, rank: int, world: int, accum_handles, exchange_handles, rgba8_pinned=None, depth_pinned=None):
+        """rzb_resolve_sliced: the one-kernel-per-rank exchange step (flag barrier in peer memory, slice sum over NVLink,
+        tone map into rank 0's staging image). Asynchronous; resolve_sliced_wait() completes it."""
+        a, e = b"".join(accum_handles), b"".join(exchange_handles)
+        self._check(self._l.rzb_resolve_sliced(self._h, int(rank), int(world), a if a else None, e if e else None,
+                                               _ptr(rgba8_pinned), _ptr(depth_pinned)))
+
+    def resolve_sliced_wait(self) -> float:
+        ms = C.c_float(0.0)
+        self._check(self._l.rzb_resolve_sliced_wait(self._h, C.byref(ms)))
+        return float(ms.value)
 
     def accum_tensor(self):
         """The device accumulator as a torch tensor [h, w, 4] float32 sharing memory (for NCCL collectives)."""

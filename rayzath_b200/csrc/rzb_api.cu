@@ -40,6 +40,13 @@ namespace
 	};
 }
 
+namespace rzb
+{
+	size_t sortTempBytes(uint32_t n, int end_bit);
+	cudaError_t sortPairs(void* temp, size_t temp_bytes, const uint32_t* keys_in, uint32_t* keys_out, const uint32_t* vals_in,
+		uint32_t* vals_out, uint32_t n, int end_bit, cudaStream_t stream);
+}
+
 struct rzb_ctx
 {
 	int device = 0;
@@ -55,6 +62,13 @@ struct rzb_ctx
 	unsigned long long* d_work = nullptr; // RZB_FLAG_COUNT_WORK counters (16 x u64)
 	uint64_t counted_segments = 0;
 	std::vector<std::pair<std::string, void*>> ipc_open; // opened peer accumulators (handle bytes -> mapped pointer)
+	// sliced resolve (rzb_resolve_sliced): exchange buffer = ExchangeHeader + RGBA8 staging image, epoch of the last call
+	void* d_exchange = nullptr;
+	size_t exchange_pixels = 0;
+	uint32_t exchange_epoch = 0;
+	cudaEvent_t ev_exchange[2] = {nullptr, nullptr};
+	float last_exchange_ms = 0.0f;
+	bool exchange_timed = false;
 	std::string error;
 
 	// scene mirror: grow-only device buffers, reused across rzb_set_scene calls (no cudaMalloc/cudaFree when the
@@ -92,11 +106,20 @@ struct rzb_ctx
 	// geometry of the last full rzb_set_scene (RZB_SCENE_KEEP_GEOMETRY)
 	bool geom_valid = false;
 	std::vector<uint32_t> geom_mesh_base;
-	uint32_t geom_top_base = 0, geom_top_capacity = 0, geom_triangle_count = 0;
+	uint32_t geom_top_base = 0, geom_top_capacity = 0, geom_triangle_count = 0, geom_mesh_depth = 0;
 	bool geom_own_trees = false;
 	bool set_carveout = true;      // RZB200_CARVEOUT=0 disables the shared-memory carve-out hint
 	bool own_trees = false;        // rzb_scene::flags & RZB_SCENE_OWN_TREES: conservative box tests
 	bool debug_sync = false;       // RZB200_DEBUG_SYNC: synchronise after every kernel of rzb_render and name the one that faulted
+	// ray sorting between passes (RZB200_SORT=1): keys written by k_shade -> radix sort -> slot order of the next trace
+	bool sort_enabled = false;
+	uint32_t sort_bits = 6;        // RZB200_SORT_BITS: Morton cells per axis = 2^bits
+	bool order_valid = false;      // false until the first sort after a reset
+	DeviceBuffer sort_buf[5];      // keys, keys_out, iota, order, temp
+	uint32_t sort_capacity = 0;
+	float sort_min[3] = {0.0f, 0.0f, 0.0f}, sort_scale = 1.0f;
+	float last_sort_ms = 0.0f;
+	uint32_t x_flags = 0;          // internal DScene::flags bits (kFlag*)
 };
 
 namespace
@@ -303,12 +326,16 @@ extern "C" int rzb_create(int device, rzb_ctx** out)
 	cudaEventCreateWithFlags(&ctx->ev_resolve[0], cudaEventDisableTiming);
 	cudaEventCreateWithFlags(&ctx->ev_resolve[1], cudaEventDisableTiming);
 	if (cudaMallocHost(reinterpret_cast<void**>(&ctx->h_pick), 16) != cudaSuccess) ctx->h_pick = nullptr;
+	else std::memset(ctx->h_pick, 0, 16);
 	if ((e = cudaMalloc(reinterpret_cast<void**>(&ctx->d_work), 128)) != cudaSuccess) { delete ctx; return cudaFail(nullptr, e, "cudaMalloc(work)"); }
 	cudaMemsetAsync(ctx->d_work, 0, 128, ctx->stream);
 	if ((e = cudaMalloc(reinterpret_cast<void**>(&ctx->d_counters), 256)) != cudaSuccess) { delete ctx; return cudaFail(nullptr, e, "cudaMalloc(counters)"); }
 	cudaMemsetAsync(ctx->d_counters, 0, 256, ctx->stream);
 	ctx->debug_sync = std::getenv("RZB200_DEBUG_SYNC") != nullptr;
 	if (const char* env = std::getenv("RZB200_CARVEOUT")) ctx->set_carveout = std::atoi(env) != 0;
+	if (const char* env = std::getenv("RZB200_SORT")) ctx->sort_enabled = std::atoi(env) != 0;
+	if (const char* env = std::getenv("RZB200_SORT_BITS")) ctx->sort_bits = uint32_t(std::min(std::max(std::atoi(env), 1), 7));
+	if (const char* env = std::getenv("RZB200_ANYHIT_ORDER")) ctx->x_flags |= std::atoi(env) == 1 ? kFlagAnyHitNearFirst : 0u;
 	ctx->trace_grid = gridFor(ctx, reinterpret_cast<const void*>(&k_trace_paths<false, false>), kTraceBlock);
 	ctx->shadow_grid = gridFor(ctx, reinterpret_cast<const void*>(&k_trace_shadow<false>), kTraceBlock);
 	ctx->trace_grid_fast = gridFor(ctx, reinterpret_cast<const void*>(&k_trace_paths<false, true>), kTraceBlock);
@@ -333,6 +360,9 @@ extern "C" void rzb_destroy(rzb_ctx* ctx)
 	if (ctx->d_prev_accum) cudaFree(ctx->d_prev_accum);
 	if (ctx->d_prev_depth) cudaFree(ctx->d_prev_depth);
 	for (auto& h : ctx->ipc_open) cudaIpcCloseMemHandle(h.second);
+	if (ctx->d_exchange) cudaFree(ctx->d_exchange);
+	for (auto& b : ctx->sort_buf) if (b.ptr) cudaFree(b.ptr);
+	for (cudaEvent_t ev : ctx->ev_exchange) if (ev) cudaEventDestroy(ev);
 	cudaEventDestroy(ctx->ev_begin);
 	cudaEventDestroy(ctx->ev_end);
 	cudaEventDestroy(ctx->ev_resolve[0]);
@@ -378,6 +408,43 @@ namespace
 	}
 }
 
+namespace
+{
+	// Walks a caller-supplied tree from its root (node 0) and checks what the device traversal relies on: leaves
+	// (count != 0) stay inside [0, leaf_limit); inner nodes (count == 0) have their two children as an adjacent pair at
+	// an odd index; every node is reached at most once (no cycles, no shared subtrees -- nodes no one references are
+	// tolerated). Returns NULL and the depth of the deepest node, or what is wrong.
+	const char* validateTree(const rzb_node* nodes, uint32_t node_count, uint32_t leaf_limit, uint32_t& depth_out)
+	{
+		depth_out = 0;
+		if (node_count == 0) return "no nodes";
+		std::vector<uint8_t> seen(node_count, 0);
+		std::vector<std::pair<uint32_t, uint32_t>> todo;
+		todo.emplace_back(0u, 0u);
+		seen[0] = 1;
+		while (!todo.empty())
+		{
+			const uint32_t i = todo.back().first, depth = todo.back().second;
+			todo.pop_back();
+			depth_out = std::max(depth_out, depth);
+			const rzb_node& n = nodes[i];
+			const uint32_t count = n.type_count & 0x3FFFFFFFu;
+			if (count != 0)
+			{
+				if (uint64_t(n.begin) + count > leaf_limit) return "leaf range outside the object array";
+				continue;
+			}
+			if (uint64_t(n.begin) + 1 >= node_count || (n.begin & 1u) == 0)
+				return "bad child index (children are an adjacent pair at an odd index; a leaf has count != 0, an empty tree has no nodes)";
+			if (seen[n.begin] || seen[n.begin + 1]) return "a node is referenced twice (cycle or shared subtree)";
+			seen[n.begin] = seen[n.begin + 1] = 1;
+			todo.emplace_back(n.begin, depth + 1u);
+			todo.emplace_back(n.begin + 1u, depth + 1u);
+		}
+		return nullptr;
+	}
+}
+
 extern "C" int rzb_set_scene(rzb_ctx* ctx, const rzb_scene* s)
 {
 	if (!ctx || !s) return fail(ctx, RZB_ERR_INVALID, "rzb_set_scene: NULL argument");
@@ -412,6 +479,7 @@ extern "C" int rzb_set_scene(rzb_ctx* ctx, const rzb_scene* s)
 	uint32_t top_base = 0;
 	size_t total_nodes = 0;
 	uint32_t top_capacity = 0;
+	uint32_t mesh_depth = ctx->geom_mesh_depth;
 	if (keep_geometry)
 	{
 		mesh_base = ctx->geom_mesh_base;
@@ -421,6 +489,7 @@ extern "C" int rzb_set_scene(rzb_ctx* ctx, const rzb_scene* s)
 	else
 	{
 		ctx->geom_valid = false; // until this upload has succeeded
+		mesh_depth = 0;
 		table.reserve(s->mesh_count);
 		size_t cursor = 1;
 		uint64_t expect_node = 0;
@@ -432,9 +501,9 @@ extern "C" int rzb_set_scene(rzb_ctx* ctx, const rzb_scene* s)
 				return fail(ctx, RZB_ERR_INVALID, "rzb_set_scene: mesh range outside node/triangle arrays");
 			if (mesh.node_count != 0 && mesh.node_offset < expect_node)
 				return fail(ctx, RZB_ERR_INVALID, "rzb_set_scene: mesh node ranges must be disjoint and ascending");
-			if (mesh.node_count != 0)
+			if (mesh.node_count != 0) expect_node = uint64_t(mesh.node_offset) + mesh.node_count;
+			if (mesh.node_count != 0 && mesh.tri_count != 0) // a mesh without triangles has no tree to walk (its root would be a leaf with count 0)
 			{
-				expect_node = uint64_t(mesh.node_offset) + mesh.node_count;
 				if ((cursor & 1u) == 0) ++cursor;
 				mesh_base[m] = uint32_t(cursor);
 				cursor += mesh.node_count;
@@ -448,40 +517,39 @@ extern "C" int rzb_set_scene(rzb_ctx* ctx, const rzb_scene* s)
 		cursor += top_capacity;
 		if (cursor >= (1u << 30)) return fail(ctx, RZB_ERR_INVALID, "rzb_set_scene: too many nodes");
 		total_nodes = cursor + 1;
+		// every tree must BE a tree (each node reached once from the root: no cycles, no shared subtrees) and the deepest
+		// one bounds the traversal stack (rzb_device.cuh: Stack)
 		for (uint32_t m = 0; m < s->mesh_count; ++m)
 		{
 			const rzb_mesh& mesh = s->meshes[m];
-			for (uint32_t i = 0; i < mesh.node_count; ++i)
-			{
-				const rzb_node& n = s->mesh_nodes[mesh.node_offset + i];
-				const uint32_t count = n.type_count & 0x3FFFFFFFu;
-				if (count != 0)
-				{
-					if (uint64_t(n.begin) + count > mesh.tri_count) return fail(ctx, RZB_ERR_INVALID, "rzb_set_scene: leaf outside mesh triangles");
-				}
-				else if (uint64_t(n.begin) + 1 >= mesh.node_count || (n.begin & 1u) == 0)
-					return fail(ctx, RZB_ERR_INVALID, "rzb_set_scene: bad child index in mesh tree");
-			}
+			if (mesh_base[m] == kNoIndex) continue;
+			uint32_t depth = 0;
+			const char* what = validateTree(s->mesh_nodes + mesh.node_offset, mesh.node_count, mesh.tri_count, depth);
+			if (what) return fail(ctx, RZB_ERR_INVALID, std::string("rzb_set_scene: mesh tree: ") + what);
+			mesh_depth = std::max(mesh_depth, depth);
 		}
+		ctx->geom_mesh_depth = mesh_depth;
 	}
 	// instance tree (small): fixed up on the host
-	std::vector<rzb_node> top_nodes(s->instance_node_count);
-	for (uint32_t i = 0; i < s->instance_node_count; ++i)
+	// (a world without instances has no tree to walk: its nodes, if any, are not looked at)
+	const uint32_t top_node_count = s->instance_count ? s->instance_node_count : 0u;
+	std::vector<rzb_node> top_nodes(top_node_count);
+	uint32_t top_depth = 0;
+	if (top_node_count)
+	{
+		const char* what = validateTree(s->instance_nodes, top_node_count, s->instance_count, top_depth);
+		if (what) return fail(ctx, RZB_ERR_INVALID, std::string("rzb_set_scene: instance tree: ") + what);
+	}
+	for (uint32_t i = 0; i < top_node_count; ++i)
 	{
 		rzb_node n = s->instance_nodes[i];
-		const uint32_t count = n.type_count & 0x3FFFFFFFu;
-		if (count != 0)
-		{
-			if (uint64_t(n.begin) + count > s->instance_count) return fail(ctx, RZB_ERR_INVALID, "rzb_set_scene: leaf outside instances");
-		}
-		else
-		{
-			if (uint64_t(n.begin) + 1 >= s->instance_node_count || (n.begin & 1u) == 0)
-				return fail(ctx, RZB_ERR_INVALID, "rzb_set_scene: bad child index in instance tree");
-			n.begin += top_base;
-		}
+		if ((n.type_count & 0x3FFFFFFFu) == 0u) n.begin += top_base;
 		top_nodes[i] = n;
 	}
+	// one deferred sibling per level of either tree plus the instance-range entry must fit the traversal stack
+	if (top_depth + 1u + mesh_depth + 2u > uint32_t(kSmemStack + kLocalStack))
+		return fail(ctx, RZB_ERR_INVALID, "rzb_set_scene: trees too deep for the traversal stack (instance tree depth + mesh tree depth must stay below "
+			+ std::to_string(kSmemStack + kLocalStack - 2) + ")");
 
 	// ---- instances
 	std::vector<DInstance> insts(s->instance_count);
@@ -588,7 +656,7 @@ extern "C" int rzb_set_scene(rzb_ctx* ctx, const rzb_scene* s)
 				k_iota<<<(s->triangle_count + 255) / 256, 256, 0, ctx->stream>>>(static_cast<uint32_t*>(B[rzb_ctx::kBufTriHost].ptr), s->triangle_count);
 		}
 	}
-	if (s->instance_node_count)
+	if (top_node_count)
 		RZB_CUDA(ctx, cudaMemcpyAsync(d_nodes + 2 * size_t(top_base), top_nodes.data(), top_nodes.size() * 32, cudaMemcpyHostToDevice, ctx->stream));
 	RZB_CUDA(ctx, cudaGetLastError());
 	sc.nodes = d_nodes;
@@ -609,7 +677,7 @@ extern "C" int rzb_set_scene(rzb_ctx* ctx, const rzb_scene* s)
 	sc.default_material = s->default_material;
 	sc.direct_light_count = s->direct_light_count;
 	sc.spot_light_count = s->spot_light_count;
-	sc.flags = ctx->cfg.flags;
+	sc.flags = ctx->cfg.flags | ctx->x_flags;
 	RZB_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); // host staging vectors die at return; the caller may reuse its arrays
 	ctx->sc = sc;
 	if (!keep_geometry)
@@ -623,6 +691,19 @@ extern "C" int rzb_set_scene(rzb_ctx* ctx, const rzb_scene* s)
 	}
 	ctx->own_trees = ctx->geom_own_trees;
 	ctx->has_scene = true;
+	// world bounds (root of the instance tree) for the Morton cells of the ray-order keys: cubic cells
+	if (top_node_count)
+	{
+		const rzb_node& root = s->instance_nodes[0];
+		float extent = 0.0f;
+		for (int k = 0; k < 3; ++k)
+		{
+			ctx->sort_min[k] = root.bb_min[k];
+			extent = std::max(extent, root.bb_max[k] - root.bb_min[k]);
+		}
+		ctx->sort_scale = extent > 0.0f && std::isfinite(extent) ? float(1u << ctx->sort_bits) / extent : 0.0f;
+	}
+	ctx->order_valid = false;
 	return RZB_OK;
 }
 
@@ -672,7 +753,7 @@ extern "C" int rzb_set_config(rzb_ctx* ctx, const rzb_config* config)
 	if (!ctx || !config) return fail(ctx, RZB_ERR_INVALID, "rzb_set_config: NULL argument");
 	if (config->max_depth == 0 || config->max_depth > 255) return fail(ctx, RZB_ERR_INVALID, "rzb_set_config: max_depth must be 1..255");
 	ctx->cfg = *config;
-	ctx->sc.flags = config->flags;
+	ctx->sc.flags = config->flags | ctx->x_flags;
 	return RZB_OK;
 }
 
@@ -716,6 +797,7 @@ extern "C" int rzb_reset(rzb_ctx* ctx)
 	ctx->counted_segments = 0;
 	ctx->launches += 1;
 	ctx->passes = 0;
+	ctx->order_valid = false;
 	ctx->frame_ready = true;
 	return RZB_OK;
 }
@@ -750,7 +832,29 @@ extern "C" int rzb_render(rzb_ctx* ctx, uint32_t passes)
 	// per-stage device timing: up to 256 passes of this call are bracketed by events (4 per sampled pass)
 	const uint32_t stride = (passes + 255u) / 256u;
 	const uint32_t n_sampled = passes ? (passes + stride - 1u) / stride : 0u;
-	while (ctx->ev_stage.size() < size_t(n_sampled) * 4)
+	const uint32_t n_slots = f.slot_end - f.slot_begin;
+	const int sort_end_bit = int(3u * ctx->sort_bits + 3u + 1u);
+	size_t sort_temp = 0;
+	if (ctx->sort_enabled)
+	{
+		sort_temp = sortTempBytes(n_slots, sort_end_bit);
+		if ((rc = ensureBuf(ctx, ctx->sort_buf[4], sort_temp))) return rc;
+		if (ctx->sort_capacity < n_slots || ctx->sort_buf[2].ptr == nullptr)
+		{
+			for (int k = 0; k < 4; ++k)
+				if ((rc = ensureBuf(ctx, ctx->sort_buf[k], size_t(n_slots) * 4))) return rc;
+			ctx->sort_capacity = n_slots;
+			ctx->order_valid = false;
+		}
+		// values = slot indices of the band
+		k_iota_from<<<(n_slots + 255) / 256, 256, 0, ctx->stream>>>(static_cast<uint32_t*>(ctx->sort_buf[2].ptr), n_slots, f.slot_begin);
+		f.sort_keys = static_cast<uint32_t*>(ctx->sort_buf[0].ptr);
+		for (int k = 0; k < 3; ++k) f.sort_min[k] = ctx->sort_min[k];
+		f.sort_scale = ctx->sort_scale;
+		f.sort_bits = ctx->sort_bits;
+	}
+	else { f.sort_keys = nullptr; f.order = nullptr; }
+	while (ctx->ev_stage.size() < size_t(n_sampled) * 5)
 	{
 		cudaEvent_t ev = nullptr;
 		RZB_CUDA(ctx, cudaEventCreate(&ev));
@@ -763,8 +867,9 @@ extern "C" int rzb_render(rzb_ctx* ctx, uint32_t passes)
 	{
 		f.pass_index = uint32_t(ctx->passes);
 		const bool timed = (p % stride) == 0u;
-		cudaEvent_t* ev = timed ? &ctx->ev_stage[size_t(ctx->sampled_passes) * 4] : nullptr;
+		cudaEvent_t* ev = timed ? &ctx->ev_stage[size_t(ctx->sampled_passes) * 5] : nullptr;
 		RZB_CUDA(ctx, cudaMemsetAsync(ctx->d_counters, 0, 12, ctx->stream));
+		f.order = (ctx->sort_enabled && ctx->order_valid) ? static_cast<const uint32_t*>(ctx->sort_buf[3].ptr) : nullptr;
 		if (timed) cudaEventRecord(ev[0], ctx->stream);
 		if (count) { if (fast) k_trace_paths<true, true><<<ctx->trace_grid_fast, kTraceBlock, 0, ctx->stream>>>(ctx->sc, f); else k_trace_paths<true, false><<<ctx->trace_grid, kTraceBlock, 0, ctx->stream>>>(ctx->sc, f); }
 		else { if (fast) k_trace_paths<false, true><<<ctx->trace_grid_fast, kTraceBlock, 0, ctx->stream>>>(ctx->sc, f); else k_trace_paths<false, false><<<ctx->trace_grid, kTraceBlock, 0, ctx->stream>>>(ctx->sc, f); }
@@ -787,6 +892,16 @@ extern "C" int rzb_render(rzb_ctx* ctx, uint32_t passes)
 		}
 		if (timed) cudaEventRecord(ev[2], ctx->stream);
 		ctx->launches += 2;
+		if (ctx->sort_enabled)
+		{
+			// order of the NEXT pass's closest-hit queries: radix sort of (ray key, slot)
+			RZB_CUDA(ctx, sortPairs(ctx->sort_buf[4].ptr, sort_temp, static_cast<const uint32_t*>(ctx->sort_buf[0].ptr),
+				static_cast<uint32_t*>(ctx->sort_buf[1].ptr), static_cast<const uint32_t*>(ctx->sort_buf[2].ptr),
+				static_cast<uint32_t*>(ctx->sort_buf[3].ptr), n_slots, sort_end_bit, ctx->stream));
+			ctx->order_valid = true;
+			ctx->launches += 4; // histogram + one onesweep pass per 8 key bits
+		}
+		if (timed) cudaEventRecord(ev[4], ctx->stream);
 		if (lights)
 		{
 			if (count) k_trace_shadow<true><<<ctx->shadow_grid, kTraceBlock, 0, ctx->stream>>>(ctx->sc, f);
@@ -976,16 +1091,18 @@ extern "C" int rzb_get_render_stats(rzb_ctx* ctx, rzb_render_stats* out)
 	{
 		float ms = 0.0f;
 		if (cudaEventElapsedTime(&ms, ctx->ev_begin, ctx->ev_end) == cudaSuccess) ctx->last_render_ms = ms;
-		double t = 0.0, sh = 0.0, sd = 0.0;
+		double t = 0.0, sh = 0.0, sd = 0.0, so = 0.0;
 		for (uint32_t i = 0; i < ctx->sampled_passes; ++i)
 		{
-			const cudaEvent_t* ev = &ctx->ev_stage[size_t(i) * 4];
+			const cudaEvent_t* ev = &ctx->ev_stage[size_t(i) * 5];
 			if (cudaEventElapsedTime(&ms, ev[0], ev[1]) == cudaSuccess) t += ms;
 			if (cudaEventElapsedTime(&ms, ev[1], ev[2]) == cudaSuccess) sh += ms;
-			if (ctx->last_had_shadow && cudaEventElapsedTime(&ms, ev[2], ev[3]) == cudaSuccess) sd += ms;
+			if (cudaEventElapsedTime(&ms, ev[2], ev[4]) == cudaSuccess) so += ms;
+			if (ctx->last_had_shadow && cudaEventElapsedTime(&ms, ev[4], ev[3]) == cudaSuccess) sd += ms;
 		}
 		if (ctx->sampled_passes)
 		{
+			ctx->last_sort_ms = float(so / ctx->sampled_passes);
 			ctx->last_trace_ms = float(t / ctx->sampled_passes);
 			ctx->last_shade_ms = float(sh / ctx->sampled_passes);
 			ctx->last_shadow_ms = float(sd / ctx->sampled_passes);
@@ -999,6 +1116,8 @@ extern "C" int rzb_get_render_stats(rzb_ctx* ctx, rzb_render_stats* out)
 	out->last_trace_ms = ctx->last_trace_ms;
 	out->last_shade_ms = ctx->last_shade_ms;
 	out->last_shadow_ms = ctx->last_shadow_ms;
+	out->last_sort_ms = ctx->last_sort_ms;
+	out->last_exchange_ms = ctx->last_exchange_ms;
 	return RZB_OK;
 }
 
@@ -1055,6 +1174,124 @@ extern "C" int rzb_resolve_ipc(rzb_ctx* ctx, const void* handles, uint32_t n_pee
 	return tonemapAndCopy(ctx, peers, rgba8, depth);
 }
 
+namespace
+{
+	int openIpc(rzb_ctx* ctx, const char* handle64, void** mapped_out)
+	{
+		const std::string key(handle64, 64);
+		for (auto& h : ctx->ipc_open)
+			if (h.first == key) { *mapped_out = h.second; return RZB_OK; }
+		cudaIpcMemHandle_t h;
+		std::memcpy(&h, key.data(), 64);
+		void* mapped = nullptr;
+		RZB_CUDA(ctx, cudaIpcOpenMemHandle(&mapped, h, cudaIpcMemLazyEnablePeerAccess));
+		ctx->ipc_open.emplace_back(key, mapped);
+		*mapped_out = mapped;
+		return RZB_OK;
+	}
+	int ensureExchange(rzb_ctx* ctx)
+	{
+		const size_t n = size_t(ctx->cam.width) * ctx->cam.height;
+		if (ctx->d_exchange && ctx->exchange_pixels == n) return RZB_OK;
+		if (ctx->d_exchange) cudaFree(ctx->d_exchange);
+	for (auto& b : ctx->sort_buf) if (b.ptr) cudaFree(b.ptr);
+		ctx->d_exchange = nullptr;
+		ctx->exchange_pixels = 0;
+		RZB_CUDA(ctx, cudaMalloc(&ctx->d_exchange, sizeof(ExchangeHeader) + n * 4));
+		RZB_CUDA(ctx, cudaMemset(ctx->d_exchange, 0, sizeof(ExchangeHeader)));
+		ctx->exchange_pixels = n;
+		ctx->exchange_epoch = 0;
+		return RZB_OK;
+	}
+}
+
+extern "C" int rzb_exchange_ipc_handle(rzb_ctx* ctx, void* handle_out)
+{
+	if (!ctx || !handle_out) return fail(ctx, RZB_ERR_INVALID, "rzb_exchange_ipc_handle: NULL argument");
+	if (!ctx->has_camera) return fail(ctx, RZB_ERR_STATE, "rzb_exchange_ipc_handle: no camera");
+	DeviceGuard guard(ctx->device);
+	const int rc = ensureExchange(ctx);
+	if (rc) return rc;
+	cudaIpcMemHandle_t h;
+	RZB_CUDA(ctx, cudaIpcGetMemHandle(&h, ctx->d_exchange));
+	std::memcpy(handle_out, &h, 64);
+	return RZB_OK;
+}
+
+extern "C" int rzb_resolve_sliced(rzb_ctx* ctx, uint32_t rank, uint32_t world, const void* accum_handles,
+	const void* exchange_handles, uint8_t* rgba8_pinned, float* depth_pinned)
+{
+	if (!ctx || world == 0 || world > 8 || rank >= world || (world > 1 && (!accum_handles || !exchange_handles)))
+		return fail(ctx, RZB_ERR_INVALID, "rzb_resolve_sliced: bad arguments");
+	if (!ctx->has_camera) return fail(ctx, RZB_ERR_STATE, "rzb_resolve_sliced: no camera");
+	DeviceGuard guard(ctx->device);
+	int rc = ensureExchange(ctx);
+	if (rc) return rc;
+	SlicedArgs a{};
+	for (uint32_t r = 0; r < world; ++r)
+	{
+		if (r == rank)
+		{
+			a.accum[r] = ctx->frame.accum;
+			a.header[r] = static_cast<ExchangeHeader*>(ctx->d_exchange);
+			continue;
+		}
+		void* m = nullptr;
+		if ((rc = openIpc(ctx, static_cast<const char*>(accum_handles) + size_t(r) * 64, &m))) return rc;
+		a.accum[r] = static_cast<const float4*>(m);
+		if ((rc = openIpc(ctx, static_cast<const char*>(exchange_handles) + size_t(r) * 64, &m))) return rc;
+		a.header[r] = static_cast<ExchangeHeader*>(m);
+	}
+	const uint32_t n = ctx->cam.width * ctx->cam.height;
+	a.root_rgba = reinterpret_cast<uchar4*>(reinterpret_cast<char*>(a.header[0]) + sizeof(ExchangeHeader));
+	a.rank = rank; a.world = world;
+	a.epoch = ++ctx->exchange_epoch;
+	// slices of whole 32-pixel groups, so that every 128-byte line of the staging image has one writer
+	const uint32_t groups = (n + 31u) / 32u;
+	a.begin = std::min(n, uint32_t((uint64_t(groups) * rank / world) * 32u));
+	a.end = std::min(n, uint32_t((uint64_t(groups) * (rank + 1u) / world) * 32u));
+	a.aperture_area = ctx->cam.aperture * ctx->cam.aperture * 3.14159265358979323846f;
+	a.exposure_time = ctx->cam.exposure_time;
+	a.spin_limit = 20ull * 1000ull * 1000ull * 1000ull; // ~10 s of SM clock: a peer that never arrives ends the wait
+	for (cudaEvent_t& ev : ctx->ev_exchange)
+		if (!ev) RZB_CUDA(ctx, cudaEventCreate(&ev));
+	RZB_CUDA(ctx, cudaEventRecord(ctx->ev_exchange[0], ctx->stream));
+	const uint32_t slice = a.end - a.begin;
+	const int grid = int(std::max<uint32_t>(1u, std::min<uint32_t>((slice + 255u) / 256u, uint32_t(ctx->sm_count) * 4u)));
+	k_resolve_sliced<<<grid, 256, 0, ctx->stream>>>(a);
+	ctx->launches += 1;
+	RZB_CUDA(ctx, cudaGetLastError());
+	RZB_CUDA(ctx, cudaEventRecord(ctx->ev_exchange[1], ctx->stream));
+	ctx->exchange_timed = true;
+	if (rank == 0)
+	{
+		if (rgba8_pinned) RZB_CUDA(ctx, cudaMemcpyAsync(rgba8_pinned, a.root_rgba, size_t(n) * 4, cudaMemcpyDeviceToHost, ctx->stream));
+		if (depth_pinned) RZB_CUDA(ctx, cudaMemcpyAsync(depth_pinned, ctx->frame.depth, size_t(n) * 4, cudaMemcpyDeviceToHost, ctx->stream));
+	}
+	// completion + "a peer never arrived" travel through slot 0 of the asynchronous-resolve protocol
+	if (ctx->h_pick)
+		RZB_CUDA(ctx, cudaMemcpyAsync(ctx->h_pick + 3, &static_cast<ExchangeHeader*>(ctx->d_exchange)->timed_out, 4, cudaMemcpyDeviceToHost, ctx->stream));
+	RZB_CUDA(ctx, cudaEventRecord(ctx->ev_resolve[0], ctx->stream));
+	return RZB_OK;
+}
+
+extern "C" int rzb_resolve_sliced_wait(rzb_ctx* ctx, float* exchange_ms_or_null)
+{
+	if (!ctx) return RZB_ERR_INVALID;
+	DeviceGuard guard(ctx->device);
+	RZB_CUDA(ctx, cudaEventSynchronize(ctx->ev_resolve[0]));
+	if (ctx->exchange_timed)
+	{
+		float ms = 0.0f;
+		if (cudaEventElapsedTime(&ms, ctx->ev_exchange[0], ctx->ev_exchange[1]) == cudaSuccess) ctx->last_exchange_ms = ms;
+		cudaGetLastError();
+	}
+	if (exchange_ms_or_null) *exchange_ms_or_null = ctx->last_exchange_ms;
+	if (ctx->h_pick && ctx->h_pick[3] != 0u)
+		return fail(ctx, RZB_ERR_STATE, "rzb_resolve_sliced: a peer rank never reached the exchange step (spin limit hit); the frame is incomplete");
+	return RZB_OK;
+}
+
 extern "C" int rzb_timings(rzb_ctx* ctx, char* buf, size_t buf_size)
 {
 	if (!ctx || !buf || buf_size == 0) return RZB_ERR_INVALID;
@@ -1086,8 +1323,11 @@ namespace
 			o[i] = make_float4(origins[3 * size_t(i)], origins[3 * size_t(i) + 1], origins[3 * size_t(i) + 2], near_far[2 * size_t(i)]);
 			d[i] = make_float4(directions[3 * size_t(i)], directions[3 * size_t(i) + 1], directions[3 * size_t(i) + 2], near_far[2 * size_t(i) + 1]);
 		}
-		RZB_CUDA(ctx, cudaMemcpy(ctx->scratch[0].ptr, o.data(), size_t(n) * 16, cudaMemcpyHostToDevice));
-		RZB_CUDA(ctx, cudaMemcpy(ctx->scratch[1].ptr, d.data(), size_t(n) * 16, cudaMemcpyHostToDevice));
+		// on the context's stream (a non-blocking stream has no implicit ordering with the legacy default stream); the
+		// staging vectors die at return, so wait for the copies here -- the kernels that follow are stream-ordered anyway
+		RZB_CUDA(ctx, cudaMemcpyAsync(ctx->scratch[0].ptr, o.data(), size_t(n) * 16, cudaMemcpyHostToDevice, ctx->stream));
+		RZB_CUDA(ctx, cudaMemcpyAsync(ctx->scratch[1].ptr, d.data(), size_t(n) * 16, cudaMemcpyHostToDevice, ctx->stream));
+		RZB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
 		return RZB_OK;
 	}
 }

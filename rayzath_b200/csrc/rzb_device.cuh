@@ -118,7 +118,10 @@ namespace rzb
 
 	// ---- short stack: first kSmemStack entries per thread in shared memory (interleaved by thread so a
 	// warp's pushes hit 32 consecutive 8-byte words), the rest in local memory. Depth bound: two trees of
-	// depth <= 33 (max_depth 31 in both builders) plus one instance-range entry.
+	// depth <= 33 (max_depth 31 in both builders) plus one instance-range entry. rzb_set_scene REJECTS scenes whose
+	// trees could need more than kSmemStack + kLocalStack entries (depth of the instance tree + 1 + depth of the deepest
+	// mesh tree, computed on the host; children must follow their parent, so trees are acyclic), so push never
+	// overflows for an accepted scene; the index clamps below only keep a corrupted tree from reading out of bounds.
 	// Shared memory taken here is L1 taken from the node / triangle fetches (one 256 KB array per SM): measured on B200
 	// at 1080p, entries in shared memory 20 / 12 / 8 / 4 / 2 -> materials scene 1058 / 1100 / 1108 / 1103 / 1088 Mrays/s,
 	// 1M triangles 1140 / 1159 / 1161 / 1153 / 1135 (at 8 blocks per SM the 20-entry stack left the shadow kernel
@@ -144,19 +147,19 @@ namespace rzb
 		__device__ __forceinline__ void push(uint32_t a, uint32_t b)
 		{
 			if (sp < kSmemStack) smem[sp * kTraceBlock] = make_uint2(a, b);
-			else if (sp - kSmemStack < kLocalStack) local[sp - kSmemStack] = make_uint2(a, b);
+			else local[min(sp - kSmemStack, kLocalStack - 1)] = make_uint2(a, b);
 			++sp;
 		}
 		__device__ __forceinline__ uint2 pop()
 		{
 			--sp;
 			if (sp < kSmemStack) return smem[sp * kTraceBlock];
-			return local[sp - kSmemStack];
+			return local[min(sp - kSmemStack, kLocalStack - 1)];
 		}
 		__device__ __forceinline__ uint2 peek() const
 		{
 			if (sp - 1 < kSmemStack) return smem[(sp - 1) * kTraceBlock];
-			return local[sp - 1 - kSmemStack];
+			return local[min(sp - 1 - kSmemStack, kLocalStack - 1)];
 		}
 	};
 

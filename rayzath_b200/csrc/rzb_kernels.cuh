@@ -57,7 +57,39 @@ namespace rzb
 
 		uint32_t max_depth, direct_samples, spot_samples;
 		uint64_t seed;
+		// ray sorting (optional): k_shade writes one key per slot, a radix sort turns them into `order`, the next
+		// pass's k_trace_paths pulls slots through it (NULL = slot order)
+		uint32_t* sort_keys;
+		const uint32_t* order;
+		float sort_min[3], sort_scale; // Morton cells: cubic, (o - sort_min) * sort_scale in [0, 2^sort_bits)
+		uint32_t sort_bits;            // cells per axis = 2^sort_bits
 	};
+
+	// Key of a ray for the order pass. Regenerated camera rays keep their tile order (they are coherent as they are);
+	// bounce rays are grouped by the Morton cell of their origin, then by direction octant; slots without a pixel last.
+	constexpr uint32_t kSortInvalid = 0xFFFFFFFFu;
+	__device__ __forceinline__ uint32_t spread3(uint32_t v)
+	{
+		v &= 0x3FFu;
+		v = (v | (v << 16)) & 0x030000FFu;
+		v = (v | (v << 8)) & 0x0300F00Fu;
+		v = (v | (v << 4)) & 0x030C30C3u;
+		v = (v | (v << 2)) & 0x09249249u;
+		return v;
+	}
+	__device__ __forceinline__ uint32_t ray_sort_key(const DFrame& f, const uint32_t slot, const bool camera_ray,
+		const float3 o, const float3 d)
+	{
+		const uint32_t cell_bits = 3u * f.sort_bits + 3u;
+		if (camera_ray) return slot >> 5; // < 2^18 up to 8.3M slots
+		const float top = float((1u << f.sort_bits) - 1u);
+		const uint32_t cx = uint32_t(fminf(fmaxf((o.x - f.sort_min[0]) * f.sort_scale, 0.0f), top));
+		const uint32_t cy = uint32_t(fminf(fmaxf((o.y - f.sort_min[1]) * f.sort_scale, 0.0f), top));
+		const uint32_t cz = uint32_t(fminf(fmaxf((o.z - f.sort_min[2]) * f.sort_scale, 0.0f), top));
+		const uint32_t morton = (spread3(cx) << 2) | (spread3(cy) << 1) | spread3(cz);
+		const uint32_t octant = (uint32_t(d.x < 0.0f) << 2) | (uint32_t(d.y < 0.0f) << 1) | uint32_t(d.z < 0.0f);
+		return (1u << cell_bits) | (morton << 3) | octant;
+	}
 
 	// slot -> pixel: 256-slot chunks cover 16x16 pixels (8 tiles of 8x4, 2 across x 4 down); a warp works through one
 	// chunk at a time, so all its rays start in one small screen region
@@ -131,6 +163,11 @@ namespace rzb
 		const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
 		if (i < n) out[i] = i;
 	}
+	__global__ void k_iota_from(uint32_t* __restrict__ out, uint32_t n, uint32_t first)
+	{
+		const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+		if (i < n) out[i] = first + i;
+	}
 
 	// ---------------------------------------------------------------- k_reset
 	__global__ void __launch_bounds__(128) k_reset(DFrame f, uint32_t world_material)
@@ -198,7 +235,8 @@ namespace rzb
 		{
 			const uint32_t base = f.slot_begin + warp_batch(&f.counters[0]);
 			if (base >= f.slot_end) break;
-			const uint32_t slot = base + (threadIdx.x & 31u);
+			uint32_t slot = base + (threadIdx.x & 31u);
+			if (f.order != nullptr && slot < f.slot_end) slot = f.order[slot - f.slot_begin];
 			uint32_t x, y;
 			const bool active = slot < f.slot_end && slot_to_pixel(f, slot, x, y);
 			float4 so = make_float4(0.0f, 0.0f, 0.0f, 0.0f), sd = make_float4(0.0f, 0.0f, 1.0f, 0.0f);
@@ -471,6 +509,8 @@ namespace rzb
 			f.st_d[slot] = make_float4(next_d.x, next_d.y, next_d.z, thr.x);
 			f.st_c[slot] = make_float2(thr.y, thr.z);
 		}
+		if (f.sort_keys != nullptr && slot < f.slot_end)
+			f.sort_keys[slot - f.slot_begin] = valid ? ray_sort_key(f, slot, depth == 0u, next_o, next_d) : kSortInvalid;
 	}
 
 	// ---------------------------------------------------------------- k_reproject
@@ -554,6 +594,18 @@ namespace rzb
 		const float4* accum[8];
 		uint32_t count;
 	};
+	// ComputeFinalColor: divide by the sample count, then three separate multiplications, then c/(c+1);
+	// kept in this order (no FMA possible: pure mul/div chain) so RGBA8 truncation matches the oracle bit for bit
+	__device__ __forceinline__ uchar4 tonemap_pixel(const float4 p, const float aperture_area, const float exposure_time)
+	{
+		const float a = p.w == 0.0f ? 1.0f : p.w;
+		float r = fdiv(p.x, a), g = fdiv(p.y, a), b = fdiv(p.z, a);
+		r = fmul(fmul(fmul(r, aperture_area), exposure_time), 1.0e5f);
+		g = fmul(fmul(fmul(g, aperture_area), exposure_time), 1.0e5f);
+		b = fmul(fmul(fmul(b, aperture_area), exposure_time), 1.0e5f);
+		r = fdiv(r, fadd(r, 1.0f)); g = fdiv(g, fadd(g, 1.0f)); b = fdiv(b, fadd(b, 1.0f));
+		return make_uchar4((unsigned char)(fmul(r, 255.0f)), (unsigned char)(fmul(g, 255.0f)), (unsigned char)(fmul(b, 255.0f)), 255);
+	}
 	__global__ void k_tonemap(const float4* __restrict__ accum, PeerList peers, uchar4* __restrict__ rgba,
 		uint32_t n_pixels, float aperture_area, float exposure_time)
 	{
@@ -565,16 +617,99 @@ namespace rzb
 			const float4 q = peers.accum[k][i]; // peer-mapped address: the load crosses NVLink
 			p.x += q.x; p.y += q.y; p.z += q.z; p.w += q.w;
 		}
-		// ComputeFinalColor: divide by the sample count, then three separate multiplications, then c/(c+1);
-		// kept in this order (no FMA possible: pure mul/div chain) so RGBA8 truncation matches the oracle bit for bit
-		const float a = p.w == 0.0f ? 1.0f : p.w;
-		float r = fdiv(p.x, a), g = fdiv(p.y, a), b = fdiv(p.z, a);
-		r = fmul(fmul(fmul(r, aperture_area), exposure_time), 1.0e5f);
-		g = fmul(fmul(fmul(g, aperture_area), exposure_time), 1.0e5f);
-		b = fmul(fmul(fmul(b, aperture_area), exposure_time), 1.0e5f);
-		r = fdiv(r, fadd(r, 1.0f)); g = fdiv(g, fadd(g, 1.0f)); b = fdiv(b, fadd(b, 1.0f));
-		rgba[i] = make_uchar4((unsigned char)(fmul(r, 255.0f)), (unsigned char)(fmul(g, 255.0f)), (unsigned char)(fmul(b, 255.0f)), 255);
+		rgba[i] = tonemap_pixel(p, aperture_area, exposure_time);
 	}
+	// ---------------------------------------------------------------- k_resolve_sliced
+	// The exchange step of the one-process-per-GPU path as ONE kernel per rank, no NCCL call and no host round trip:
+	//   1. barrier in   every rank tells every peer "my passes are done" by storing the call's epoch into the peer's
+	//                   exchange header over NVLink; every block waits until all ranks have arrived in ITS OWN header
+	//   2. slice        rank r sums pixels [begin, end) of ALL ranks' accumulators (peer loads over NVLink: all-to-all,
+	//                   every GPU pulls (N-1)/N of one frame instead of rank 0 pulling N-1 frames), tone-maps them and
+	//                   stores the RGBA8 pixels into the root's staging image (peer stores for r != 0)
+	//   3. barrier out  the last block of the rank tells every peer "I am done with your accumulator and my pixels are in
+	//                   the root's image" and waits for the same from all peers: when the kernel ends, peers may touch
+	//                   their accumulators again and the root may copy the image to the host.
+	// Flags only ever grow (epoch = number of the call), so nothing has to be reset between calls.
+	struct ExchangeHeader
+	{
+		uint32_t arrive[8];   // [r]: last epoch rank r has finished rendering for
+		uint32_t done[8];     // [r]: last epoch rank r has finished reading / writing for
+		uint32_t finished_blocks;
+		uint32_t timed_out;   // a peer never showed up (spin limit): the frame is incomplete
+		uint32_t _pad[46];
+	};
+	static_assert(sizeof(ExchangeHeader) == 256, "ExchangeHeader");
+	struct SlicedArgs
+	{
+		const float4* accum[8];    // all ranks, this rank's own first-hand pointer at [rank]
+		ExchangeHeader* header[8]; // all ranks
+		uchar4* root_rgba;         // staging image in the root's exchange buffer
+		uint32_t rank, world, epoch;
+		uint32_t begin, end;       // this rank's pixel slice
+		float aperture_area, exposure_time;
+		unsigned long long spin_limit; // clock64 ticks
+	};
+	__device__ __forceinline__ void store_flag_sys(uint32_t* p, uint32_t v)
+	{
+		asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+	}
+	__device__ __forceinline__ uint32_t load_flag_sys(const uint32_t* p)
+	{
+		uint32_t v;
+		asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+		return v;
+	}
+	__device__ __forceinline__ bool wait_flags(const uint32_t* flags, uint32_t world, uint32_t epoch, unsigned long long limit)
+	{
+		// threads 0..world-1 each watch one flag of this rank's own header
+		bool ok = true;
+		if (threadIdx.x < world)
+		{
+			const long long t0 = clock64();
+			while (int32_t(load_flag_sys(flags + threadIdx.x) - epoch) < 0)
+			{
+				if ((unsigned long long)(clock64() - t0) > limit) { ok = false; break; }
+				__nanosleep(100);
+			}
+		}
+		return ok;
+	}
+	__global__ void __launch_bounds__(256) k_resolve_sliced(SlicedArgs a)
+	{
+		ExchangeHeader* own = a.header[a.rank];
+		if (blockIdx.x == 0 && threadIdx.x < a.world)
+		{
+			__threadfence_system();
+			store_flag_sys(&a.header[threadIdx.x]->arrive[a.rank], a.epoch);
+		}
+		if (!wait_flags(own->arrive, a.world, a.epoch, a.spin_limit)) own->timed_out = 1u;
+		__syncthreads();
+		for (uint32_t i = a.begin + blockIdx.x * blockDim.x + threadIdx.x; i < a.end; i += gridDim.x * blockDim.x)
+		{
+			float4 p = __ldcv(a.accum[a.rank] + i);
+			for (uint32_t r = 0; r < a.world; ++r)
+			{
+				if (r == a.rank) continue;
+				const float4 q = __ldcv(a.accum[r] + i); // peer-mapped address: the load crosses NVLink
+				p.x += q.x; p.y += q.y; p.z += q.z; p.w += q.w;
+			}
+			a.root_rgba[i] = tonemap_pixel(p, a.aperture_area, a.exposure_time);
+		}
+		__threadfence_system();
+		__syncthreads();
+		__shared__ bool last;
+		if (threadIdx.x == 0) last = atomicAdd(&own->finished_blocks, 1u) == gridDim.x - 1u;
+		__syncthreads();
+		if (!last) return;
+		if (threadIdx.x == 0) own->finished_blocks = 0u;
+		if (threadIdx.x < a.world)
+		{
+			__threadfence_system();
+			store_flag_sys(&a.header[threadIdx.x]->done[a.rank], a.epoch);
+		}
+		if (!wait_flags(own->done, a.world, a.epoch, a.spin_limit)) own->timed_out = 1u;
+	}
+
 	__global__ void k_accum_add(float4* __restrict__ accum, const float4* __restrict__ other, uint32_t n)
 	{
 		const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;

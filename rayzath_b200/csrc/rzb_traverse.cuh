@@ -31,6 +31,8 @@ namespace rzb
 {
 	constexpr float kSlabMargin = 4.0e-7f; // > 2 ulp relative (2^-22 = 2.4e-7)
 	constexpr float kInf = __builtin_huge_valf();
+	// internal bits of DScene::flags (above the public RZB_FLAG_* bits)
+	constexpr uint32_t kFlagAnyHitNearFirst = 1u << 16;
 
 	// exact predicate (the reference's arithmetic); bit 0 = box, bit 1 = range; tmin returned through the reference
 	__device__ __noinline__ uint32_t slab_exact(const float4 n0, const float4 n1, const V3 o, const V3 d,
@@ -188,7 +190,10 @@ namespace rzb
 				const bool h1 = slab_hit<FAST>(p2, p3, t.o, t.d, t.rcp, t.near_, t.far_, t.margin, tm1);
 				// near child first: `flip` = the second child is the near one
 				// own trees (FAST): nearer entry first; reference trees: by ray sign on the split axis, as the reference does
-				const bool flip = !ANY && (FAST ? (h0 && h1 && tm1 < tm0) : ((t.sbits >> (t.cur_tc >> 30)) & 1u) != 0u);
+				// any hit: the result does not depend on the order; RZB_FLAG_X_ANYHIT_NEAR_FIRST (experiment switch, set by the
+				// context from RZB200_ANYHIT_ORDER) visits the nearer entry first instead of the first child
+				const bool flip = ANY ? ((sc.flags & kFlagAnyHitNearFirst) != 0u && h0 && h1 && tm1 < tm0)
+					: (FAST ? (h0 && h1 && tm1 < tm0) : ((t.sbits >> (t.cur_tc >> 30)) & 1u) != 0u);
 				const bool hit_a = flip ? h1 : h0, hit_b = flip ? h0 : h1;
 				if (hit_a)
 				{

@@ -159,7 +159,13 @@ namespace RayZath::Cuda
 				{
 					rzb_ctx* c = cs.ctxs[d];
 					if (!cs.scene_current)
-						check(c, rzb_set_scene(c, cs.geometry_version == m_geometry_version ? &scene_update : &scene), "rzb_set_scene");
+					{
+						// geometry unchanged: send instances / materials / lights only. When the instance tree has outgrown the
+						// room the last full upload reserved for it (RZB_ERR_STATE), send the whole scene, which re-reserves.
+						int rc = cs.geometry_version == m_geometry_version ? rzb_set_scene(c, &scene_update) : RZB_ERR_STATE;
+						if (rc == RZB_ERR_STATE) rc = rzb_set_scene(c, &scene);
+						check(c, rc, "rzb_set_scene");
+					}
 					// one disjoint sample stream per device
 					rzb_config cfg = rzb_host::flattenConfig(config, m_seed + 0x9E3779B97F4A7C15ull * (uint64_t(ci) * 64 + d));
 					cfg.flags |= RZB_FLAG_TEMPORAL_REPROJECTION; // as the reference: every restart blends the replaced frame in

@@ -6,7 +6,12 @@
 //     frame 0: 4 renderWorld calls on the loaded scene (sync = true)
 //     frame 1: every instance moved by (0.25, 0.1, 0), first material recoloured, 4 calls (sync = true)
 //     frame 2: 4 more calls with sync = false, then one sync = true call
+//     frame 3 (only with a third argument N): N more instances of the first mesh are created -- no mesh edit, so the
+//              upload is incremental until the instance tree outgrows the room reserved for it (1024 nodes), where the
+//              engine must fall back to a full upload instead of failing -- then 4 calls (sync = true)
 #include <cstdio>
+#include <cstdlib>
+#include <string>
 #include <fstream>
 #include <iostream>
 #include <vector>
@@ -48,8 +53,27 @@ int main(int argc, char* argv[])
 		for (int i = 0; i < 4; ++i) engine.renderWorld(RZ::Engine::RenderEngine::CUDAGPU, true, false);
 		engine.renderWorld(RZ::Engine::RenderEngine::CUDAGPU, true, true);
 		append(out, *cameras[0]);
-		std::printf("{\"width\": %u, \"height\": %u, \"rays\": %llu}\n", cameras[0]->width(), cameras[0]->height(),
-			(unsigned long long)cameras[0]->rayCount());
+		const unsigned long long rays_frame2 = cameras[0]->rayCount();
+		uint32_t grown = 0;
+		if (argc > 3)
+		{
+			const int extra = std::atoi(argv[3]);
+			RayZath::Engine::Handle<RZ::Mesh> mesh;
+			RayZath::Engine::Handle<RZ::Material> mat;
+			for (uint32_t i = 0; i < instances.count() && !mesh; ++i)
+				if (instances[i] && instances[i]->mesh()) { mesh = instances[i]->mesh(); mat = instances[i]->material(0); }
+			for (int i = 0; i < extra; ++i)
+			{
+				const float x = float(i % 40) * 0.3f - 6.0f, z = float(i / 40) * 0.3f - 1.0f;
+				instances.create(RZ::ConStruct<RZ::Instance>("grown " + std::to_string(i), Math::vec3f(x, 2.5f, z),
+					Math::vec3f(0.0f, 0.0f, 0.0f), Math::vec3f(0.1f, 0.1f, 0.1f), mesh, mat));
+			}
+			for (int i = 0; i < 4; ++i) engine.renderWorld(RZ::Engine::RenderEngine::CUDAGPU, true, true);
+			append(out, *cameras[0]);
+			grown = instances.count();
+		}
+		std::printf("{\"width\": %u, \"height\": %u, \"rays\": %llu, \"instances_after_growth\": %u, \"rays_after_growth\": %llu}\n",
+			cameras[0]->width(), cameras[0]->height(), rays_frame2, grown, (unsigned long long)cameras[0]->rayCount());
 		return 0;
 	}
 	catch (const std::exception& e)

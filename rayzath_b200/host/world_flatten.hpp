@@ -168,10 +168,14 @@ namespace rzb_host
 		void addLeaf(const RZ::Mesh& mesh, const tri_node_t& n, uint32_t node_base, uint32_t tri_base)
 		{
 			(void)node_base;
-			out.mesh_nodes.push_back(makeNode(n.boundingBox(), 0,
-				uint32_t(out.triangles.size()) - tri_base, uint32_t(n.objects().size())));
+			// the leaf's count is what is actually emitted: a null component pointer in the leaf is skipped (as the
+			// instance path below does), so the range never reaches into the next leaf's triangles
+			const uint32_t begin = uint32_t(out.triangles.size());
+			const size_t node_at = out.mesh_nodes.size();
+			out.mesh_nodes.push_back(makeNode(n.boundingBox(), 0, begin - tri_base, 0));
 			for (const auto* object : n.objects())
 				if (object) addTriangle(mesh, *object);
+			out.mesh_nodes[node_at].type_count = uint32_t(out.triangles.size()) - begin;
 		}
 		void buildChildren(const RZ::Mesh& mesh, const tri_node_t& n, uint32_t node_base, uint32_t tri_base)
 		{

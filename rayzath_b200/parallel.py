@@ -8,8 +8,12 @@ read-only scene and the per-pixel accumulator, whose rgb sum and alpha (complete
 and ONE exchange step at resolve time: sum the float4 accumulators onto the root and tone-map there. Two
 implementations of that step:
   * `reduce_accum`        torch.distributed.reduce (NCCL over NVLink; gloo on CPU tensors in the tests)
-  * `FusedResolve`        the B200-native one: ranks export their accumulator as CUDA IPC handles, the root maps
-                          them and ONE kernel (k_tonemap) loads the peers' pixels over NVLink, sums and tone-maps.
+  * `SlicedResolve`       the B200-native one (bench.py's default): ranks export their accumulator and a small
+                          exchange buffer as CUDA IPC handles; per resolve ONE kernel per rank does a flag barrier in
+                          peer memory, sums ITS slice of all accumulators over NVLink (all-to-all ingress), tone-maps it
+                          into rank 0's staging image and does the closing barrier -- no NCCL call, no host round trip
+  * `FusedResolve`        its predecessor: the root alone pulls all peers' pixels (incast on one GPU's NVLink ingress),
+                          ordered by two NCCL token all-reduces
 The reference is single-GPU (device 0, cuda_engine_core.cu:17); this module has no counterpart there.
 """
 from __future__ import annotations
@@ -70,12 +74,17 @@ class FusedResolve:
       the root only after every rank's preceding work has completed) -> root: k_tonemap loads the peers' float4
       pixels over NVLink, sums them with its own and tone-maps, RGBA8 + depth to HOST buffers -> token all_reduce
       (peers may not touch their accumulators before the root has read them).
-    All ranks must call it. Returns (rgba8, depth) on the root, None elsewhere."""
+    All ranks must call it. Returns (rgba8, depth) on the root, None elsewhere.
+
+    Precondition: the context renders on torch's CURRENT stream (ctx.set_stream(torch.cuda.current_stream().cuda_stream)),
+    because the token all-reduce orders only work of the stream NCCL runs on; a context on its private stream is
+    synchronised with the host before the first token instead (correct, but the host waits)."""
 
     def __init__(self, ctx):
         import torch
         import torch.distributed as dist
         self.ctx, self.dist = ctx, dist
+        self._torch = torch
         self.rank, self.world = dist.get_rank(), dist.get_world_size()
         handles: List[bytes] = [b""] * self.world
         dist.all_gather_object(handles, ctx.accum_ipc_handle())
@@ -83,9 +92,56 @@ class FusedResolve:
         self.token = torch.zeros(1, dtype=torch.float32, device="cuda:%d" % ctx.device)
 
     def __call__(self, want_depth: bool = False):
+        if self.ctx.caller_stream != self._torch.cuda.current_stream().cuda_stream:
+            self.ctx.synchronize()  # rendering is not on the stream the token travels on: wait for it on the host
         self.dist.all_reduce(self.token)
         out = None
         if self.rank == 0:
             out = self.ctx.resolve_ipc(self.peer_handles, want_depth=want_depth)
         self.dist.all_reduce(self.token)
         return out
+
+
+
+class SlicedResolve:
+    """The exchange step of the one-process-per-GPU path without NCCL and without a host round trip
+    (rzb_resolve_sliced, k_resolve_sliced): stream-ordered behind the render passes of each rank,
+
+      barrier in (flags stored into every peer's exchange header over NVLink) -> rank r sums slice r of ALL ranks'
+      float4 accumulators through peer loads, tone-maps it and stores RGBA8 into rank 0's staging image -> barrier out
+      (peers may render into their accumulators again; rank 0 copies image + depth to its pinned host buffers).
+
+    Every GPU pulls (N-1)/N of one frame instead of rank 0 pulling N-1 frames, and nothing but the slowest rank's
+    render time is on the critical path. All ranks must call it the same number of times (the flags carry the call
+    number). `rgba8_pinned` / `depth_pinned`: page-locked numpy arrays on rank 0 (ignored elsewhere); valid after
+    wait()."""
+
+    def __init__(self, ctx, rgba8_pinned=None, depth_pinned=None, group=None):
+        import torch.distributed as dist
+        self.ctx, self.dist = ctx, dist
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        mine = (ctx.accum_ipc_handle(), ctx.exchange_ipc_handle())
+        both = [None] * self.world
+        dist.all_gather_object(both, mine, group=group)
+        self.accum_handles = [b[0] for b in both]
+        self.exchange_handles = [b[1] for b in both]
+        self.rgba8, self.depth = rgba8_pinned, depth_pinned
+        self._ms = None
+        self._pending = False
+
+    def __call__(self):
+        root = self.rank == 0
+        self.ctx.resolve_sliced(self.rank, self.world, self.accum_handles, self.exchange_handles,
+                                self.rgba8 if root else None, self.depth if root else None)
+        self._pending = True
+
+    def wait(self):
+        """Blocks until this rank's exchange kernel (and, on rank 0, the copies to the host) have finished."""
+        if self._pending:
+            self._ms = self.ctx.resolve_sliced_wait()
+            self._pending = False
+        return (self.rgba8, self.depth) if self.rank == 0 else None
+
+    def last_ms(self):
+        """Device time of this rank's last exchange kernel (includes waiting for the slowest rank to arrive)."""
+        return self._ms

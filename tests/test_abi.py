@@ -30,7 +30,7 @@ def test_binding_covers_header():
 
 
 def test_abi_version():
-    assert capi.lib().rzb_abi_version() == 2
+    assert capi.lib().rzb_abi_version() == 3
 
 
 def test_struct_sizes():

@@ -64,3 +64,23 @@ def test_world_edits_between_frames(tmp_path):
     assert (np.abs(a - b) > 1).mean() < 1e-3        # same seed, same rays: equal up to atomic-add order in the last bit
     assert np.abs(a[1] - a[0]).mean() > 1.0         # the edit is visible
     assert abs(a[2].mean() - a[1].mean()) / a[1].mean() < 0.05 and np.abs(a[2] - a[1]).mean() < np.abs(a[1] - a[0]).mean()
+
+
+@pytest.mark.skipif(not os.path.exists(SELFTEST), reason="drop-in self-test not built (needs /root/reference at build time)")
+def test_instance_tree_growth_falls_back_to_full_upload(tmp_path):
+    """adding instances without touching a mesh keeps the upload incremental (RZB_SCENE_KEEP_GEOMETRY) until
+    the instance tree outgrows the node range reserved for it (max(2 x nodes, 1024)); rzb_set_scene then answers
+    RZB_ERR_STATE and the engine must re-send the whole scene instead of throwing. 700 extra instances of an existing
+    mesh -> an instance tree of > 1024 nodes; the frame renders and the new geometry is visible."""
+    import numpy as np
+    w = scenes.materials_scene(resolution=(320, 180), res=24)
+    w.save_reference(str(tmp_path), "scene")
+    out = tmp_path / "grow.raw"
+    env = dict(os.environ, RZB200_SEED="11")
+    r = subprocess.run([SELFTEST, "scene.json", str(out), "700"], cwd=tmp_path, env=env, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    info = json.loads(r.stdout.strip().splitlines()[-1])
+    assert info["instances_after_growth"] >= 700
+    assert info["rays_after_growth"] == 4 * 8 * 320 * 180  # accumulation restarted with the edit
+    f = np.fromfile(out, dtype=np.uint8).reshape(4, 180, 320, 4)[..., :3].astype(np.int32)
+    assert np.abs(f[3] - f[2]).mean() > 0.5  # the grown instances are in the picture

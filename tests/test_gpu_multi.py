@@ -1,5 +1,6 @@
 """One process per rank, sample streams sharded over the ranks, accumulators combined by the fused IPC resolve
-(rank 0 loads the peers' pixels through CUDA IPC mappings -- NVLink between GPUs -- sums and tone-maps in one kernel).
+(rank 0 loads the peers' pixels through CUDA IPC mappings -- NVLink between GPUs -- sums and tone-maps in one kernel)
+and by the sliced resolve (every rank sums and tone-maps its slice of the frame; flag barriers in peer memory, no NCCL).
 Runs with 2 ranks on 2 GPUs (NCCL) when the box has them, else with 2 ranks sharing GPU 0 (gloo for the host-side
 ordering; the IPC path is the same). Checked bit-exactly against the oracle's tone map of the summed accumulators."""
 import os
@@ -41,6 +42,20 @@ def _worker(rank, world, port, n_gpus, out_dir):
     fused = parallel.FusedResolve(ctx)
     out = fused(want_depth=True)
     np.save(os.path.join(out_dir, "acc_%d.npy" % rank), ctx.read_accum())
+    # the sliced resolve (one kernel per rank: flag barrier in peer memory, slice sum over NVLink, tone map into rank
+    # 0's staging image), twice: the flags carry the call number
+    rgba_pin = torch.empty((90, 160, 4), dtype=torch.uint8, pin_memory=True).numpy()
+    depth_pin = torch.empty((90, 160), dtype=torch.float32, pin_memory=True).numpy()
+    sliced = parallel.SlicedResolve(ctx, rgba_pin, depth_pin)
+    for _ in range(2):
+        rgba_pin[:] = 0
+        sliced()
+        sliced.wait()
+    assert sliced.last_ms() is not None and sliced.last_ms() >= 0.0
+    if rank == 0:
+        np.save(os.path.join(out_dir, "rgba_sliced.npy"), rgba_pin.copy())
+        np.save(os.path.join(out_dir, "depth_sliced.npy"), depth_pin.copy())
+        np.save(os.path.join(out_dir, "depth_fused.npy"), out[1])
     if rank == 0:
         np.save(os.path.join(out_dir, "rgba.npy"), out[0])
         # the NCCL/gloo reduce path must give the same sum
@@ -69,4 +84,6 @@ def test_fused_ipc_resolve_two_ranks(tmp_path):
     cam = scenes.materials_scene(resolution=(160, 90), res=16).camera_struct()[0]
     expect = O.tonemap(a0 + a1, float(cam["aperture"]), float(cam["exposure_time"]))
     assert np.array_equal(np.load(tmp_path / "rgba.npy"), expect)
+    assert np.array_equal(np.load(tmp_path / "rgba_sliced.npy"), expect)
+    assert np.array_equal(np.load(tmp_path / "depth_sliced.npy"), np.load(tmp_path / "depth_fused.npy"))
     assert np.array_equal(np.load(tmp_path / "reduced.npy"), a0 + a1)
