@@ -144,22 +144,23 @@ namespace rzb
 		uint2* smem; // &smem_stack[0][threadIdx.x], stride blockDim.x
 		uint2 local[kLocalStack];
 		int sp;
+		static __device__ __forceinline__ int clamp_local(int i) { return i < kLocalStack ? i : kLocalStack - 1; }
 		__device__ __forceinline__ void push(uint32_t a, uint32_t b)
 		{
 			if (sp < kSmemStack) smem[sp * kTraceBlock] = make_uint2(a, b);
-			else local[min(sp - kSmemStack, kLocalStack - 1)] = make_uint2(a, b);
+			else local[clamp_local(sp - kSmemStack)] = make_uint2(a, b);
 			++sp;
 		}
 		__device__ __forceinline__ uint2 pop()
 		{
 			--sp;
 			if (sp < kSmemStack) return smem[sp * kTraceBlock];
-			return local[min(sp - kSmemStack, kLocalStack - 1)];
+			return local[clamp_local(sp - kSmemStack)];
 		}
 		__device__ __forceinline__ uint2 peek() const
 		{
 			if (sp - 1 < kSmemStack) return smem[(sp - 1) * kTraceBlock];
-			return local[min(sp - 1 - kSmemStack, kLocalStack - 1)];
+			return local[clamp_local(sp - 1 - kSmemStack)];
 		}
 	};
 
