@@ -308,6 +308,9 @@ int rzb_resolve_wait(rzb_ctx* ctx, uint32_t slot, uint32_t* instance, uint32_t* 
 /* page-locked host memory for the asynchronous copies */
 int rzb_host_alloc(size_t bytes, void** out);
 int rzb_host_free(void* p);
+/* mean of the accumulator's alpha channel over the pixels this context renders = completed paths per pixel ("spp",
+ * cuda_render_kernel.cu:45,104): what a host that renders "to N spp" stops at. Synchronises. */
+int rzb_mean_samples(rzb_ctx* ctx, double* mean_out);
 /* device pointer of the linear float4 accumulator (for NCCL reduction by the caller) and its size. */
 int rzb_accum_device_ptr(rzb_ctx* ctx, void** device_ptr, size_t* bytes);
 /* add `count` float4 pixels from a DEVICE buffer into the accumulator (after a reduce-scatter or P2P read). */

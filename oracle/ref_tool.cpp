@@ -15,9 +15,17 @@
 //   rendercuda <scene.json> <calls> <rpp> <out.rzs|-> [max_depth] [spot_samples] [direct_samples] [warmup_calls=1]
 //                                               (rz_ref_tool_cuda only) <calls> x Engine::renderWorld(CUDAGPU) with <rpp> passes each:
 //                                               the reference's own CUDA engine; dumps RGBA8 + depth ; prints timing JSON
+//   tracecuda <scene.json> <rays.rzs> <out.rzs> (rz_ref_tool_cuda only) closest-hit records from the reference's own CUDA
+//                                               traversal (cuda_world.cuh:80-90 on the device World the engine mirrored);
+//                                               same record format as `trace`
+//   movecuda <scene.json> <calls> <rpp> <out.rzs> <dx> <dy> <dz> [max_depth]
+//                                               (rz_ref_tool_cuda only) <calls> x renderWorld(CUDAGPU), camera moved by
+//                                               (dx,dy,dz), ONE more renderWorld call: the restart blends the replaced
+//                                               frame in (Camera::reproject, cuda_camera.cuh:390-426); dumps both images
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <filesystem>
 #include <iostream>
 #include <string>
@@ -40,6 +48,9 @@
 
 #ifdef RZ_WITH_HEADLESS
 #include "headless.hpp"
+#endif
+#ifdef RZ_WITH_CUDA_ENGINE
+#include "ref_trace_cuda.h"
 #endif
 
 namespace RZ = RayZath::Engine;
@@ -297,6 +308,93 @@ static int cmdRenderCuda(int argc, char** argv)
 }
 #endif
 
+#ifdef RZ_WITH_CUDA_ENGINE
+static int cmdTraceCuda(const std::string& scene, const std::string& rays_path, const std::string& out_path)
+{
+	auto& engine = RZ::Engine::instance();
+	auto& world = engine.world();
+	world.loader().loadScene(scene);
+	engine.renderConfig().tracing().rpp(1);
+	if (engine.renderEngine() != RZ::Engine::RenderEngine::CUDAGPU)
+	{
+		std::fprintf(stderr, "rz_ref_tool: the reference CUDA engine failed to initialise (no GPU?)\n");
+		return 3;
+	}
+	// one call mirrors the world to the device exactly as the reference does (World::reconstructAll)
+	engine.renderWorld(RZ::Engine::RenderEngine::CUDAGPU, true, true);
+	// BVH-order triangle index of the device mesh -> host triangle index: Mesh::reconstruct emits leaf by leaf in the
+	// order world_flatten.hpp restates (cuda_instance.cu:101-220)
+	rzb_host::FlatScene flat;
+	rzb_host::WorldFlattener(world, flat).run();
+	std::vector<uint32_t> mesh_of_instance(world.container<RZ::ObjectType::Instance>().count(), RZB_NO_INDEX);
+	for (const auto& in : flat.instances)
+		if (in.host_index < mesh_of_instance.size()) mesh_of_instance[in.host_index] = in.mesh;
+
+	const auto arrays = rzs::read(rays_path);
+	const RaySet rays = raysOf(arrays);
+	std::vector<RefCudaHit> raw(rays.n);
+	const auto t0 = std::chrono::steady_clock::now();
+	const int rc = refCudaTrace(engine.m_cuda_engine.get(), rays.o, rays.d, rays.nf, uint32_t(rays.n), raw.data());
+	const double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+	if (rc) return 4;
+	std::vector<rzb_hit> hits(rays.n);
+	for (size_t i = 0; i < rays.n; ++i)
+	{
+		rzb_hit h{};
+		h.instance = RZB_NO_INDEX; h.triangle = RZB_NO_INDEX;
+		h.t = raw[i].t;
+		if (raw[i].instance != 0xFFFFFFFFu)
+		{
+			h.instance = raw[i].instance;
+			const uint32_t m = raw[i].instance < mesh_of_instance.size() ? mesh_of_instance[raw[i].instance] : RZB_NO_INDEX;
+			if (m != RZB_NO_INDEX && raw[i].triangle_bvh_order < flat.meshes[m].tri_count)
+				h.triangle = flat.tri_host_index[flat.meshes[m].tri_offset + raw[i].triangle_bvh_order];
+			h.b1 = raw[i].b1; h.b2 = raw[i].b2; h.external = raw[i].external;
+		}
+		hits[i] = h;
+	}
+	rzs::Writer w;
+	w.add("hits", hits);
+	w.write(out_path);
+	std::printf("{\"rays\": %zu, \"seconds\": %.6f}\n", rays.n, secs);
+	std::fflush(stdout);
+	std::_Exit(0);
+}
+
+static int cmdMoveCuda(int argc, char** argv)
+{
+	const std::string scene = argv[2];
+	const uint32_t calls = uint32_t(std::atoi(argv[3]));
+	const uint32_t rpp = uint32_t(std::atoi(argv[4]));
+	const std::string out_path = argv[5];
+	const Math::vec3f delta(float(std::atof(argv[6])), float(std::atof(argv[7])), float(std::atof(argv[8])));
+	auto& engine = RZ::Engine::instance();
+	auto& world = engine.world();
+	world.loader().loadScene(scene);
+	if (argc > 9) engine.renderConfig().tracing().maxDepth(uint8_t(std::atoi(argv[9])));
+	engine.renderConfig().tracing().rpp(rpp);
+	if (engine.renderEngine() != RZ::Engine::RenderEngine::CUDAGPU) return 3;
+	auto& cameras = world.container<RZ::ObjectType::Camera>();
+	if (!cameras.count() || !cameras[0]) return 5;
+	auto& cam = *cameras[0];
+	const uint64_t n = uint64_t(cam.width()) * cam.height();
+	rzs::Writer w;
+	for (uint32_t c = 0; c < calls; ++c) engine.renderWorld(RZ::Engine::RenderEngine::CUDAGPU, true, true);
+	std::vector<uint8_t> before(n * 4);
+	std::memcpy(before.data(), cam.imageBuffer().GetMapAddress(), n * 4);
+	w.add("rgba8_before", before.data(), 4, n);
+	cam.position(cam.position() + delta);
+	engine.renderWorld(RZ::Engine::RenderEngine::CUDAGPU, true, true);
+	w.add("rgba8_after", cam.imageBuffer().GetMapAddress(), 4, n);
+	const uint32_t res[2] = {cam.width(), cam.height()};
+	w.add("resolution", res, 4, 2);
+	w.write(out_path);
+	std::printf("{\"calls\": %u, \"rpp\": %u, \"rays_after_move\": %llu}\n", calls, rpp, (unsigned long long)cam.rayCount());
+	std::fflush(stdout);
+	std::_Exit(0);
+}
+#endif
+
 int main(int argc, char** argv)
 {
 	try
@@ -308,6 +406,8 @@ int main(int argc, char** argv)
 		if (cmd == "render" && argc >= 5) return cmdRender(argc, argv);
 #ifdef RZ_WITH_CUDA_ENGINE
 		if (cmd == "rendercuda" && argc >= 6) return cmdRenderCuda(argc, argv);
+		if (cmd == "tracecuda" && argc == 5) return cmdTraceCuda(argv[2], argv[3], argv[4]);
+		if (cmd == "movecuda" && argc >= 9) return cmdMoveCuda(argc, argv);
 #endif
 #ifdef RZ_WITH_HEADLESS
 		if (cmd == "headless" && argc >= 3)

@@ -107,6 +107,7 @@ SYMBOLS = {
     "rzb_render": (C.c_int, [_P, C.c_uint32]),
     "rzb_resolve": (C.c_int, [_P, _P, _P, C.POINTER(C.c_uint64)]),
     "rzb_read_accum": (C.c_int, [_P, _P]),
+    "rzb_mean_samples": (C.c_int, [_P, C.POINTER(C.c_double)]),
     "rzb_accum_device_ptr": (C.c_int, [_P, C.POINTER(_P), C.POINTER(C.c_size_t)]),
     "rzb_accum_add_device": (C.c_int, [_P, _P, C.c_size_t]),
     "rzb_resolve_peers": (C.c_int, [_P, C.POINTER(_P), C.c_uint32, _P, _P, C.POINTER(C.c_uint64)]),
@@ -459,6 +460,12 @@ class Context:
         out = np.empty((self.height, self.width, 4), dtype=f4)
         self._check(self._l.rzb_read_accum(self._h, out.ctypes.data))
         return out
+
+    def mean_samples(self) -> float:
+        """Completed paths per pixel so far (mean of the accumulator's alpha channel over this context's pixels)."""
+        m = C.c_double(0.0)
+        self._check(self._l.rzb_mean_samples(self._h, C.byref(m)))
+        return float(m.value)
 
     def accum_device_ptr(self):
         p, n = _P(), C.c_size_t(0)

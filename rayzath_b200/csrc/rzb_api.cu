@@ -42,9 +42,8 @@ namespace
 
 namespace rzb
 {
-	size_t sortTempBytes(uint32_t n, int end_bit);
-	cudaError_t sortPairs(void* temp, size_t temp_bytes, const uint32_t* keys_in, uint32_t* keys_out, const uint32_t* vals_in,
-		uint32_t* vals_out, uint32_t n, int end_bit, cudaStream_t stream);
+	size_t scanTempBytes(uint32_t n);
+	cudaError_t exclusiveScan(void* temp, size_t temp_bytes, const uint32_t* in, uint32_t* out, uint32_t n, cudaStream_t stream);
 }
 
 struct rzb_ctx
@@ -111,13 +110,19 @@ struct rzb_ctx
 	bool set_carveout = true;      // RZB200_CARVEOUT=0 disables the shared-memory carve-out hint
 	bool own_trees = false;        // rzb_scene::flags & RZB_SCENE_OWN_TREES: conservative box tests
 	bool debug_sync = false;       // RZB200_DEBUG_SYNC: synchronise after every kernel of rzb_render and name the one that faulted
-	// ray sorting between passes (RZB200_SORT=1): keys written by k_shade -> radix sort -> slot order of the next trace
-	bool sort_enabled = false;
-	uint32_t sort_bits = 6;        // RZB200_SORT_BITS: Morton cells per axis = 2^bits
-	bool order_valid = false;      // false until the first sort after a reset
-	DeviceBuffer sort_buf[5];      // keys, keys_out, iota, order, temp
-	uint32_t sort_capacity = 0;
-	float sort_min[3] = {0.0f, 0.0f, 0.0f}, sort_scale = 1.0f;
+	// ray ordering between passes (default on; RZB200_SORT=0 switches it off): k_shade bins the next pass's rays (and the
+	// shadow rays it queues) by (Morton cell of the origin, direction bin) with one atomic per ray, a prefix sum over the
+	// bins and a scatter turn that into the slot order the traversal kernels pull their batches in
+	bool sort_enabled = true;
+	uint32_t sort_bits = 5;        // RZB200_SORT_BITS: Morton cells per axis = 2^bits
+	uint32_t sort_dir_bits = 0;    // RZB200_SORT_DIRBITS: 0 = direction octant (8 bins), n = octahedral map with 2^n x 2^n bins
+	bool sort_shadow = true;       // RZB200_SORT_SHADOW=0: leave the shadow queue in append order
+	uint32_t sort_shadow_bits = 6; // RZB200_SORT_SHADOW_BITS: Morton cells per axis of the shadow-ray bins
+	bool sort_dir_major = false;   // RZB200_SORT_MAJOR=1: direction bin is the major key, origin cell the minor one
+	bool order_valid = false;      // false until the first ordering after a reset
+	enum { kSortKeys, kSortRank, kSortOrder, kSortBins, kSortOffsets, kSortTemp, kSortShKeys, kSortShRank, kSortShOrder, kSortBufCount };
+	DeviceBuffer sort_buf[kSortBufCount];
+	float sort_min[3] = {0.0f, 0.0f, 0.0f}, sort_extent = 0.0f;
 	float last_sort_ms = 0.0f;
 	uint32_t x_flags = 0;          // internal DScene::flags bits (kFlag*)
 };
@@ -334,7 +339,11 @@ extern "C" int rzb_create(int device, rzb_ctx** out)
 	ctx->debug_sync = std::getenv("RZB200_DEBUG_SYNC") != nullptr;
 	if (const char* env = std::getenv("RZB200_CARVEOUT")) ctx->set_carveout = std::atoi(env) != 0;
 	if (const char* env = std::getenv("RZB200_SORT")) ctx->sort_enabled = std::atoi(env) != 0;
-	if (const char* env = std::getenv("RZB200_SORT_BITS")) ctx->sort_bits = uint32_t(std::min(std::max(std::atoi(env), 1), 7));
+	if (const char* env = std::getenv("RZB200_SORT_BITS")) ctx->sort_bits = uint32_t(std::min(std::max(std::atoi(env), 1), 6));
+	if (const char* env = std::getenv("RZB200_SORT_DIRBITS")) ctx->sort_dir_bits = uint32_t(std::min(std::max(std::atoi(env), 0), 4));
+	if (const char* env = std::getenv("RZB200_SORT_SHADOW")) ctx->sort_shadow = std::atoi(env) != 0;
+	if (const char* env = std::getenv("RZB200_SORT_SHADOW_BITS")) ctx->sort_shadow_bits = uint32_t(std::min(std::max(std::atoi(env), 1), 7));
+	if (const char* env = std::getenv("RZB200_SORT_MAJOR")) ctx->sort_dir_major = std::atoi(env) != 0;
 	if (const char* env = std::getenv("RZB200_ANYHIT_ORDER")) ctx->x_flags |= std::atoi(env) == 1 ? kFlagAnyHitNearFirst : 0u;
 	ctx->trace_grid = gridFor(ctx, reinterpret_cast<const void*>(&k_trace_paths<false, false>), kTraceBlock);
 	ctx->shadow_grid = gridFor(ctx, reinterpret_cast<const void*>(&k_trace_shadow<false>), kTraceBlock);
@@ -701,7 +710,7 @@ extern "C" int rzb_set_scene(rzb_ctx* ctx, const rzb_scene* s)
 			ctx->sort_min[k] = root.bb_min[k];
 			extent = std::max(extent, root.bb_max[k] - root.bb_min[k]);
 		}
-		ctx->sort_scale = extent > 0.0f && std::isfinite(extent) ? float(1u << ctx->sort_bits) / extent : 0.0f;
+		ctx->sort_extent = extent > 0.0f && std::isfinite(extent) ? extent : 0.0f;
 	}
 	ctx->order_valid = false;
 	return RZB_OK;
@@ -833,27 +842,43 @@ extern "C" int rzb_render(rzb_ctx* ctx, uint32_t passes)
 	const uint32_t stride = (passes + 255u) / 256u;
 	const uint32_t n_sampled = passes ? (passes + stride - 1u) / stride : 0u;
 	const uint32_t n_slots = f.slot_end - f.slot_begin;
-	const int sort_end_bit = int(3u * ctx->sort_bits + 3u + 1u);
-	size_t sort_temp = 0;
+	// ---- ray ordering set-up: bin tables = [camera groups | bounce bins | 1 bin for slots without a pixel | shadow bins]
+	size_t scan_temp = 0;
+	uint32_t n_bins = 0;
 	if (ctx->sort_enabled)
 	{
-		sort_temp = sortTempBytes(n_slots, sort_end_bit);
-		if ((rc = ensureBuf(ctx, ctx->sort_buf[4], sort_temp))) return rc;
-		if (ctx->sort_capacity < n_slots || ctx->sort_buf[2].ptr == nullptr)
-		{
-			for (int k = 0; k < 4; ++k)
-				if ((rc = ensureBuf(ctx, ctx->sort_buf[k], size_t(n_slots) * 4))) return rc;
-			ctx->sort_capacity = n_slots;
-			ctx->order_valid = false;
-		}
-		// values = slot indices of the band
-		k_iota_from<<<(n_slots + 255) / 256, 256, 0, ctx->stream>>>(static_cast<uint32_t*>(ctx->sort_buf[2].ptr), n_slots, f.slot_begin);
-		f.sort_keys = static_cast<uint32_t*>(ctx->sort_buf[0].ptr);
-		for (int k = 0; k < 3; ++k) f.sort_min[k] = ctx->sort_min[k];
-		f.sort_scale = ctx->sort_scale;
+		const uint32_t dir_bins_log2 = ctx->sort_dir_bits ? 2u * ctx->sort_dir_bits : 3u;
 		f.sort_bits = ctx->sort_bits;
+		f.sort_dir_bits = ctx->sort_dir_bits;
+		f.sort_camera_bins = (n_slots + 31u) / 32u;
+		f.sort_bounce_bins = 1u << (3u * ctx->sort_bits + dir_bins_log2);
+		f.sort_shadow_base = f.sort_camera_bins + f.sort_bounce_bins + 1u;
+		f.sort_shadow_bits = ctx->sort_shadow_bits;
+		f.sort_dir_major = ctx->sort_dir_major ? 1u : 0u;
+		const uint32_t shadow_bins = (lights && ctx->sort_shadow) ? (1u << (3u * ctx->sort_shadow_bits + 2u)) : 0u;
+		n_bins = f.sort_shadow_base + shadow_bins;
+		for (int k = 0; k < 3; ++k) f.sort_min[k] = ctx->sort_min[k];
+		f.sort_scale = ctx->sort_extent > 0.0f ? 1.0f / ctx->sort_extent : 0.0f; // to [0, 1); the kernels scale by their cell count
+		scan_temp = scanTempBytes(n_bins + 1u);
+		const bool grow = ctx->sort_buf[rzb_ctx::kSortKeys].bytes < size_t(n_slots) * 4 || ctx->sort_buf[rzb_ctx::kSortBins].bytes < size_t(n_bins + 1u) * 4;
+		if ((rc = ensureBuf(ctx, ctx->sort_buf[rzb_ctx::kSortTemp], scan_temp))) return rc;
+		for (int k : {int(rzb_ctx::kSortKeys), int(rzb_ctx::kSortRank), int(rzb_ctx::kSortOrder)})
+			if ((rc = ensureBuf(ctx, ctx->sort_buf[k], size_t(n_slots) * 4))) return rc;
+		for (int k : {int(rzb_ctx::kSortBins), int(rzb_ctx::kSortOffsets)})
+			if ((rc = ensureBuf(ctx, ctx->sort_buf[k], size_t(n_bins + 1u) * 4))) return rc;
+		if (shadow_bins)
+			for (int k : {int(rzb_ctx::kSortShKeys), int(rzb_ctx::kSortShRank), int(rzb_ctx::kSortShOrder)})
+				if ((rc = ensureBuf(ctx, ctx->sort_buf[k], size_t(f.shadow_capacity) * 4))) return rc;
+		if (grow) ctx->order_valid = false;
+		f.sort_keys = static_cast<uint32_t*>(ctx->sort_buf[rzb_ctx::kSortKeys].ptr);
+		f.sort_rank = static_cast<uint32_t*>(ctx->sort_buf[rzb_ctx::kSortRank].ptr);
+		f.sort_bin_count = static_cast<uint32_t*>(ctx->sort_buf[rzb_ctx::kSortBins].ptr);
+		f.sh_keys = shadow_bins ? static_cast<uint32_t*>(ctx->sort_buf[rzb_ctx::kSortShKeys].ptr) : nullptr;
+		f.sh_rank = shadow_bins ? static_cast<uint32_t*>(ctx->sort_buf[rzb_ctx::kSortShRank].ptr) : nullptr;
+		RZB_CUDA(ctx, cudaMemsetAsync(f.sort_bin_count, 0, size_t(n_bins + 1u) * 4, ctx->stream));
 	}
-	else { f.sort_keys = nullptr; f.order = nullptr; }
+	else { f.sort_keys = nullptr; f.sort_rank = nullptr; f.sort_bin_count = nullptr; f.sh_keys = nullptr; f.sh_rank = nullptr; f.order = nullptr; }
+	f.sh_order = nullptr;
 	while (ctx->ev_stage.size() < size_t(n_sampled) * 5)
 	{
 		cudaEvent_t ev = nullptr;
@@ -869,7 +894,7 @@ extern "C" int rzb_render(rzb_ctx* ctx, uint32_t passes)
 		const bool timed = (p % stride) == 0u;
 		cudaEvent_t* ev = timed ? &ctx->ev_stage[size_t(ctx->sampled_passes) * 5] : nullptr;
 		RZB_CUDA(ctx, cudaMemsetAsync(ctx->d_counters, 0, 12, ctx->stream));
-		f.order = (ctx->sort_enabled && ctx->order_valid) ? static_cast<const uint32_t*>(ctx->sort_buf[3].ptr) : nullptr;
+		f.order = (ctx->sort_enabled && ctx->order_valid) ? static_cast<const uint32_t*>(ctx->sort_buf[rzb_ctx::kSortOrder].ptr) : nullptr;
 		if (timed) cudaEventRecord(ev[0], ctx->stream);
 		if (count) { if (fast) k_trace_paths<true, true><<<ctx->trace_grid_fast, kTraceBlock, 0, ctx->stream>>>(ctx->sc, f); else k_trace_paths<true, false><<<ctx->trace_grid, kTraceBlock, 0, ctx->stream>>>(ctx->sc, f); }
 		else { if (fast) k_trace_paths<false, true><<<ctx->trace_grid_fast, kTraceBlock, 0, ctx->stream>>>(ctx->sc, f); else k_trace_paths<false, false><<<ctx->trace_grid, kTraceBlock, 0, ctx->stream>>>(ctx->sc, f); }
@@ -894,12 +919,17 @@ extern "C" int rzb_render(rzb_ctx* ctx, uint32_t passes)
 		ctx->launches += 2;
 		if (ctx->sort_enabled)
 		{
-			// order of the NEXT pass's closest-hit queries: radix sort of (ray key, slot)
-			RZB_CUDA(ctx, sortPairs(ctx->sort_buf[4].ptr, sort_temp, static_cast<const uint32_t*>(ctx->sort_buf[0].ptr),
-				static_cast<uint32_t*>(ctx->sort_buf[1].ptr), static_cast<const uint32_t*>(ctx->sort_buf[2].ptr),
-				static_cast<uint32_t*>(ctx->sort_buf[3].ptr), n_slots, sort_end_bit, ctx->stream));
+			// bins -> offsets (one prefix sum over both tables), then scatter: the order of the NEXT pass's closest-hit
+			// queries and of THIS pass's shadow queries
+			uint32_t* offsets = static_cast<uint32_t*>(ctx->sort_buf[rzb_ctx::kSortOffsets].ptr);
+			RZB_CUDA(ctx, exclusiveScan(ctx->sort_buf[rzb_ctx::kSortTemp].ptr, scan_temp, f.sort_bin_count, offsets, n_bins + 1u, ctx->stream));
+			RZB_CUDA(ctx, cudaMemsetAsync(f.sort_bin_count, 0, size_t(n_bins + 1u) * 4, ctx->stream));
+			uint32_t* sh_order = f.sh_keys ? static_cast<uint32_t*>(ctx->sort_buf[rzb_ctx::kSortShOrder].ptr) : nullptr;
+			const uint32_t scatter_n = std::max(n_slots, f.sh_keys ? f.shadow_capacity : 0u);
+			k_scatter_order<<<(scatter_n + 255) / 256, 256, 0, ctx->stream>>>(f, offsets, static_cast<uint32_t*>(ctx->sort_buf[rzb_ctx::kSortOrder].ptr), sh_order);
+			f.sh_order = sh_order;
 			ctx->order_valid = true;
-			ctx->launches += 4; // histogram + one onesweep pass per 8 key bits
+			ctx->launches += 3;
 		}
 		if (timed) cudaEventRecord(ev[4], ctx->stream);
 		if (lights)
@@ -1056,6 +1086,25 @@ extern "C" int rzb_read_accum(rzb_ctx* ctx, float* rgba_f32)
 	return RZB_OK;
 }
 
+extern "C" int rzb_mean_samples(rzb_ctx* ctx, double* mean_out)
+{
+	if (!ctx || !mean_out) return fail(ctx, RZB_ERR_INVALID, "rzb_mean_samples: NULL argument");
+	if (!ctx->has_camera) return fail(ctx, RZB_ERR_STATE, "rzb_mean_samples: no camera");
+	DeviceGuard guard(ctx->device);
+	const uint32_t n = ctx->cam.width * ctx->cam.height;
+	double* d_sum = reinterpret_cast<double*>(ctx->d_work + 15);
+	RZB_CUDA(ctx, cudaMemsetAsync(d_sum, 0, 8, ctx->stream));
+	k_sum_alpha<<<std::min<uint32_t>((n + 255u) / 256u, uint32_t(ctx->sm_count) * 8u), 256, 0, ctx->stream>>>(ctx->frame.accum, n, d_sum);
+	ctx->launches += 1;
+	RZB_CUDA(ctx, cudaGetLastError());
+	double h = 0.0;
+	RZB_CUDA(ctx, cudaMemcpyAsync(&h, d_sum, 8, cudaMemcpyDeviceToHost, ctx->stream));
+	RZB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	const uint64_t band = bandPixels(ctx);
+	*mean_out = band ? h / double(band) : 0.0;
+	return RZB_OK;
+}
+
 extern "C" int rzb_accum_device_ptr(rzb_ctx* ctx, void** device_ptr, size_t* bytes)
 {
 	if (!ctx || !device_ptr) return fail(ctx, RZB_ERR_INVALID, "rzb_accum_device_ptr: NULL argument");
@@ -1194,7 +1243,6 @@ namespace
 		const size_t n = size_t(ctx->cam.width) * ctx->cam.height;
 		if (ctx->d_exchange && ctx->exchange_pixels == n) return RZB_OK;
 		if (ctx->d_exchange) cudaFree(ctx->d_exchange);
-	for (auto& b : ctx->sort_buf) if (b.ptr) cudaFree(b.ptr);
 		ctx->d_exchange = nullptr;
 		ctx->exchange_pixels = 0;
 		RZB_CUDA(ctx, cudaMalloc(&ctx->d_exchange, sizeof(ExchangeHeader) + n * 4));

@@ -57,17 +57,26 @@ namespace rzb
 
 		uint32_t max_depth, direct_samples, spot_samples;
 		uint64_t seed;
-		// ray sorting (optional): k_shade writes one key per slot, a radix sort turns them into `order`, the next
-		// pass's k_trace_paths pulls slots through it (NULL = slot order)
-		uint32_t* sort_keys;
+		// ray ordering: k_shade bins the next pass's rays and the shadow rays it queues (one atomic each: bin counter ->
+		// rank inside the bin); after a prefix sum over the bins k_scatter_order writes slot / queue indices in bin
+		// order; the traversal kernels pull their batches through `order` / `sh_order` (NULL = slot / append order)
+		uint32_t* sort_keys;      // [slot - slot_begin] bin of the slot's next ray
+		uint32_t* sort_rank;      // [slot - slot_begin] rank inside its bin
+		uint32_t* sort_bin_count; // camera groups | bounce bins | no-pixel bin | shadow bins
+		uint32_t* sh_keys;        // [queue index] (NULL: shadow queue stays in append order)
+		uint32_t* sh_rank;
 		const uint32_t* order;
-		float sort_min[3], sort_scale; // Morton cells: cubic, (o - sort_min) * sort_scale in [0, 2^sort_bits)
-		uint32_t sort_bits;            // cells per axis = 2^sort_bits
+		const uint32_t* sh_order;
+		float sort_min[3], sort_scale; // Morton cells: cubic, (o - sort_min) * sort_scale in [0, 1)
+		uint32_t sort_bits;            // cells per axis = 2^sort_bits (path bins)
+		uint32_t sort_shadow_bits;     // the same for the shadow-ray bins
+		uint32_t sort_dir_major;       // 1: direction bin major, origin cell minor
+		uint32_t sort_dir_bits;        // 0: direction octant; n: octahedral map, 2^n x 2^n bins
+		uint32_t sort_camera_bins, sort_bounce_bins, sort_shadow_base;
 	};
 
-	// Key of a ray for the order pass. Regenerated camera rays keep their tile order (they are coherent as they are);
-	// bounce rays are grouped by the Morton cell of their origin, then by direction octant; slots without a pixel last.
-	constexpr uint32_t kSortInvalid = 0xFFFFFFFFu;
+	// Bin of a ray for the order pass. Regenerated camera rays keep their tile order (one bin per 32 slots: they are
+	// coherent as they are); bounce rays are grouped by the Morton cell of their origin, then by direction bin.
 	__device__ __forceinline__ uint32_t spread3(uint32_t v)
 	{
 		v &= 0x3FFu;
@@ -77,18 +86,50 @@ namespace rzb
 		v = (v | (v << 2)) & 0x09249249u;
 		return v;
 	}
-	__device__ __forceinline__ uint32_t ray_sort_key(const DFrame& f, const uint32_t slot, const bool camera_ray,
-		const float3 o, const float3 d)
+	__device__ __forceinline__ uint32_t morton_cell(const DFrame& f, const float3 o, const uint32_t bits)
 	{
-		const uint32_t cell_bits = 3u * f.sort_bits + 3u;
-		if (camera_ray) return slot >> 5; // < 2^18 up to 8.3M slots
-		const float top = float((1u << f.sort_bits) - 1u);
-		const uint32_t cx = uint32_t(fminf(fmaxf((o.x - f.sort_min[0]) * f.sort_scale, 0.0f), top));
-		const uint32_t cy = uint32_t(fminf(fmaxf((o.y - f.sort_min[1]) * f.sort_scale, 0.0f), top));
-		const uint32_t cz = uint32_t(fminf(fmaxf((o.z - f.sort_min[2]) * f.sort_scale, 0.0f), top));
-		const uint32_t morton = (spread3(cx) << 2) | (spread3(cy) << 1) | spread3(cz);
-		const uint32_t octant = (uint32_t(d.x < 0.0f) << 2) | (uint32_t(d.y < 0.0f) << 1) | uint32_t(d.z < 0.0f);
-		return (1u << cell_bits) | (morton << 3) | octant;
+		const float cells = float(1u << bits), top = cells - 1.0f, sc = f.sort_scale * cells;
+		const uint32_t cx = uint32_t(fminf(fmaxf((o.x - f.sort_min[0]) * sc, 0.0f), top));
+		const uint32_t cy = uint32_t(fminf(fmaxf((o.y - f.sort_min[1]) * sc, 0.0f), top));
+		const uint32_t cz = uint32_t(fminf(fmaxf((o.z - f.sort_min[2]) * sc, 0.0f), top));
+		return (spread3(cx) << 2) | (spread3(cy) << 1) | spread3(cz);
+	}
+	__device__ __forceinline__ uint32_t direction_bin(const DFrame& f, const float3 d)
+	{
+		if (f.sort_dir_bits == 0u) return (uint32_t(d.x < 0.0f) << 2) | (uint32_t(d.y < 0.0f) << 1) | uint32_t(d.z < 0.0f);
+		// octahedral map of the direction onto [0, 1)^2, 2^n x 2^n cells of about equal solid angle
+		const float inv = 1.0f / fmaxf(fabsf(d.x) + fabsf(d.y) + fabsf(d.z), 1.0e-30f);
+		float u = d.x * inv, v = d.z * inv;
+		if (d.y < 0.0f)
+		{
+			const float uu = (1.0f - fabsf(v)) * (u >= 0.0f ? 1.0f : -1.0f);
+			v = (1.0f - fabsf(u)) * (v >= 0.0f ? 1.0f : -1.0f);
+			u = uu;
+		}
+		const float cells = float(1u << f.sort_dir_bits);
+		const uint32_t iu = uint32_t(fminf(fmaxf((u * 0.5f + 0.5f) * cells, 0.0f), cells - 1.0f));
+		const uint32_t iv = uint32_t(fminf(fmaxf((v * 0.5f + 0.5f) * cells, 0.0f), cells - 1.0f));
+		return (iu << f.sort_dir_bits) | iv;
+	}
+	__device__ __forceinline__ uint32_t ray_sort_bin(const DFrame& f, const uint32_t slot, const bool has_pixel,
+		const bool camera_ray, const float3 o, const float3 d)
+	{
+		if (!has_pixel) return f.sort_camera_bins + f.sort_bounce_bins;
+		if (camera_ray) return (slot - f.slot_begin) >> 5;
+		const uint32_t dir_log2 = f.sort_dir_bits ? 2u * f.sort_dir_bits : 3u;
+		if (f.sort_dir_major) return f.sort_camera_bins + ((direction_bin(f, d) << (3u * f.sort_bits)) | morton_cell(f, o, f.sort_bits));
+		return f.sort_camera_bins + ((morton_cell(f, o, f.sort_bits) << dir_log2) | direction_bin(f, d));
+	}
+	// one atomic per ray: its rank inside the bin (lanes of a warp that share a bin share the atomic)
+	__device__ __forceinline__ uint32_t bin_rank(uint32_t* bin_count, const uint32_t bin)
+	{
+		const uint32_t peers = __match_any_sync(__activemask(), bin);
+		const uint32_t lane = threadIdx.x & 31u;
+		const uint32_t leader = __ffs(peers) - 1u;
+		uint32_t base = 0u;
+		if (lane == leader) base = atomicAdd(bin_count + bin, uint32_t(__popc(peers)));
+		base = __shfl_sync(peers, base, leader);
+		return base + __popc(peers & ((1u << lane) - 1u));
 	}
 
 	// slot -> pixel: 256-slot chunks cover 16x16 pixels (8 tiles of 8x4, 2 across x 4 down); a warp works through one
@@ -271,7 +312,7 @@ namespace rzb
 
 	// ---------------------------------------------------------------- shadow queue append (warp-ballot compaction)
 	__device__ __forceinline__ void shadow_push(const DFrame& f, bool want, float3 o, float3 d, float dist,
-		uint32_t pixel, float3 contrib)
+		uint32_t pixel, float3 contrib, uint32_t light_class)
 	{
 		const uint32_t active = __activemask();
 		const uint32_t ballot = __ballot_sync(active, want);
@@ -287,6 +328,13 @@ namespace rzb
 		f.sh_o[idx] = make_float4(o.x, o.y, o.z, dist);
 		f.sh_d[idx] = make_float4(d.x, d.y, d.z, __uint_as_float(pixel));
 		f.sh_c[idx] = make_float4(contrib.x, contrib.y, contrib.z, 0.0f);
+		if (f.sh_keys != nullptr)
+		{
+			// shadow rays of one light leave a surface cell in (nearly) one direction: cell-major, light class minor
+			const uint32_t bin = f.sort_shadow_base + ((morton_cell(f, o, f.sort_shadow_bits) << 2) | (light_class & 3u));
+			f.sh_keys[idx] = bin;
+			f.sh_rank[idx] = bin_rank(f.sort_bin_count, bin);
+		}
 	}
 
 	__device__ __forceinline__ bool all_finite(const float3 a, const float3 b, const float3 c)
@@ -426,7 +474,7 @@ namespace rzb
 						const float radiance = Le * Lw + Se * vSw;
 						const float3 c = f3(L.color[0], L.color[1], L.color[2]) * brdf_color * (radiance * inv_pdf) * carry;
 						const bool want = radiance >= 1.0e-4f && all_finite(c, next_o, vPLn);
-						shadow_push(f, want, next_o, vPLn, kFltMax, pixel, c);
+						shadow_push(f, want, next_o, vPLn, kFltMax, pixel, c, li & 1u);
 					}
 				}
 				if (do_spot)
@@ -471,7 +519,7 @@ namespace rzb
 						const float radiance = (Le * Lw + Se * vSw) * sctr * beam;
 						const float3 c = f3(L.color[0], L.color[1], L.color[2]) * brdf_color * (radiance * inv_pdf) * carry;
 						const bool want = b >= 1.0e-4f && beam >= 1.0e-4f && radiance >= 1.0e-4f && all_finite(c, next_o, vPLn);
-						shadow_push(f, want, next_o, vPLn, dPL, pixel, c);
+						shadow_push(f, want, next_o, vPLn, dPL, pixel, c, 2u | (li & 1u));
 					}
 				}
 			}
@@ -510,7 +558,11 @@ namespace rzb
 			f.st_c[slot] = make_float2(thr.y, thr.z);
 		}
 		if (f.sort_keys != nullptr && slot < f.slot_end)
-			f.sort_keys[slot - f.slot_begin] = valid ? ray_sort_key(f, slot, depth == 0u, next_o, next_d) : kSortInvalid;
+		{
+			const uint32_t bin = ray_sort_bin(f, slot, valid, depth == 0u, next_o, next_d);
+			f.sort_keys[slot - f.slot_begin] = bin;
+			f.sort_rank[slot - f.slot_begin] = bin_rank(f.sort_bin_count, bin);
+		}
 	}
 
 	// ---------------------------------------------------------------- k_reproject
@@ -545,6 +597,17 @@ namespace rzb
 		f.accum[p] = acc;
 	}
 
+	// ---------------------------------------------------------------- k_scatter_order
+	// bin offsets (prefix sum over DFrame::sort_bin_count) + rank inside the bin -> position in the order arrays
+	__global__ void __launch_bounds__(256) k_scatter_order(DFrame f, const uint32_t* __restrict__ offsets,
+		uint32_t* __restrict__ order, uint32_t* __restrict__ sh_order)
+	{
+		const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+		if (i < f.slot_end - f.slot_begin) order[offsets[f.sort_keys[i]] + f.sort_rank[i]] = f.slot_begin + i;
+		if (sh_order != nullptr && i < min(f.counters[1], f.shadow_capacity))
+			sh_order[offsets[f.sh_keys[i]] - offsets[f.sort_shadow_base] + f.sh_rank[i]] = i;
+	}
+
 	// ---------------------------------------------------------------- k_trace_shadow
 	// Any-hit queries over the shadow queue, whole-warp batches of 32 entries, free-running lanes, CONSERVATIVE box
 	// test on every tree (64 registers, 8 blocks per SM). The result of a shadow query is the product of the opacities
@@ -570,8 +633,9 @@ namespace rzb
 		{
 			const uint32_t base = warp_batch(&f.counters[2]);
 			if (base >= n) break;
-			const uint32_t i = base + (threadIdx.x & 31u);
+			uint32_t i = base + (threadIdx.x & 31u);
 			const bool active = i < n;
+			if (active && f.sh_order != nullptr) i = f.sh_order[i];
 			float4 o = make_float4(0.0f, 0.0f, 0.0f, 0.0f), d = make_float4(0.0f, 0.0f, 1.0f, 0.0f);
 			if (active) { o = f.sh_o[i]; d = f.sh_d[i]; }
 			RayResult r;
@@ -710,6 +774,22 @@ namespace rzb
 		if (!wait_flags(own->done, a.world, a.epoch, a.spin_limit)) own->timed_out = 1u;
 	}
 
+	// sum of the accumulator's alpha channel (completed paths per pixel): the "spp" a host stops at
+	__global__ void __launch_bounds__(256) k_sum_alpha(const float4* __restrict__ accum, uint32_t n, double* __restrict__ out)
+	{
+		double s = 0.0;
+		for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) s += double(accum[i].w);
+		for (int off = 16; off > 0; off >>= 1) s += __shfl_down_sync(0xFFFFFFFFu, s, off);
+		__shared__ double warp_sum[8];
+		if ((threadIdx.x & 31u) == 0u) warp_sum[threadIdx.x >> 5] = s;
+		__syncthreads();
+		if (threadIdx.x == 0)
+		{
+			double t = 0.0;
+			for (int k = 0; k < 8; ++k) t += warp_sum[k];
+			atomicAdd(out, t);
+		}
+	}
 	__global__ void k_accum_add(float4* __restrict__ accum, const float4* __restrict__ other, uint32_t n)
 	{
 		const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;

@@ -36,6 +36,9 @@ namespace RayZath::Cuda
 {
 	namespace RZ = RayZath::Engine;
 
+	class EngineCore;
+	static EngineCore* g_core = nullptr; // the live engine, for the headless runner's hooks (rzb200_engine_*)
+
 	class EngineCore
 	{
 		struct CameraState
@@ -99,9 +102,71 @@ namespace RayZath::Cuda
 			rzb_ctx* probe = nullptr;
 			if (rzb_create(m_devices[0], &probe) != RZB_OK) fail(nullptr, "B200 render path unavailable");
 			rzb_destroy(probe);
+			g_core = this;
+		}
+		// ---- hooks of the headless task format (task keys "seed", "devices", "spp", "accumulator")
+		void configure(const bool has_seed, const uint64_t seed, const char* devices)
+		{
+			std::lock_guard<std::mutex> lg(m_mtx);
+			if (has_seed) m_seed = seed;
+			if (devices && *devices)
+			{
+				std::vector<int> list;
+				std::stringstream ss(devices);
+				for (std::string tok; std::getline(ss, tok, ',');)
+					if (!tok.empty()) list.push_back(std::atoi(tok.c_str()));
+				if (!list.empty() && list != m_devices)
+				{
+					dropContexts();
+					m_devices = list;
+				}
+			}
+			// a new task starts from a clean accumulation with the new seed
+			for (auto& [idx, cam] : m_cameras) cam.scene_current = false;
+		}
+		double meanSpp(const uint32_t camera)
+		{
+			std::lock_guard<std::mutex> lg(m_mtx);
+			auto it = m_cameras.find(camera);
+			if (it == m_cameras.end()) return 0.0;
+			double sum = 0.0;
+			for (rzb_ctx* c : it->second.ctxs)
+			{
+				double m = 0.0;
+				check(c, rzb_mean_samples(c, &m), "rzb_mean_samples");
+				sum += m; // sample streams of several devices add up
+			}
+			return sum;
+		}
+		bool readAccum(const uint32_t camera, float* out, const size_t floats)
+		{
+			std::lock_guard<std::mutex> lg(m_mtx);
+			auto it = m_cameras.find(camera);
+			if (it == m_cameras.end() || it->second.ctxs.empty()) return false;
+			const size_t n = size_t(it->second.width) * it->second.height * 4;
+			if (floats < n) return false;
+			std::vector<float> tmp;
+			for (size_t d = 0; d < it->second.ctxs.size(); ++d)
+			{
+				if (d == 0) { check(it->second.ctxs[0], rzb_read_accum(it->second.ctxs[0], out), "rzb_read_accum"); continue; }
+				tmp.resize(n);
+				check(it->second.ctxs[d], rzb_read_accum(it->second.ctxs[d], tmp.data()), "rzb_read_accum");
+				for (size_t i = 0; i < n; ++i) out[i] += tmp[i];
+			}
+			return true;
+		}
+		void dropContexts()
+		{
+			for (auto& [idx, cam] : m_cameras)
+			{
+				for (rzb_ctx* c : cam.ctxs) rzb_destroy(c);
+				for (int k = 0; k < 2; ++k) { rzb_host_free(cam.pin_rgba[k]); rzb_host_free(cam.pin_depth[k]); }
+			}
+			m_cameras.clear();
 		}
 		~EngineCore()
 		{
+			if (g_core == this) g_core = nullptr;
 			// RZB200_VERBOSE: leave a trace on stderr that the B200 path (not the CPU fallback) rendered
 			if (std::getenv("RZB200_VERBOSE") && !m_timings.empty())
 				std::fprintf(stderr, "[rzb200] %zu device(s), seed %llu\n%s", m_devices.size(), (unsigned long long)m_seed, m_timings.c_str());
@@ -297,6 +362,25 @@ namespace RayZath::Cuda
 	};
 
 	Engine::Engine() : m_engine_core(std::make_unique<EngineCore>()) {}
+}
+
+// Hooks for the headless runner's extra task keys (linux_port/patch_headless_cpp.py declares them weak, so the same
+// generated headless.cpp also links against the reference's own engines, where the keys are ignored).
+extern "C" void rzb200_engine_configure(int has_seed, unsigned long long seed, const char* devices)
+{
+	if (RayZath::Cuda::g_core) RayZath::Cuda::g_core->configure(has_seed != 0, seed, devices);
+}
+extern "C" double rzb200_engine_mean_spp(unsigned camera)
+{
+	return RayZath::Cuda::g_core ? RayZath::Cuda::g_core->meanSpp(camera) : 0.0;
+}
+extern "C" int rzb200_engine_read_accum(unsigned camera, float* rgba_f32, size_t floats)
+{
+	return RayZath::Cuda::g_core && RayZath::Cuda::g_core->readAccum(camera, rgba_f32, floats) ? 0 : 1;
+}
+
+namespace RayZath::Cuda
+{
 	Engine::~Engine() = default;
 
 	void Engine::renderWorld(RayZath::Engine::World& hWorld, const RayZath::Engine::RenderConfig& render_config,

@@ -84,3 +84,35 @@ def test_instance_tree_growth_falls_back_to_full_upload(tmp_path):
     assert info["rays_after_growth"] == 4 * 8 * 320 * 180  # accumulation restarted with the edit
     f = np.fromfile(out, dtype=np.uint8).reshape(4, 180, 320, 4)[..., :3].astype(np.int32)
     assert np.abs(f[3] - f[2]).mean() > 0.5  # the grown instances are in the picture
+
+
+@pytest.mark.skipif(not os.path.exists(BIN), reason="drop-in binary not built (needs /root/reference at build time)")
+def test_headless_task_keys(tmp_path):
+    """the task keys the reference's runner lacks ("max depth", "seed", "devices", "spp",
+    "accumulator"; linux_port/patch_headless_cpp.py) through the reference-facing entry: BASELINE config 1 (Cornell box,
+    depth 8, 64 spp) reproduced from a task file alone -- the run stops on the spp target, not on the pass budget or the
+    timeout, reports depth 8, and leaves the float accumulator whose alpha channel is the sample count."""
+    import numpy as np
+    w = scenes.cornell(resolution=(256, 256))
+    w.save_reference(str(tmp_path), "scene")
+    json.dump({"tasks": [{"scene path": "scene.json", "engine": ["CUDAGPU"], "rpp": 1000000, "timeout": 120.0,
+                          "max depth": 8, "seed": 5, "devices": "0", "spp": 64, "accumulator": "accum.f32"}]},
+              open(tmp_path / "tasks.json", "w"))
+    os.makedirs(tmp_path / "report")
+    env = dict(os.environ, RZB200_VERBOSE="1")
+    env.pop("RZB200_SEED", None)
+    r = subprocess.run([BIN, "--headless", "tasks.json", "report", "-r"], cwd=tmp_path, env=env, capture_output=True,
+                       text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert "seed 5\n" in r.stderr, r.stderr[-400:]
+    reports = [os.path.join(dp, f) for dp, _, fs in os.walk(tmp_path / "report") for f in fs if f == "report.txt"]
+    text = open(reports[0]).read()
+    assert "max depth: 8" in text, text
+    m = re.search(r"duration: ([0-9.]+)s", text)
+    assert m and float(m.group(1)) < 60.0, text  # stopped by "spp", long before the timeout
+    acc_files = [os.path.join(dp, f) for dp, _, fs in os.walk(tmp_path / "report") for f in fs if f == "accum.f32"]
+    assert len(acc_files) == 1
+    acc = np.fromfile(acc_files[0], dtype=np.float32).reshape(256, 256, 4)
+    spp = float(acc[..., 3].mean())
+    assert 64.0 <= spp < 64.0 * 4, spp  # the check runs between renderWorld calls of up to 1024 passes (auto-tuned)
+    assert np.isfinite(acc).all() and acc[..., :3].sum() > 0

@@ -3,6 +3,8 @@
   * the oracle restatement (oracle/rz_oracle.c) on seeded inputs, up to BASELINE.json's full sizes,
   * size-independent properties of the estimator (sample counting, linearity of accumulation, tone map).
 Integer / index / byte results are bit-exact; floating-point images use the tolerance stated in each test."""
+import os
+
 import numpy as np
 import pytest
 
@@ -10,6 +12,8 @@ import rz_oracle as O
 from rayzath_b200 import capi, scenes
 from rayzath_b200.world import World
 from tests.golden_scenes import GOLDEN_SCENES, RENDER_SETTINGS, shadow_rays
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 pytestmark = pytest.mark.gpu
 NAMES = list(GOLDEN_SCENES)
@@ -619,3 +623,67 @@ def test_incremental_scene_update_keeps_geometry():
             c.reset()
             c.render(4)
         assert np.allclose(a.read_accum(), b.read_accum(), rtol=1e-5, atol=1e-5)
+
+
+# ------------------------------------------------------------------ converged images at BASELINE sizes and sample counts
+CONVERGED = {
+    # name: (world, flags)
+    "config1_cornell_512": lambda: scenes.cornell(resolution=(512, 512)),
+    "config2_materials_1080p": lambda: scenes.materials_scene(resolution=(1920, 1080), res=64, cpu_comparable=True),
+    "config3_heightfield_1m_1080p": lambda: scenes.heightfield_scene(resolution=(1920, 1080)),
+}
+
+
+@pytest.mark.parametrize("name", list(CONVERGED))
+def test_converged_image_at_baseline_spp(name):
+    """BASELINE.json configs 1-3 at their own resolution and sample count (64 / 256 / 64 spp) against the reference CPU
+    engine. The fixture tests/golden/converged_<name>.npz holds k x k block means (k = 4 for 512x512, 8 for 1080p) of
+    TWO independent reference renders A and B (tests/tools/make_golden_images.py, generated where /root/reference
+    exists), i.e. its own Monte-Carlo noise floor. Stated tolerances, all on radiance = rgb sum / sample count:
+      equal spp      block relRMSE(GPU at the BASELINE spp, A) <= 1.1 x block relRMSE(A, B): the GPU estimator is
+                     indistinguishable from a third run of the reference's;
+      converged      GPU at 16x the spp against the mean of A and B: block relRMSE <= 1.1 x relRMSE(A, B) / 2 + 0.003
+                     (what is left is the reference's own noise, halved by averaging), and <= 0.03 on 4x coarser blocks;
+      mean           image mean within 1 % of the reference's."""
+    path = os.path.join(ROOT, "tests", "golden", "converged_%s.npz" % name)
+    if not os.path.exists(path):
+        pytest.skip("fixture not generated")
+    fx = np.load(path)
+    W, H = (int(x) for x in fx["resolution"])
+    k, depth = int(fx["block"][0]), int(fx["max_depth"][0])
+    A, B = fx["block_mean_a"].astype(np.float64), fx["block_mean_b"].astype(np.float64)
+    M = 0.5 * (A + B)
+    spp_ref = float(fx["spp_a"][0])
+    w = CONVERGED[name]()
+
+    def rel(a, b):
+        return float(np.sqrt(np.mean((a - b) ** 2)) / np.mean(b))
+
+    def coarse(img):
+        h, wd = img.shape[0] // 4 * 4, img.shape[1] // 4 * 4
+        return img[:h, :wd].reshape(h // 4, 4, wd // 4, 4, 3).mean(axis=(1, 3))
+
+    with capi.Context(0) as c:
+        c.set_scene(w.flatten())
+        c.set_camera(w.camera_struct())
+        c.set_config(1, 1, depth, capi.FLAG_CPU_SEMANTICS, 77)
+        c.reset()
+        target, results = spp_ref, []
+        for factor in (1.0, 16.0):
+            while c.mean_samples() < spp_ref * factor:
+                c.render(max(8, int(0.25 * int(fx["passes"][0]) * factor)))
+            acc = c.read_accum()
+            rad = acc[..., :3] / np.maximum(acc[..., 3:4], 1.0)
+            results.append((float(acc[..., 3].mean()), _block_mean(rad, H, W, k).astype(np.float64), float(rad.mean())))
+    floor = rel(A, B)
+    (spp1, G1, m1), (spp2, G2, m2) = results
+    ref_mean = 0.5 * (float(fx["mean_a"][0]) + float(fx["mean_b"][0]))
+    print("%s: ref spp %.1f, block-%d relRMSE A-vs-B %.4f | GPU %.0f spp vs A %.4f | GPU %.0f spp vs mean(A,B) %.4f (coarse x4: %.4f) | "
+          "means %.6g / %.6g / %.6g" % (name, spp_ref, k, floor, spp1, rel(G1, A), spp2, rel(G2, M), rel(coarse(G2), coarse(M)),
+                                        ref_mean, m1, m2))
+    assert spp1 < 1.6 * spp_ref
+    assert rel(G1, A) <= 1.1 * floor * np.sqrt(max(spp_ref / spp1, 0.5) * 0.5 + 0.5), (rel(G1, A), floor)
+    assert rel(G2, M) <= 1.1 * floor / 2.0 + 0.003, (rel(G2, M), floor)
+    assert rel(coarse(G2), coarse(M)) <= 0.03
+    assert abs(m2 - ref_mean) / ref_mean < 0.01, (m2, ref_mean)
+    assert abs(m1 - ref_mean) / ref_mean < 0.02, (m1, ref_mean)
