@@ -115,7 +115,7 @@ struct rzb_ctx
 	// bins and a scatter turn that into the slot order the traversal kernels pull their batches in
 	bool sort_enabled = true;
 	uint32_t sort_bits = 5;        // RZB200_SORT_BITS: Morton cells per axis = 2^bits
-	uint32_t sort_dir_bits = 0;    // RZB200_SORT_DIRBITS: 0 = direction octant (8 bins), n = octahedral map with 2^n x 2^n bins
+	uint32_t sort_dir_bits = 3;    // RZB200_SORT_DIRBITS: 0 = direction octant (8 bins), n = octahedral map with 2^n x 2^n bins
 	bool sort_shadow = true;       // RZB200_SORT_SHADOW=0: leave the shadow queue in append order
 	uint32_t sort_shadow_bits = 6; // RZB200_SORT_SHADOW_BITS: Morton cells per axis of the shadow-ray bins
 	bool sort_dir_major = false;   // RZB200_SORT_MAJOR=1: direction bin is the major key, origin cell the minor one
@@ -125,6 +125,12 @@ struct rzb_ctx
 	float sort_min[3] = {0.0f, 0.0f, 0.0f}, sort_extent = 0.0f;
 	float last_sort_ms = 0.0f;
 	uint32_t x_flags = 0;          // internal DScene::flags bits (kFlag*)
+	// closest-hit kernel flavour: several rays per lane with phase voting (rzb_traverse_mr.cuh) or one ray per lane
+	// (RZB200_TRACE=lane); RZB200_MR_BLOCKS caps the resident blocks per SM of the former (more L1 per block)
+	bool trace_mr = true;
+	int mr_blocks = 0;
+	int mr_grid[2] = {0, 0};       // [FAST]
+	size_t mr_smem = 0;
 };
 
 namespace
@@ -338,6 +344,8 @@ extern "C" int rzb_create(int device, rzb_ctx** out)
 	cudaMemsetAsync(ctx->d_counters, 0, 256, ctx->stream);
 	ctx->debug_sync = std::getenv("RZB200_DEBUG_SYNC") != nullptr;
 	if (const char* env = std::getenv("RZB200_CARVEOUT")) ctx->set_carveout = std::atoi(env) != 0;
+	if (const char* env = std::getenv("RZB200_TRACE")) ctx->trace_mr = std::string(env) != "lane";
+	if (const char* env = std::getenv("RZB200_MR_BLOCKS")) ctx->mr_blocks = std::atoi(env);
 	if (const char* env = std::getenv("RZB200_SORT")) ctx->sort_enabled = std::atoi(env) != 0;
 	if (const char* env = std::getenv("RZB200_SORT_BITS")) ctx->sort_bits = uint32_t(std::min(std::max(std::atoi(env), 1), 6));
 	if (const char* env = std::getenv("RZB200_SORT_DIRBITS")) ctx->sort_dir_bits = uint32_t(std::min(std::max(std::atoi(env), 0), 4));
@@ -350,6 +358,33 @@ extern "C" int rzb_create(int device, rzb_ctx** out)
 	ctx->trace_grid_fast = gridFor(ctx, reinterpret_cast<const void*>(&k_trace_paths<false, true>), kTraceBlock);
 	ctx->rays_grid = gridFor(ctx, reinterpret_cast<const void*>(&k_trace_rays<false, false>), kTraceBlock);
 	ctx->any_grid = gridFor(ctx, reinterpret_cast<const void*>(&k_trace_any_rays), kTraceBlock);
+	{
+		// multi-ray kernels: dynamic shared memory = the rays' hot state, padded when fewer resident blocks are asked for
+		const size_t need = size_t(kMrFields) * kMrRays * kMrBlock * sizeof(float4);
+		int max_smem = 0;
+		cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerMultiprocessor, device);
+		size_t bytes = need;
+		if (ctx->mr_blocks > 0 && max_smem > 0)
+			bytes = std::max(need, std::min<size_t>(size_t(max_smem) / size_t(ctx->mr_blocks + 1) + 1024, size_t(max_smem) / size_t(ctx->mr_blocks) - 1024));
+		ctx->mr_smem = bytes;
+		const void* kernels[6] = {reinterpret_cast<const void*>(&k_trace_paths_mr<false, false>), reinterpret_cast<const void*>(&k_trace_paths_mr<false, true>),
+			reinterpret_cast<const void*>(&k_trace_paths_mr<true, false>), reinterpret_cast<const void*>(&k_trace_paths_mr<true, true>),
+			reinterpret_cast<const void*>(&k_trace_rays_mr<false, false>), reinterpret_cast<const void*>(&k_trace_rays_mr<false, true>)};
+		for (int i = 0; i < 6; ++i)
+		{
+			cudaFuncSetAttribute(kernels[i], cudaFuncAttributeMaxDynamicSharedMemorySize, int(bytes));
+			int per_sm = 0;
+			if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernels[i], kMrBlock, bytes) != cudaSuccess || per_sm < 1) per_sm = 1;
+			if (ctx->set_carveout && max_smem > 0)
+			{
+				const int pct = int(std::min<size_t>(100, (size_t(per_sm) * (bytes + 1024) * 100 + size_t(max_smem) - 1) / size_t(max_smem)));
+				cudaFuncSetAttribute(kernels[i], cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+				if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernels[i], kMrBlock, bytes) != cudaSuccess || per_sm < 1) per_sm = 1;
+			}
+			if (i < 2) ctx->mr_grid[i] = ctx->sm_count * per_sm;
+		}
+		cudaGetLastError();
+	}
 	*out = ctx;
 	return RZB_OK;
 }
@@ -896,7 +931,13 @@ extern "C" int rzb_render(rzb_ctx* ctx, uint32_t passes)
 		RZB_CUDA(ctx, cudaMemsetAsync(ctx->d_counters, 0, 12, ctx->stream));
 		f.order = (ctx->sort_enabled && ctx->order_valid) ? static_cast<const uint32_t*>(ctx->sort_buf[rzb_ctx::kSortOrder].ptr) : nullptr;
 		if (timed) cudaEventRecord(ev[0], ctx->stream);
-		if (count) { if (fast) k_trace_paths<true, true><<<ctx->trace_grid_fast, kTraceBlock, 0, ctx->stream>>>(ctx->sc, f); else k_trace_paths<true, false><<<ctx->trace_grid, kTraceBlock, 0, ctx->stream>>>(ctx->sc, f); }
+		if (ctx->trace_mr)
+		{
+			const int grid = ctx->mr_grid[fast ? 1 : 0];
+			if (count) { if (fast) k_trace_paths_mr<true, true><<<grid, kMrBlock, ctx->mr_smem, ctx->stream>>>(ctx->sc, f); else k_trace_paths_mr<true, false><<<grid, kMrBlock, ctx->mr_smem, ctx->stream>>>(ctx->sc, f); }
+			else { if (fast) k_trace_paths_mr<false, true><<<grid, kMrBlock, ctx->mr_smem, ctx->stream>>>(ctx->sc, f); else k_trace_paths_mr<false, false><<<grid, kMrBlock, ctx->mr_smem, ctx->stream>>>(ctx->sc, f); }
+		}
+		else if (count) { if (fast) k_trace_paths<true, true><<<ctx->trace_grid_fast, kTraceBlock, 0, ctx->stream>>>(ctx->sc, f); else k_trace_paths<true, false><<<ctx->trace_grid, kTraceBlock, 0, ctx->stream>>>(ctx->sc, f); }
 		else { if (fast) k_trace_paths<false, true><<<ctx->trace_grid_fast, kTraceBlock, 0, ctx->stream>>>(ctx->sc, f); else k_trace_paths<false, false><<<ctx->trace_grid, kTraceBlock, 0, ctx->stream>>>(ctx->sc, f); }
 		if (ctx->debug_sync)
 		{
@@ -1388,6 +1429,11 @@ extern "C" int rzb_trace_closest_device(rzb_ctx* ctx, const void* rays_o_near, c
 	DeviceGuard guard(ctx->device);
 	RZB_CUDA(ctx, cudaMemsetAsync(ctx->d_counters + 8, 0, 4, ctx->stream));
 	if (elapsed_ms) RZB_CUDA(ctx, cudaEventRecord(ctx->ev_begin, ctx->stream));
+	if (ctx->trace_mr)
+		(ctx->own_trees ? k_trace_rays_mr<false, true> : k_trace_rays_mr<false, false>)<<<ctx->mr_grid[ctx->own_trees ? 1 : 0], kMrBlock, ctx->mr_smem, ctx->stream>>>(ctx->sc,
+			static_cast<const float4*>(rays_o_near), static_cast<const float4*>(rays_d_far), n,
+			static_cast<DHit*>(hits_out_device), ctx->d_counters + 8, nullptr);
+	else
 	(ctx->own_trees ? k_trace_rays<false, true> : k_trace_rays<false, false>)<<<ctx->rays_grid, kTraceBlock, 0, ctx->stream>>>(ctx->sc,
 		static_cast<const float4*>(rays_o_near), static_cast<const float4*>(rays_d_far), n,
 		static_cast<DHit*>(hits_out_device), ctx->d_counters + 8, nullptr);
@@ -1436,6 +1482,10 @@ extern "C" int rzb_trace_closest(rzb_ctx* ctx, const float* origins, const float
 		(ctx->own_trees ? k_trace_rays<true, true> : k_trace_rays<true, false>)<<<ctx->rays_grid, kTraceBlock, 0, ctx->stream>>>(ctx->sc,
 			static_cast<const float4*>(ctx->scratch[0].ptr), static_cast<const float4*>(ctx->scratch[1].ptr), n,
 			static_cast<DHit*>(ctx->scratch[2].ptr), ctx->d_counters + 8, d_stats);
+	else if (ctx->trace_mr)
+		(ctx->own_trees ? k_trace_rays_mr<false, true> : k_trace_rays_mr<false, false>)<<<ctx->mr_grid[ctx->own_trees ? 1 : 0], kMrBlock, ctx->mr_smem, ctx->stream>>>(ctx->sc,
+			static_cast<const float4*>(ctx->scratch[0].ptr), static_cast<const float4*>(ctx->scratch[1].ptr), n,
+			static_cast<DHit*>(ctx->scratch[2].ptr), ctx->d_counters + 8, nullptr);
 	else
 		(ctx->own_trees ? k_trace_rays<false, true> : k_trace_rays<false, false>)<<<ctx->rays_grid, kTraceBlock, 0, ctx->stream>>>(ctx->sc,
 			static_cast<const float4*>(ctx->scratch[0].ptr), static_cast<const float4*>(ctx->scratch[1].ptr), n,

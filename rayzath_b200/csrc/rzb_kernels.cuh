@@ -19,6 +19,7 @@
 #pragma once
 
 #include "rzb_shade.cuh"
+#include "rzb_traverse_mr.cuh"
 
 namespace rzb
 {
@@ -308,6 +309,147 @@ namespace rzb
 			f.hit_inst[slot] = r.inst;
 		}
 		if (STATS) flush_counters(cnt, f.work);
+	}
+
+	// ---------------------------------------------------------------- multi-ray-per-lane closest hit (rzb_traverse_mr.cuh)
+	// The warp loop shared by k_trace_paths_mr and k_trace_rays_mr. `Source` hands out work items and takes results:
+	//   uint32_t total() const; uint32_t* counter() const;
+	//   bool load(idx, handle, o, d, near, far, user)   false: the item has no ray (a slot without a pixel)
+	//   void store(handle, user, result)
+	template <bool STATS, bool FAST, class Source>
+	__device__ __forceinline__ void mr_run(const DScene& sc, const Source& src, float4* smem, unsigned long long* work_out,
+		unsigned long long* occupancy_out)
+	{
+		MrHot hot{smem + threadIdx.x};
+		MrCold cold;
+		MrLane lane{0u, 0u};
+		TraceCounters cnt{0u, 0u, 0u, 0u};
+		const uint32_t lane_id = threadIdx.x & 31u;
+		const uint32_t n = src.total();
+		bool work_left = true;
+		uint32_t occ_active = 0u, occ_rounds = 0u;
+		for (;;)
+		{
+			const uint32_t phase = mr_vote(lane, work_left);
+			if (phase == kMrDead) break;
+			int k = -1;
+			if (phase == kMrNode)
+			{
+				k = lane.pick(kMrNode);
+				if (k >= 0) mr_node<FAST, STATS>(sc, hot, cold, lane, k, cnt);
+			}
+			else if (phase == kMrLeaf)
+			{
+				k = lane.pick(kMrLeaf);
+				if (k >= 0) mr_leaf<FAST, STATS>(sc, hot, cold, lane, k, cnt);
+			}
+			else if (phase == kMrHeavy)
+			{
+				k = lane.pick(kMrHeavy);
+				if (k >= 0) mr_heavy<FAST, STATS>(sc, hot, cold, lane, k, cnt);
+			}
+			else
+			{
+				// F: write the finished ray's record, then pull the next work item (one atomic per warp and round)
+				k = lane.pick(kMrDone);
+				if (k >= 0)
+				{
+					RayResult r;
+					mr_result(hot, cold, k, r);
+					src.store(cold.handle[k], cold.user[k], r);
+					lane.set_tag(k, kMrEmpty);
+				}
+				else if (work_left) k = lane.pick(kMrEmpty);
+				const bool want = k >= 0 && work_left;
+				const uint32_t wanting = __ballot_sync(0xFFFFFFFFu, want);
+				uint32_t base = 0u;
+				if (wanting != 0u)
+				{
+					const uint32_t leader = __ffs(wanting) - 1u;
+					if (lane_id == leader) base = atomicAdd(src.counter(), uint32_t(__popc(wanting)));
+					base = __shfl_sync(0xFFFFFFFFu, base, leader);
+					if (base + uint32_t(__popc(wanting)) >= n) work_left = false;
+				}
+				if (want)
+				{
+					const uint32_t idx = base + __popc(wanting & ((1u << lane_id) - 1u));
+					if (idx < n)
+					{
+						V3 o, d;
+						float near_, far_;
+						uint32_t handle, user;
+						if (src.load(idx, handle, o, d, near_, far_, user))
+						{
+							cold.handle[k] = handle; cold.user[k] = user;
+							mr_begin<FAST, STATS>(sc, hot, cold, lane, k, o, d, near_, far_, cnt);
+						}
+					}
+					else lane.set_tag(k, kMrDead);
+				}
+			}
+			if (STATS)
+			{
+				occ_active += __popc(__ballot_sync(0xFFFFFFFFu, k >= 0));
+				occ_rounds += 32u;
+			}
+		}
+		if (STATS)
+		{
+			flush_counters(cnt, work_out);
+			if (lane_id == 0u && occupancy_out)
+			{
+				atomicAdd(occupancy_out, (unsigned long long)occ_active);
+				atomicAdd(occupancy_out + 1, (unsigned long long)occ_rounds);
+			}
+		}
+	}
+
+	struct PathSource
+	{
+		const DScene* sc;
+		const DFrame* f;
+		__device__ __forceinline__ uint32_t total() const { return f->slot_end - f->slot_begin; }
+		__device__ __forceinline__ uint32_t* counter() const { return &f->counters[0]; }
+		__device__ __forceinline__ bool load(const uint32_t idx, uint32_t& slot, V3& o, V3& d, float& near_, float& far_, uint32_t& flags) const
+		{
+			slot = f->order != nullptr ? f->order[idx] : f->slot_begin + idx;
+			uint32_t x, y;
+			if (!slot_to_pixel(*f, slot, x, y)) return false;
+			const float4 so = f->st_o[slot], sd = f->st_d[slot];
+			const uint32_t bits = __float_as_uint(so.w);
+			const uint32_t depth = bits & 0xFFu, medium = bits >> kMediumShift;
+			near_ = 0.0f; far_ = kFltMax;
+			if (depth == 0u) { near_ = f->cam.near_; far_ = f->cam.far_; }
+			flags = 0u;
+			// World::closestIntersection: free flight in the current medium first (cuda_material.cuh:141-159)
+			if (!(sc->flags & RZB_FLAG_CPU_SEMANTICS))
+			{
+				const float sigma = sc->materials[medium].scattering;
+				if (sigma > 1.0e-4f)
+				{
+					Rng rng(f->seed, slot, f->pass_index);
+					const float dist = (-__logf(rng.next() + 1.0e-4f)) / sigma;
+					if (dist < far_) { far_ = dist; flags |= kHitScatterBit; }
+				}
+			}
+			o = v3(so.x, so.y, so.z); d = v3(sd.x, sd.y, sd.z);
+			return true;
+		}
+		__device__ __forceinline__ void store(const uint32_t slot, const uint32_t flags, const RayResult& r) const
+		{
+			uint32_t tri_bits = flags | (r.external ? kHitExternalBit : 0u);
+			tri_bits |= (r.tri == kNoIndex) ? kHitTriMask : (r.tri & kHitTriMask);
+			f->hit_a[slot] = make_float4(r.t, r.b1, r.b2, __uint_as_float(tri_bits));
+			f->hit_inst[slot] = r.inst;
+		}
+	};
+
+	template <bool STATS, bool FAST>
+	__global__ void __launch_bounds__(kMrBlock, 5) k_trace_paths_mr(DScene sc, DFrame f)
+	{
+		extern __shared__ float4 mr_smem[]; // [kMrFields][kMrRays][kMrBlock] (+ padding that only limits blocks per SM)
+		const PathSource src{&sc, &f};
+		mr_run<STATS, FAST>(sc, src, mr_smem, f.work, f.work + 10);
 	}
 
 	// ---------------------------------------------------------------- shadow queue append (warp-ballot compaction)
@@ -837,6 +979,40 @@ namespace rzb
 			dst[1] = make_float4(__uint_as_float(r.inst), __uint_as_float(STATS ? r.steps : 0u), __uint_as_float(STATS ? r.tris : 0u), 0.0f);
 		}
 		if (STATS) flush_counters(cnt, stats);
+	}
+
+	struct RaySetSource
+	{
+		const float4* ray_o_near;
+		const float4* ray_d_far;
+		DHit* hits;
+		uint32_t* cnt;
+		uint32_t n;
+		__device__ __forceinline__ uint32_t total() const { return n; }
+		__device__ __forceinline__ uint32_t* counter() const { return cnt; }
+		__device__ __forceinline__ bool load(const uint32_t idx, uint32_t& handle, V3& o, V3& d, float& near_, float& far_, uint32_t& user) const
+		{
+			const float4 ro = __ldg(ray_o_near + idx), rd = __ldg(ray_d_far + idx);
+			handle = idx; user = 0u;
+			o = v3(ro.x, ro.y, ro.z); d = v3(rd.x, rd.y, rd.z);
+			near_ = ro.w; far_ = rd.w;
+			return true;
+		}
+		__device__ __forceinline__ void store(const uint32_t idx, const uint32_t, const RayResult& r) const
+		{
+			const uint32_t tri_bits = (r.tri == kNoIndex ? kHitTriMask : (r.tri & kHitTriMask)) | (r.external ? kHitExternalBit : 0u);
+			float4* dst = reinterpret_cast<float4*>(hits + idx);
+			dst[0] = make_float4(r.t, r.b1, r.b2, __uint_as_float(tri_bits));
+			dst[1] = make_float4(__uint_as_float(r.inst), 0.0f, 0.0f, 0.0f);
+		}
+	};
+	template <bool STATS, bool FAST>
+	__global__ void __launch_bounds__(kMrBlock, 5) k_trace_rays_mr(DScene sc, const float4* __restrict__ ray_o_near,
+		const float4* __restrict__ ray_d_far, uint32_t n, DHit* __restrict__ hits, uint32_t* counter, unsigned long long* stats)
+	{
+		extern __shared__ float4 mr_smem[];
+		const RaySetSource src{ray_o_near, ray_d_far, hits, counter, n};
+		mr_run<STATS, FAST>(sc, src, mr_smem, stats, nullptr);
 	}
 
 	__global__ void k_convert_hits(DScene sc, const DHit* __restrict__ in, rzb_hit* __restrict__ out, uint32_t n)

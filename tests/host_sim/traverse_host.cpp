@@ -17,12 +17,15 @@ static inline uint32_t __float_as_uint(float f) { uint32_t u; std::memcpy(&u, &f
 static inline float __uint_as_float(uint32_t u) { float f; std::memcpy(&f, &u, 4); return f; }
 template <typename T> static inline T __ldg(const T* p) { return *p; }
 static inline int __any_sync(unsigned, int p) { return p; }
+static inline unsigned __ballot_sync(unsigned, int p) { return p ? 1u : 0u; }
+static inline int __popc(unsigned v) { return __builtin_popcount(v); }
 struct { unsigned x = 0; } threadIdx;
 #define RZB_HOST_SIM 1
 #ifndef __noinline__
 #define __noinline__ __attribute__((noinline))
 #endif
 #include "../../rayzath_b200/csrc/rzb_traverse.cuh"
+#include "../../rayzath_b200/csrc/rzb_traverse_mr.cuh"
 
 using namespace rzb;
 
@@ -35,8 +38,23 @@ namespace rzb
 	}
 }
 
+static int trav_host_run_impl(const rzb_scene* s, const float* origins, const float* dirs, const float* near_far, uint32_t n,
+	int any, rzb_hit* hits_out, float* masks_out, uint64_t* counters4, int mr);
+
 extern "C" int trav_host_run(const rzb_scene* s, const float* origins, const float* dirs, const float* near_far, uint32_t n,
 	int any, rzb_hit* hits_out, float* masks_out, uint64_t* counters4)
+{
+	return trav_host_run_impl(s, origins, dirs, near_far, n, any, hits_out, masks_out, counters4, 0);
+}
+// the multi-ray-per-lane walk (rzb_traverse_mr.cuh): ONE lane with kMrRays rays in flight, phases chosen by mr_vote
+extern "C" int trav_host_run_mr(const rzb_scene* s, const float* origins, const float* dirs, const float* near_far, uint32_t n,
+	rzb_hit* hits_out, uint64_t* counters4)
+{
+	return trav_host_run_impl(s, origins, dirs, near_far, n, 0, hits_out, nullptr, counters4, 1);
+}
+
+static int trav_host_run_impl(const rzb_scene* s, const float* origins, const float* dirs, const float* near_far, uint32_t n,
+	int any, rzb_hit* hits_out, float* masks_out, uint64_t* counters4, int mr)
 {
 	// build the device layout exactly like rzb_set_scene does (single mesh table walk, host side)
 	std::vector<uint32_t> mesh_base(s->mesh_count, kNoIndex);
@@ -100,6 +118,57 @@ extern "C" int trav_host_run(const rzb_scene* s, const float* origins, const flo
 	sc.instance_count = s->instance_count;
 	sc.flags = RZB_FLAG_CPU_SEMANTICS;
 
+	if (mr)
+	{
+		std::vector<float4> smem(size_t(kMrFields) * kMrRays * kMrBlock);
+		MrHot hot{smem.data()};
+		static MrCold cold;
+		MrLane lane{0u, 0u};
+		TraceCounters cnt{0u, 0u, 0u, 0u};
+		uint32_t next_ray = 0;
+		auto write = [&](int k) {
+			RayResult r;
+			mr_result(hot, cold, k, r);
+			const uint32_t i = cold.handle[k];
+			rzb_hit h{};
+			h.instance = RZB_NO_INDEX; h.triangle = RZB_NO_INDEX;
+			h.t = r.t;
+			if (r.inst != kNoIndex)
+			{
+				h.instance = s->instances[r.inst].host_index;
+				h.triangle = s->tri_host_index ? s->tri_host_index[r.tri] : r.tri;
+				h.b1 = r.b1; h.b2 = r.b2; h.external = r.external ? 1u : 0u;
+			}
+			hits_out[i] = h;
+		};
+		for (;;)
+		{
+			const bool work_left = next_ray < n;
+			const uint32_t phase = mr_vote(lane, work_left);
+			if (phase == kMrDead) break;
+			if (phase == kMrNode) mr_node<false, true>(sc, hot, cold, lane, lane.pick(kMrNode), cnt);
+			else if (phase == kMrLeaf) mr_leaf<false, true>(sc, hot, cold, lane, lane.pick(kMrLeaf), cnt);
+			else if (phase == kMrHeavy) mr_heavy<false, true>(sc, hot, cold, lane, lane.pick(kMrHeavy), cnt);
+			else
+			{
+				int k = lane.pick(kMrDone);
+				if (k >= 0) { write(k); lane.set_tag(k, kMrEmpty); }
+				else if (work_left) k = lane.pick(kMrEmpty);
+				if (k >= 0 && work_left)
+				{
+					const uint32_t i = next_ray++;
+					cold.handle[k] = i; cold.user[k] = 0u;
+					mr_begin<false, true>(sc, hot, cold, lane, k, v3(origins[3 * i], origins[3 * i + 1], origins[3 * i + 2]),
+						v3(dirs[3 * i], dirs[3 * i + 1], dirs[3 * i + 2]), near_far[2 * i], near_far[2 * i + 1], cnt);
+				}
+			}
+		}
+		if (counters4)
+		{
+			counters4[0] = cnt.top_nodes; counters4[1] = cnt.instances; counters4[2] = cnt.mesh_nodes; counters4[3] = cnt.triangles;
+		}
+		return 0;
+	}
 	std::vector<uint2> smem(size_t(kSmemStack) * kTraceBlock);
 	Stack st;
 	st.smem = smem.data();

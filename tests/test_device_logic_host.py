@@ -22,13 +22,14 @@ NAMES = list(GOLDEN_SCENES)
 @pytest.fixture(scope="module")
 def sim():
     os.makedirs(os.path.dirname(OUT), exist_ok=True)
-    deps = [SRC] + [os.path.join(ROOT, "rayzath_b200", "csrc", f) for f in ("rzb_traverse.cuh", "rzb_device.cuh")]
+    deps = [SRC] + [os.path.join(ROOT, "rayzath_b200", "csrc", f) for f in ("rzb_traverse.cuh", "rzb_traverse_mr.cuh", "rzb_device.cuh")]
     if not os.path.exists(OUT) or any(os.path.getmtime(d) > os.path.getmtime(OUT) for d in deps):
         subprocess.run(["g++", "-std=c++17", "-O1", "-fPIC", "-shared", "-ffp-contract=off", "-I/usr/local/cuda/include",
                         "-o", OUT, SRC], check=True)
     lib = C.CDLL(OUT)
     P = C.c_void_p
     lib.trav_host_run.argtypes = [P, P, P, P, C.c_uint32, C.c_int, P, P, P]
+    lib.trav_host_run_mr.argtypes = [P, P, P, P, C.c_uint32, P, P]
     return lib
 
 
@@ -83,3 +84,35 @@ def test_device_any_hit_logic_matches_reference(name, sim, golden, flats):
     sim.trav_host_run(C.addressof(scene.struct), so.ctypes.data, sd.ctypes.data, snf.ctypes.data, len(so), 1, None,
                       masks.ctypes.data, None)
     assert np.array_equal(masks, g["masks"])
+
+
+def _closest_mr(lib, scene, o, d, nf):
+    o, d, nf = (np.ascontiguousarray(x, dtype=np.float32) for x in (o, d, nf))
+    hits = np.zeros(len(o), dtype=capi.hit_dtype)
+    cnt = np.zeros(4, np.uint64)
+    lib.trav_host_run_mr(C.addressof(scene.struct), o.ctypes.data, d.ctypes.data, nf.ctypes.data, len(o), hits.ctypes.data,
+                         cnt.ctypes.data)
+    return hits, cnt
+
+
+@pytest.mark.parametrize("name", NAMES)
+def test_multi_ray_lane_walk_matches_oracle(name, sim, golden, flats):
+    """rzb_traverse_mr.cuh (several rays per lane, phase voting) on the host: one lane with kMrRays rays in flight. Every
+    ray must perform exactly the oracle's operation sequence -- records bit-equal, box / instance / triangle counts equal --
+    on the golden primary rays and on 20,000 incoherent rays."""
+    g = golden[name]
+    scene = O.Scene(flats[name])
+    rng = np.random.default_rng(5)
+    n = 20000
+    io = rng.uniform(-3, 3, (n, 3)).astype(np.float32)
+    io[:, 1] = rng.uniform(0.05, 3, n)
+    idd = rng.normal(size=(n, 3)).astype(np.float32)
+    idd = (idd / np.sqrt((idd * idd).sum(axis=1, dtype=np.float32))[:, None]).astype(np.float32)
+    inf = np.tile(np.array([0.0, 3.0e38], dtype=np.float32), (n, 1))
+    o = np.concatenate([g["ray_origins"], io])
+    d = np.concatenate([g["ray_directions"], idd])
+    nf = np.concatenate([g["ray_near_far"], inf])
+    hits, cnt = _closest_mr(sim, scene, o, d, nf)
+    ref, rst = O.trace_closest(scene, o, d, nf, order=O.ORDER_CUDA, minmax=O.MINMAX_FMINF, stats=True)
+    assert np.array_equal(hits.view(np.uint8), ref.view(np.uint8))
+    assert cnt.tolist() == [int(rst[k]) for k in ("top_nodes", "instances_entered", "mesh_nodes", "triangles")]
