@@ -389,6 +389,14 @@ int rzb_build_mesh_bvh_sah(const float* vertices, uint32_t nv, const uint32_t* t
 int rzb_build_mesh_bvh_lbvh(int device, const float* vertices, uint32_t nv, const uint32_t* tris, uint32_t nt,
 	uint32_t max_leaf, rzb_node* nodes_out, uint32_t node_capacity, uint32_t* node_count_out, uint32_t* order_out,
 	float* device_ms_out);
+/* Refit: the vertices of a mesh moved, its triangle list did not -- recompute the boxes of an existing
+ * tree (any builder's) bottom-up, keeping its topology and triangle order: leaf box = exact min / max of its triangles'
+ * vertices, inner box = union of the children's. The result is a valid tree for the deformed mesh (closest-hit records equal
+ * a fresh build's except exact ties) but no longer the tree the reference's builder would make for it: upload it with
+ * RZB_SCENE_OWN_TREES. nodes is updated in place; order as returned by the builder. O(triangles) on the host
+ * (a full GPU rebuild of 1M triangles with rzb_build_mesh_bvh_lbvh takes ~2.5 ms of device time). */
+int rzb_refit_mesh_bvh(const float* vertices, uint32_t nv, const uint32_t* tris, uint32_t nt,
+	rzb_node* nodes, uint32_t node_count, const uint32_t* order);
 /* Instance BVH (bvh_tree_node.hpp:117-215 + cuda_bvh.cuh:86-111): boxes[n][6] = min xyz, max xyz. */
 int rzb_build_instance_bvh(const float* boxes, uint32_t n,
 	rzb_node* nodes_out, uint32_t node_capacity, uint32_t* node_count_out, uint32_t* order_out);

@@ -135,6 +135,7 @@ SYMBOLS = {
                                           C.POINTER(C.c_float)]),
     "rzb_build_mesh_bvh_sah": (C.c_int, [_P, C.c_uint32, _P, C.c_uint32, C.c_uint32, _P, C.c_uint32, C.POINTER(C.c_uint32), _P]),
     "rzb_build_instance_bvh": (C.c_int, [_P, C.c_uint32, _P, C.c_uint32, C.POINTER(C.c_uint32), _P]),
+    "rzb_refit_mesh_bvh": (C.c_int, [_P, C.c_uint32, _P, C.c_uint32, _P, C.c_uint32, _P]),
     "rzb_rotation_axes": (C.c_int, [_P, C.c_int, _P]),
     "rzb_instance_bbox": (C.c_int, [_P, C.c_uint32, _P, _P, _P, _P]),
     "rzb_face_normals": (C.c_int, [_P, C.c_uint32, _P, C.c_uint32, _P]),
@@ -229,6 +230,19 @@ def build_mesh_bvh_sah(vertices: np.ndarray, tris: np.ndarray, max_leaf: int = 8
     if rc:
         raise RzbError(rc, "rzb_build_mesh_bvh_sah failed")
     return nodes[:count.value].copy(), order
+
+
+def refit_mesh_bvh(vertices: np.ndarray, tris: np.ndarray, nodes: np.ndarray, order: np.ndarray) -> np.ndarray:
+    """rzb_refit_mesh_bvh: new boxes for an existing tree after the vertices moved (topology and order kept).
+    Returns the refitted copy of `nodes`."""
+    v = _c(vertices, f4).reshape(-1, 3)
+    t = _c(tris, u4).reshape(-1, 3)
+    out = np.ascontiguousarray(nodes, dtype=node_dtype).copy()
+    o = _c(order, u4)
+    rc = lib().rzb_refit_mesh_bvh(v.ctypes.data, v.shape[0], t.ctypes.data, t.shape[0], out.ctypes.data, out.shape[0], o.ctypes.data)
+    if rc:
+        raise RzbError(rc, "rzb_refit_mesh_bvh failed")
+    return out
 
 
 def build_mesh_bvh_lbvh(vertices: np.ndarray, tris: np.ndarray, max_leaf: int = 4, device: int = 0, timing=False):

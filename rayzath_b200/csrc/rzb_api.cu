@@ -125,10 +125,11 @@ struct rzb_ctx
 	float sort_min[3] = {0.0f, 0.0f, 0.0f}, sort_extent = 0.0f;
 	float last_sort_ms = 0.0f;
 	uint32_t x_flags = 0;          // internal DScene::flags bits (kFlag*)
-	// closest-hit kernel flavour: several rays per lane with phase voting (rzb_traverse_mr.cuh) or one ray per lane
-	// (RZB200_TRACE=lane); RZB200_MR_BLOCKS caps the resident blocks per SM of the former (more L1 per block)
-	bool trace_mr = true;
-	int mr_blocks = 0;
+	// closest-hit kernel flavour: one ray per lane (default) or several rays per lane with phase voting
+	// (rzb_traverse_mr.cuh, RZB200_TRACE=mr: measured slower on B200, DESIGN.md section 4 -- kept as the measured
+	// alternative; RZB200_MR_RAYS = rays per lane, RZB200_MR_BLOCKS caps its resident blocks per SM)
+	bool trace_mr = false;
+	int mr_blocks = 0, mr_k = 2, mr_steps = 2;
 	int mr_grid[2] = {0, 0};       // [FAST]
 	size_t mr_smem = 0;
 };
@@ -315,6 +316,32 @@ extern "C" const char* rzb_last_error(const rzb_ctx* ctx)
 	return ctx ? ctx->error.c_str() : g_create_error.c_str();
 }
 
+namespace
+{
+	typedef void (*MrPathKernel)(DScene, DFrame);
+	typedef void (*MrRaysKernel)(DScene, const float4*, const float4*, uint32_t, DHit*, uint32_t*, unsigned long long*);
+	template <int K, int STEPS>
+	MrPathKernel mrPathKernelKS(const bool stats, const bool fast)
+	{
+		if (stats) return fast ? &k_trace_paths_mr<K, STEPS, true, true> : &k_trace_paths_mr<K, STEPS, true, false>;
+		return fast ? &k_trace_paths_mr<K, STEPS, false, true> : &k_trace_paths_mr<K, STEPS, false, false>;
+	}
+	const void* mrPathKernel(const int k, const int steps, const bool stats, const bool fast)
+	{
+		(void)steps; // instantiated: 2 or 4 rays per lane, two pair steps per node round
+		const MrPathKernel f = k <= 2 ? mrPathKernelKS<2, 2>(stats, fast) : mrPathKernelKS<4, 2>(stats, fast);
+		return reinterpret_cast<const void*>(f);
+	}
+	template <int K, int STEPS>
+	MrRaysKernel mrRaysKernelKS(const bool fast) { return fast ? &k_trace_rays_mr<K, STEPS, false, true> : &k_trace_rays_mr<K, STEPS, false, false>; }
+	const void* mrRaysKernel(const int k, const int steps, const bool fast)
+	{
+		(void)steps;
+		const MrRaysKernel f = k <= 2 ? mrRaysKernelKS<2, 2>(fast) : mrRaysKernelKS<4, 2>(fast);
+		return reinterpret_cast<const void*>(f);
+	}
+}
+
 extern "C" int rzb_create(int device, rzb_ctx** out)
 {
 	if (!out) return fail(nullptr, RZB_ERR_INVALID, "rzb_create: out is NULL");
@@ -344,7 +371,7 @@ extern "C" int rzb_create(int device, rzb_ctx** out)
 	cudaMemsetAsync(ctx->d_counters, 0, 256, ctx->stream);
 	ctx->debug_sync = std::getenv("RZB200_DEBUG_SYNC") != nullptr;
 	if (const char* env = std::getenv("RZB200_CARVEOUT")) ctx->set_carveout = std::atoi(env) != 0;
-	if (const char* env = std::getenv("RZB200_TRACE")) ctx->trace_mr = std::string(env) != "lane";
+	if (const char* env = std::getenv("RZB200_TRACE")) ctx->trace_mr = std::string(env) == "mr";
 	if (const char* env = std::getenv("RZB200_MR_BLOCKS")) ctx->mr_blocks = std::atoi(env);
 	if (const char* env = std::getenv("RZB200_SORT")) ctx->sort_enabled = std::atoi(env) != 0;
 	if (const char* env = std::getenv("RZB200_SORT_BITS")) ctx->sort_bits = uint32_t(std::min(std::max(std::atoi(env), 1), 6));
@@ -352,37 +379,45 @@ extern "C" int rzb_create(int device, rzb_ctx** out)
 	if (const char* env = std::getenv("RZB200_SORT_SHADOW")) ctx->sort_shadow = std::atoi(env) != 0;
 	if (const char* env = std::getenv("RZB200_SORT_SHADOW_BITS")) ctx->sort_shadow_bits = uint32_t(std::min(std::max(std::atoi(env), 1), 7));
 	if (const char* env = std::getenv("RZB200_SORT_MAJOR")) ctx->sort_dir_major = std::atoi(env) != 0;
-	if (const char* env = std::getenv("RZB200_ANYHIT_ORDER")) ctx->x_flags |= std::atoi(env) == 1 ? kFlagAnyHitNearFirst : 0u;
+	// any-hit walks visit the nearer-entry child first (measured: shadow kernel 0.240 -> 0.220 ms per pass on the
+	// 1M-triangle scene, 0.677 -> 0.670 on the materials scene; the result does not depend on the order)
+	ctx->x_flags |= kFlagAnyHitNearFirst;
+	if (const char* env = std::getenv("RZB200_ANYHIT_ORDER")) { if (std::atoi(env) == 0) ctx->x_flags &= ~kFlagAnyHitNearFirst; }
 	ctx->trace_grid = gridFor(ctx, reinterpret_cast<const void*>(&k_trace_paths<false, false>), kTraceBlock);
 	ctx->shadow_grid = gridFor(ctx, reinterpret_cast<const void*>(&k_trace_shadow<false>), kTraceBlock);
 	ctx->trace_grid_fast = gridFor(ctx, reinterpret_cast<const void*>(&k_trace_paths<false, true>), kTraceBlock);
 	ctx->rays_grid = gridFor(ctx, reinterpret_cast<const void*>(&k_trace_rays<false, false>), kTraceBlock);
 	ctx->any_grid = gridFor(ctx, reinterpret_cast<const void*>(&k_trace_any_rays), kTraceBlock);
+	if (const char* env = std::getenv("RZB200_MR_RAYS")) ctx->mr_k = std::atoi(env) <= 2 ? 2 : 4;
+	if (const char* env = std::getenv("RZB200_MR_STEPS")) ctx->mr_steps = std::min(std::max(std::atoi(env), 1), 2);
 	{
 		// multi-ray kernels: dynamic shared memory = the rays' hot state, padded when fewer resident blocks are asked for
-		const size_t need = size_t(kMrFields) * kMrRays * kMrBlock * sizeof(float4);
+		const size_t need = size_t(kMrFields) * size_t(ctx->mr_k) * kMrBlock * sizeof(float4);
 		int max_smem = 0;
 		cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerMultiprocessor, device);
 		size_t bytes = need;
 		if (ctx->mr_blocks > 0 && max_smem > 0)
 			bytes = std::max(need, std::min<size_t>(size_t(max_smem) / size_t(ctx->mr_blocks + 1) + 1024, size_t(max_smem) / size_t(ctx->mr_blocks) - 1024));
 		ctx->mr_smem = bytes;
-		const void* kernels[6] = {reinterpret_cast<const void*>(&k_trace_paths_mr<false, false>), reinterpret_cast<const void*>(&k_trace_paths_mr<false, true>),
-			reinterpret_cast<const void*>(&k_trace_paths_mr<true, false>), reinterpret_cast<const void*>(&k_trace_paths_mr<true, true>),
-			reinterpret_cast<const void*>(&k_trace_rays_mr<false, false>), reinterpret_cast<const void*>(&k_trace_rays_mr<false, true>)};
-		for (int i = 0; i < 6; ++i)
-		{
-			cudaFuncSetAttribute(kernels[i], cudaFuncAttributeMaxDynamicSharedMemorySize, int(bytes));
-			int per_sm = 0;
-			if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernels[i], kMrBlock, bytes) != cudaSuccess || per_sm < 1) per_sm = 1;
-			if (ctx->set_carveout && max_smem > 0)
+		for (int fast = 0; fast < 2; ++fast)
+			for (int stats = 0; stats < 2; ++stats)
 			{
-				const int pct = int(std::min<size_t>(100, (size_t(per_sm) * (bytes + 1024) * 100 + size_t(max_smem) - 1) / size_t(max_smem)));
-				cudaFuncSetAttribute(kernels[i], cudaFuncAttributePreferredSharedMemoryCarveout, pct);
-				if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernels[i], kMrBlock, bytes) != cudaSuccess || per_sm < 1) per_sm = 1;
+				const void* kernels[2] = {mrPathKernel(ctx->mr_k, ctx->mr_steps, stats != 0, fast != 0), mrRaysKernel(ctx->mr_k, ctx->mr_steps, fast != 0)};
+				for (const void* kernel : kernels)
+				{
+					if (!kernel) continue;
+					cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(bytes));
+					int per_sm = 0;
+					if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kMrBlock, bytes) != cudaSuccess || per_sm < 1) per_sm = 1;
+					if (ctx->set_carveout && max_smem > 0)
+					{
+						const int pct = int(std::min<size_t>(100, (size_t(per_sm) * (bytes + 1024) * 100 + size_t(max_smem) - 1) / size_t(max_smem)));
+						cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+						if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kMrBlock, bytes) != cudaSuccess || per_sm < 1) per_sm = 1;
+					}
+					if (!stats && kernel == kernels[0]) ctx->mr_grid[fast] = ctx->sm_count * per_sm;
+				}
 			}
-			if (i < 2) ctx->mr_grid[i] = ctx->sm_count * per_sm;
-		}
 		cudaGetLastError();
 	}
 	*out = ctx;
@@ -933,9 +968,8 @@ extern "C" int rzb_render(rzb_ctx* ctx, uint32_t passes)
 		if (timed) cudaEventRecord(ev[0], ctx->stream);
 		if (ctx->trace_mr)
 		{
-			const int grid = ctx->mr_grid[fast ? 1 : 0];
-			if (count) { if (fast) k_trace_paths_mr<true, true><<<grid, kMrBlock, ctx->mr_smem, ctx->stream>>>(ctx->sc, f); else k_trace_paths_mr<true, false><<<grid, kMrBlock, ctx->mr_smem, ctx->stream>>>(ctx->sc, f); }
-			else { if (fast) k_trace_paths_mr<false, true><<<grid, kMrBlock, ctx->mr_smem, ctx->stream>>>(ctx->sc, f); else k_trace_paths_mr<false, false><<<grid, kMrBlock, ctx->mr_smem, ctx->stream>>>(ctx->sc, f); }
+			const MrPathKernel kernel = reinterpret_cast<MrPathKernel>(const_cast<void*>(mrPathKernel(ctx->mr_k, ctx->mr_steps, count, fast)));
+			kernel<<<ctx->mr_grid[fast ? 1 : 0], kMrBlock, ctx->mr_smem, ctx->stream>>>(ctx->sc, f);
 		}
 		else if (count) { if (fast) k_trace_paths<true, true><<<ctx->trace_grid_fast, kTraceBlock, 0, ctx->stream>>>(ctx->sc, f); else k_trace_paths<true, false><<<ctx->trace_grid, kTraceBlock, 0, ctx->stream>>>(ctx->sc, f); }
 		else { if (fast) k_trace_paths<false, true><<<ctx->trace_grid_fast, kTraceBlock, 0, ctx->stream>>>(ctx->sc, f); else k_trace_paths<false, false><<<ctx->trace_grid, kTraceBlock, 0, ctx->stream>>>(ctx->sc, f); }
@@ -1430,7 +1464,7 @@ extern "C" int rzb_trace_closest_device(rzb_ctx* ctx, const void* rays_o_near, c
 	RZB_CUDA(ctx, cudaMemsetAsync(ctx->d_counters + 8, 0, 4, ctx->stream));
 	if (elapsed_ms) RZB_CUDA(ctx, cudaEventRecord(ctx->ev_begin, ctx->stream));
 	if (ctx->trace_mr)
-		(ctx->own_trees ? k_trace_rays_mr<false, true> : k_trace_rays_mr<false, false>)<<<ctx->mr_grid[ctx->own_trees ? 1 : 0], kMrBlock, ctx->mr_smem, ctx->stream>>>(ctx->sc,
+		reinterpret_cast<MrRaysKernel>(const_cast<void*>(mrRaysKernel(ctx->mr_k, ctx->mr_steps, ctx->own_trees)))<<<ctx->mr_grid[ctx->own_trees ? 1 : 0], kMrBlock, ctx->mr_smem, ctx->stream>>>(ctx->sc,
 			static_cast<const float4*>(rays_o_near), static_cast<const float4*>(rays_d_far), n,
 			static_cast<DHit*>(hits_out_device), ctx->d_counters + 8, nullptr);
 	else
@@ -1483,7 +1517,7 @@ extern "C" int rzb_trace_closest(rzb_ctx* ctx, const float* origins, const float
 			static_cast<const float4*>(ctx->scratch[0].ptr), static_cast<const float4*>(ctx->scratch[1].ptr), n,
 			static_cast<DHit*>(ctx->scratch[2].ptr), ctx->d_counters + 8, d_stats);
 	else if (ctx->trace_mr)
-		(ctx->own_trees ? k_trace_rays_mr<false, true> : k_trace_rays_mr<false, false>)<<<ctx->mr_grid[ctx->own_trees ? 1 : 0], kMrBlock, ctx->mr_smem, ctx->stream>>>(ctx->sc,
+		reinterpret_cast<MrRaysKernel>(const_cast<void*>(mrRaysKernel(ctx->mr_k, ctx->mr_steps, ctx->own_trees)))<<<ctx->mr_grid[ctx->own_trees ? 1 : 0], kMrBlock, ctx->mr_smem, ctx->stream>>>(ctx->sc,
 			static_cast<const float4*>(ctx->scratch[0].ptr), static_cast<const float4*>(ctx->scratch[1].ptr), n,
 			static_cast<DHit*>(ctx->scratch[2].ptr), ctx->d_counters + 8, nullptr);
 	else

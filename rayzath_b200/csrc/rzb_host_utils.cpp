@@ -77,3 +77,70 @@ extern "C" int rzb_face_normals(const float* vertices, uint32_t nv, const uint32
 	}
 	return RZB_OK;
 }
+
+// ---- refit: new boxes for an existing tree after its vertices moved. The topology (children,
+// triangle ranges, order) is kept; every leaf box becomes the exact fp32 min / max of its triangles' vertices -- what the
+// builders compute (bvh_tree_node.hpp: BoundingBox::extendBy over the objects' boxes) -- and every inner box the union
+// of its children's. Iterative post-order walk from the root; works for any layout rzb_set_scene accepts.
+#include <algorithm>
+#include <utility>
+#include <vector>
+
+extern "C" int rzb_refit_mesh_bvh(const float* vertices, uint32_t nv, const uint32_t* tris, uint32_t nt,
+	rzb_node* nodes, uint32_t node_count, const uint32_t* order)
+{
+	if (!vertices || !tris || !nodes || !order || node_count == 0) return RZB_ERR_INVALID;
+	std::vector<std::pair<uint32_t, bool>> todo; // (node, children done)
+	std::vector<uint8_t> seen(node_count, 0);
+	todo.emplace_back(0u, false);
+	seen[0] = 1;
+	while (!todo.empty())
+	{
+		const uint32_t i = todo.back().first;
+		const bool children_done = todo.back().second;
+		rzb_node& n = nodes[i];
+		const uint32_t count = n.type_count & 0x3FFFFFFFu;
+		if (count != 0u)
+		{
+			todo.pop_back();
+			if (uint64_t(n.begin) + count > nt) return RZB_ERR_INVALID;
+			float mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
+			for (uint32_t t = n.begin; t < n.begin + count; ++t)
+			{
+				const uint32_t tri = order[t];
+				if (tri >= nt) return RZB_ERR_INVALID;
+				for (int c = 0; c < 3; ++c)
+				{
+					const uint32_t v = tris[3 * size_t(tri) + c];
+					if (v >= nv) return RZB_ERR_INVALID;
+					for (int k = 0; k < 3; ++k)
+					{
+						mn[k] = std::min(mn[k], vertices[3 * size_t(v) + k]);
+						mx[k] = std::max(mx[k], vertices[3 * size_t(v) + k]);
+					}
+				}
+			}
+			for (int k = 0; k < 3; ++k) { n.bb_min[k] = mn[k]; n.bb_max[k] = mx[k]; }
+			continue;
+		}
+		if (uint64_t(n.begin) + 1 >= node_count) return RZB_ERR_INVALID;
+		if (!children_done)
+		{
+			if (seen[n.begin] || seen[n.begin + 1]) return RZB_ERR_INVALID; // not a tree
+			seen[n.begin] = seen[n.begin + 1] = 1;
+			todo.back().second = true;
+			todo.emplace_back(n.begin, false);
+			todo.emplace_back(n.begin + 1u, false);
+			continue;
+		}
+		todo.pop_back();
+		const rzb_node& a = nodes[n.begin];
+		const rzb_node& b = nodes[n.begin + 1];
+		for (int k = 0; k < 3; ++k)
+		{
+			n.bb_min[k] = std::min(a.bb_min[k], b.bb_min[k]);
+			n.bb_max[k] = std::max(a.bb_max[k], b.bb_max[k]);
+		}
+	}
+	return RZB_OK;
+}

@@ -316,13 +316,14 @@ namespace rzb
 	//   uint32_t total() const; uint32_t* counter() const;
 	//   bool load(idx, handle, o, d, near, far, user)   false: the item has no ray (a slot without a pixel)
 	//   void store(handle, user, result)
-	template <bool STATS, bool FAST, class Source>
+	template <int K, int STEPS, bool STATS, bool FAST, class Source>
 	__device__ __forceinline__ void mr_run(const DScene& sc, const Source& src, float4* smem, unsigned long long* work_out,
 		unsigned long long* occupancy_out)
 	{
-		MrHot hot{smem + threadIdx.x};
-		MrCold cold;
-		MrLane lane{0u, 0u};
+		MrHot<K> hot{smem + threadIdx.x};
+		MrCold<K> cold;
+		MrLane lane;
+		lane.init(K);
 		TraceCounters cnt{0u, 0u, 0u, 0u};
 		const uint32_t lane_id = threadIdx.x & 31u;
 		const uint32_t n = src.total();
@@ -336,17 +337,17 @@ namespace rzb
 			if (phase == kMrNode)
 			{
 				k = lane.pick(kMrNode);
-				if (k >= 0) mr_node<FAST, STATS>(sc, hot, cold, lane, k, cnt);
+				if (k >= 0) mr_node<K, FAST, STATS, STEPS>(sc, hot, cold, lane, k, cnt);
 			}
 			else if (phase == kMrLeaf)
 			{
 				k = lane.pick(kMrLeaf);
-				if (k >= 0) mr_leaf<FAST, STATS>(sc, hot, cold, lane, k, cnt);
+				if (k >= 0) mr_leaf<K, FAST, STATS>(sc, hot, cold, lane, k, cnt);
 			}
 			else if (phase == kMrHeavy)
 			{
 				k = lane.pick(kMrHeavy);
-				if (k >= 0) mr_heavy<FAST, STATS>(sc, hot, cold, lane, k, cnt);
+				if (k >= 0) mr_heavy<K, FAST, STATS>(sc, hot, cold, lane, k, cnt);
 			}
 			else
 			{
@@ -355,9 +356,9 @@ namespace rzb
 				if (k >= 0)
 				{
 					RayResult r;
-					mr_result(hot, cold, k, r);
+					mr_result<K>(hot, cold, k, r);
 					src.store(cold.handle[k], cold.user[k], r);
-					lane.set_tag(k, kMrEmpty);
+					lane.move(k, kMrDone, kMrEmpty);
 				}
 				else if (work_left) k = lane.pick(kMrEmpty);
 				const bool want = k >= 0 && work_left;
@@ -381,12 +382,13 @@ namespace rzb
 						if (src.load(idx, handle, o, d, near_, far_, user))
 						{
 							cold.handle[k] = handle; cold.user[k] = user;
-							mr_begin<FAST, STATS>(sc, hot, cold, lane, k, o, d, near_, far_, cnt);
+							mr_begin<K, FAST, STATS>(sc, hot, cold, lane, k, o, d, near_, far_, cnt);
 						}
 					}
-					else lane.set_tag(k, kMrDead);
+					else lane.move(k, kMrEmpty, kMrDead);
 				}
 			}
+			lane.rr = (lane.rr + 1u) & 3u;
 			if (STATS)
 			{
 				occ_active += __popc(__ballot_sync(0xFFFFFFFFu, k >= 0));
@@ -444,12 +446,12 @@ namespace rzb
 		}
 	};
 
-	template <bool STATS, bool FAST>
+	template <int K, int STEPS, bool STATS, bool FAST>
 	__global__ void __launch_bounds__(kMrBlock, 5) k_trace_paths_mr(DScene sc, DFrame f)
 	{
-		extern __shared__ float4 mr_smem[]; // [kMrFields][kMrRays][kMrBlock] (+ padding that only limits blocks per SM)
+		extern __shared__ float4 mr_smem[]; // [kMrFields][K][kMrBlock] (+ padding that only limits blocks per SM)
 		const PathSource src{&sc, &f};
-		mr_run<STATS, FAST>(sc, src, mr_smem, f.work, f.work + 10);
+		mr_run<K, STEPS, STATS, FAST>(sc, src, mr_smem, f.work, f.work + 10);
 	}
 
 	// ---------------------------------------------------------------- shadow queue append (warp-ballot compaction)
@@ -1006,13 +1008,13 @@ namespace rzb
 			dst[1] = make_float4(__uint_as_float(r.inst), 0.0f, 0.0f, 0.0f);
 		}
 	};
-	template <bool STATS, bool FAST>
+	template <int K, int STEPS, bool STATS, bool FAST>
 	__global__ void __launch_bounds__(kMrBlock, 5) k_trace_rays_mr(DScene sc, const float4* __restrict__ ray_o_near,
 		const float4* __restrict__ ray_d_far, uint32_t n, DHit* __restrict__ hits, uint32_t* counter, unsigned long long* stats)
 	{
 		extern __shared__ float4 mr_smem[];
 		const RaySetSource src{ray_o_near, ray_d_far, hits, counter, n};
-		mr_run<STATS, FAST>(sc, src, mr_smem, stats, nullptr);
+		mr_run<K, STEPS, STATS, FAST>(sc, src, mr_smem, stats, nullptr);
 	}
 
 	__global__ void k_convert_hits(DScene sc, const DHit* __restrict__ in, rzb_hit* __restrict__ out, uint32_t n)

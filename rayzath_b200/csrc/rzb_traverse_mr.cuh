@@ -25,7 +25,7 @@
 
 namespace rzb
 {
-	constexpr int kMrRays = 4;     // rays per lane
+	constexpr int kMrMaxRays = 4;  // rays per lane: template parameter K of everything below (2..4)
 	constexpr int kMrBlock = 128;  // threads per block
 	constexpr int kMrStack = kSmemStack + kLocalStack; // entries per ray (the depth bound rzb_set_scene enforces)
 
@@ -44,20 +44,22 @@ namespace rzb
 	};
 
 	// what the thread keeps for its kMrRays rays outside shared memory (dynamic index -> local memory; touched rarely)
+	template <int K>
 	struct MrCold
 	{
-		float park_near[kMrRays], park_far[kMrRays], park_b1[kMrRays], park_b2[kMrRays];
-		uint32_t park_tri[kMrRays], park_inst[kMrRays];
-		float lb1[kMrRays], lb2[kMrRays];
-		uint32_t cur_inst[kMrRays], handle[kMrRays], user[kMrRays];
-		float wo[kMrRays][3], wd[kMrRays][3]; // the world ray (restored when a mesh is left)
-		uint2 stack[kMrRays][kMrStack];
+		float park_near[K], park_far[K], park_b1[K], park_b2[K];
+		uint32_t park_tri[K], park_inst[K];
+		float lb1[K], lb2[K];
+		uint32_t cur_inst[K], handle[K], user[K];
+		float wo[K][3], wd[K][3]; // the world ray (restored when a mesh is left)
+		uint2 stack[K][kMrStack];
 	};
 
+	template <int K>
 	struct MrHot
 	{
 		float4* base; // &smem[0][0][threadIdx.x]
-		__device__ __forceinline__ float4& q(const int field, const int k) const { return base[(field * kMrRays + k) * kMrBlock]; }
+		__device__ __forceinline__ float4& q(const int field, const int k) const { return base[(field * K + k) * kMrBlock]; }
 	};
 	enum { kQA = 0, kQB = 1, kQC = 2, kQD = 3, kMrFields = 4 };
 
@@ -70,23 +72,42 @@ namespace rzb
 		__device__ __forceinline__ uint2 peek() const { return e[sp - 1 < kMrStack ? sp - 1 : kMrStack - 1]; }
 	};
 
-	// per-lane bookkeeping in registers: 4-bit phase tag and 8-bit stack pointer of each ray
+	// per-lane bookkeeping in registers: one bit mask per phase (bit k = ray k is in that phase; packed 4 bits per phase:
+	// phase t occupies bits [4t, 4t+4) of `tags`) and the 8-bit stack pointer of each ray
 	struct MrLane
 	{
-		uint32_t tags, sps;
-		__device__ __forceinline__ uint32_t tag(const int k) const { return (tags >> (4 * k)) & 15u; }
-		__device__ __forceinline__ void set_tag(const int k, const uint32_t t) { tags = (tags & ~(15u << (4 * k))) | (t << (4 * k)); }
+		uint32_t tags, sps, rr; // rr: rotating start of the search, so that a lane's rays take turns
+		__device__ __forceinline__ uint32_t mask(const uint32_t t) const { return (tags >> (4u * t)) & 15u; }
+		__device__ __forceinline__ void init(const int rays)
+		{
+			tags = ((1u << rays) - 1u) << (4u * kMrEmpty);
+			sps = 0u; rr = 0u;
+		}
+		// move ray k from phase `from` to phase `to`
+		__device__ __forceinline__ void move(const int k, const uint32_t from, const uint32_t to)
+		{
+			tags = (tags & ~(1u << (4u * from + k))) | (1u << (4u * to + k));
+		}
 		__device__ __forceinline__ int sp(const int k) const { return int((sps >> (8 * k)) & 255u); }
 		__device__ __forceinline__ void set_sp(const int k, const int v) { sps = (sps & ~(255u << (8 * k))) | (uint32_t(v) << (8 * k)); }
-		// first ray of this lane in phase t, or -1
+		// a ray of this lane in phase t (round-robin), or -1
 		__device__ __forceinline__ int pick(const uint32_t t) const
 		{
-#pragma unroll
-			for (int k = 0; k < kMrRays; ++k)
-				if (tag(k) == t) return k;
-			return -1;
+			const uint32_t m = mask(t);
+			if (m == 0u) return -1;
+			const uint32_t rot = ((m | (m << 4)) >> rr) & 15u; // bit j = ray (rr + j) % 4
+			return int((rr + uint32_t(__ffs(rot)) - 1u) & 3u);
 		}
 	};
+
+	__device__ __forceinline__ void mr_prefetch(const void* p)
+	{
+#ifndef RZB_HOST_SIM
+		asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
+#else
+		(void)p;
+#endif
+	}
 
 	// ---- pop of deferred nodes of the CURRENT level (the common case). Returns the ray's next phase; anything that is
 	// not a plain deferred node (instance range, end of a mesh, end of the walk) is left to the heavy phase.
@@ -131,9 +152,16 @@ namespace rzb
 		}
 	}
 
-	// ---- N: one sibling-pair step
-	template <bool FAST, bool STATS>
-	__device__ __forceinline__ void mr_node(const DScene& sc, const MrHot& hot, MrCold& cold, MrLane& lane, const int k, TraceCounters& cnt)
+	// what the ray will read first in its next round goes to L1 now (the lane serves its other rays in between)
+	__device__ __forceinline__ void mr_prefetch_next(const DScene& sc, const uint32_t next, const uint32_t cur_begin)
+	{
+		if (next == kMrNode) mr_prefetch(sc.nodes + 2 * size_t(cur_begin));
+		else if (next == kMrLeaf) mr_prefetch(sc.tri_hot + 3 * size_t(cur_begin));
+	}
+
+	// ---- N: up to STEPS sibling-pair steps while the ray stays on inner nodes
+	template <int K, bool FAST, bool STATS, int STEPS>
+	__device__ __forceinline__ void mr_node(const DScene& sc, const MrHot<K>& hot, MrCold<K>& cold, MrLane& lane, const int k, TraceCounters& cnt)
 	{
 		const float4 A = hot.q(kQA, k), B = hot.q(kQB, k), C = hot.q(kQC, k), D = hot.q(kQD, k);
 		const V3 o = v3(A.x, A.y, A.z), rcp = v3(B.x, B.y, B.z), d = v3(D.x, D.y, D.z);
@@ -144,41 +172,45 @@ namespace rzb
 		const float margin = (flags & kMrMarginInf) ? kInf : kSlabMargin;
 		const uint32_t sbits = (flags >> kMrSbitsShift) & 7u;
 		MrStackView st{cold.stack[k], lane.sp(k)};
-
-		const float4* pair = sc.nodes + 2 * size_t(cur_begin); // 64-byte aligned sibling pair
-		const float4 p0 = __ldg(pair), p1 = __ldg(pair + 1), p2 = __ldg(pair + 2), p3 = __ldg(pair + 3);
-		if (STATS) { if (in_mesh) cnt.mesh_nodes += 2; else cnt.top_nodes += 2; }
-		float tm0, tm1;
-		const bool h0 = slab_hit<FAST>(p0, p1, o, d, rcp, near_, far_, margin, tm0);
-		const bool h1 = slab_hit<FAST>(p2, p3, o, d, rcp, near_, far_, margin, tm1);
-		const bool flip = FAST ? (h0 && h1 && tm1 < tm0) : ((sbits >> (cur_tc >> 30)) & 1u) != 0u;
-		const bool hit_a = flip ? h1 : h0, hit_b = flip ? h0 : h1;
-		uint32_t next;
-		if (hit_a || hit_b)
+		uint32_t next = kMrNode;
+#pragma unroll 1
+		for (int step = 0; step < STEPS && next == kMrNode; ++step)
 		{
-			if (hit_a && hit_b)
-				st.push((in_mesh ? kEntryMeshNode : kEntryTopNode) | (cur_begin + (flip ? 0u : 1u)), __float_as_uint(flip ? tm0 : tm1));
-			const bool take_second = hit_a ? flip : !flip;
-			cur_tc = __float_as_uint(take_second ? p3.w : p1.w);
-			cur_begin = __float_as_uint(take_second ? p3.z : p1.z);
-			if ((cur_tc & 0x3FFFFFFFu) == 0u) next = kMrNode;
-			else if (in_mesh) next = kMrLeaf;
-			else
+			const float4* pair = sc.nodes + 2 * size_t(cur_begin); // 64-byte aligned sibling pair
+			const float4 p0 = __ldg(pair), p1 = __ldg(pair + 1), p2 = __ldg(pair + 2), p3 = __ldg(pair + 3);
+			if (STATS) { if (in_mesh) cnt.mesh_nodes += 2; else cnt.top_nodes += 2; }
+			float tm0, tm1;
+			const bool h0 = slab_hit<FAST>(p0, p1, o, d, rcp, near_, far_, margin, tm0);
+			const bool h1 = slab_hit<FAST>(p2, p3, o, d, rcp, near_, far_, margin, tm1);
+			const bool flip = FAST ? (h0 && h1 && tm1 < tm0) : ((sbits >> (cur_tc >> 30)) & 1u) != 0u;
+			const bool hit_a = flip ? h1 : h0, hit_b = flip ? h0 : h1;
+			if (hit_a || hit_b)
 			{
-				st.push(kEntryInstRange | cur_begin, cur_begin + (cur_tc & 0x3FFFFFFFu));
-				next = kMrHeavy;
+				if (hit_a && hit_b)
+					st.push((in_mesh ? kEntryMeshNode : kEntryTopNode) | (cur_begin + (flip ? 0u : 1u)), __float_as_uint(flip ? tm0 : tm1));
+				const bool take_second = hit_a ? flip : !flip;
+				cur_tc = __float_as_uint(take_second ? p3.w : p1.w);
+				cur_begin = __float_as_uint(take_second ? p3.z : p1.z);
+				if ((cur_tc & 0x3FFFFFFFu) == 0u) next = kMrNode;
+				else if (in_mesh) next = kMrLeaf;
+				else
+				{
+					st.push(kEntryInstRange | cur_begin, cur_begin + (cur_tc & 0x3FFFFFFFu));
+					next = kMrHeavy;
+				}
 			}
+			else next = mr_pop_inline<FAST, STATS>(sc, st, in_mesh, o, d, near_, far_, margin, cur_begin, cur_tc);
 		}
-		else next = mr_pop_inline<FAST, STATS>(sc, st, in_mesh, o, d, near_, far_, margin, cur_begin, cur_tc);
+		mr_prefetch_next(sc, next, cur_begin);
 		float2* c2 = reinterpret_cast<float2*>(&hot.q(kQC, k));
 		*c2 = make_float2(__uint_as_float(cur_begin), __uint_as_float(cur_tc));
 		lane.set_sp(k, st.sp);
-		lane.set_tag(k, next);
+		if (next != kMrNode) lane.move(k, kMrNode, next);
 	}
 
 	// ---- T: the current leaf
-	template <bool FAST, bool STATS>
-	__device__ __forceinline__ void mr_leaf(const DScene& sc, const MrHot& hot, MrCold& cold, MrLane& lane, const int k, TraceCounters& cnt)
+	template <int K, bool FAST, bool STATS>
+	__device__ __forceinline__ void mr_leaf(const DScene& sc, const MrHot<K>& hot, MrCold<K>& cold, MrLane& lane, const int k, TraceCounters& cnt)
 	{
 		const float4 A = hot.q(kQA, k), C = hot.q(kQC, k), D = hot.q(kQD, k);
 		const V3 o = v3(A.x, A.y, A.z), d = v3(D.x, D.y, D.z);
@@ -207,16 +239,17 @@ namespace rzb
 		MrStackView st{cold.stack[k], lane.sp(k)};
 		const float margin = (flags & kMrMarginInf) ? kInf : kSlabMargin;
 		const uint32_t next = mr_pop_inline<FAST, STATS>(sc, st, true, o, d, near_, far_, margin, cur_begin, cur_tc);
+		mr_prefetch_next(sc, next, cur_begin);
 		hot.q(kQC, k) = make_float4(__uint_as_float(cur_begin), __uint_as_float(cur_tc), __uint_as_float(flags), __uint_as_float(ltri));
 		lane.set_sp(k, st.sp);
-		lane.set_tag(k, next);
+		if (next != kMrLeaf) lane.move(k, kMrLeaf, next);
 	}
 
 	// ---- H: rare work. The pop loop of rzb_traverse.cuh (trav_round) on the ray's full state: leave the mesh (commit
 	// its hit to the parked world range), next instance of a range (world box test, G2L transform with IEEE divisions,
 	// mesh root test), deferred nodes of the level that was re-entered, end of the walk.
-	template <bool FAST, bool STATS>
-	__device__ __forceinline__ void mr_heavy(const DScene& sc, const MrHot& hot, MrCold& cold, MrLane& lane, const int k, TraceCounters& cnt)
+	template <int K, bool FAST, bool STATS>
+	__device__ __forceinline__ void mr_heavy(const DScene& sc, const MrHot<K>& hot, MrCold<K>& cold, MrLane& lane, const int k, TraceCounters& cnt)
 	{
 		const float4* __restrict__ nodes = sc.nodes;
 		const float4 A = hot.q(kQA, k), B = hot.q(kQB, k), C = hot.q(kQC, k), D = hot.q(kQD, k);
@@ -314,17 +347,19 @@ namespace rzb
 			if (in_mesh) { next = kMrLeaf; break; }
 			st.push(kEntryInstRange | cur_begin, cur_begin + (cur_tc & 0x3FFFFFFFu));
 		}
+		mr_prefetch_next(sc, next, cur_begin);
 		hot.q(kQA, k) = make_float4(o.x, o.y, o.z, far_);
 		hot.q(kQB, k) = make_float4(rcp.x, rcp.y, rcp.z, near_);
 		hot.q(kQC, k) = make_float4(__uint_as_float(cur_begin), __uint_as_float(cur_tc), __uint_as_float(flags), __uint_as_float(ltri));
 		hot.q(kQD, k) = make_float4(d.x, d.y, d.z, len);
 		lane.set_sp(k, st.sp);
-		lane.set_tag(k, next);
+		if (next != kMrHeavy) lane.move(k, kMrHeavy, next);
 	}
 
-	// ---- start of a walk (trav_begin of rzb_traverse.cuh): world ray into the state, root test of the instance tree
-	template <bool FAST, bool STATS>
-	__device__ __forceinline__ void mr_begin(const DScene& sc, const MrHot& hot, MrCold& cold, MrLane& lane, const int k,
+	// ---- start of a walk (trav_begin of rzb_traverse.cuh): world ray into the state, root test of the instance tree.
+	// The ray is in phase kMrEmpty when this is called.
+	template <int K, bool FAST, bool STATS>
+	__device__ __forceinline__ void mr_begin(const DScene& sc, const MrHot<K>& hot, MrCold<K>& cold, MrLane& lane, const int k,
 		const V3 o, const V3 d, const float near_in, const float far_in, TraceCounters& cnt)
 	{
 		const V3 rcp = reciprocal_rn(d);
@@ -360,11 +395,12 @@ namespace rzb
 		hot.q(kQC, k) = make_float4(__uint_as_float(cur_begin), __uint_as_float(cur_tc), __uint_as_float(flags), __uint_as_float(kNoIndex));
 		hot.q(kQD, k) = make_float4(d.x, d.y, d.z, 1.0f);
 		lane.set_sp(k, st.sp);
-		lane.set_tag(k, next);
+		lane.move(k, kMrEmpty, next);
 	}
 
 	// the finished ray's result (trav_end)
-	__device__ __forceinline__ void mr_result(const MrHot& hot, const MrCold& cold, const int k, RayResult& res)
+	template <int K>
+	__device__ __forceinline__ void mr_result(const MrHot<K>& hot, const MrCold<K>& cold, const int k, RayResult& res)
 	{
 		const uint32_t flags = __float_as_uint(hot.q(kQC, k).z);
 		res.t = cold.park_far[k]; res.near_ = cold.park_near[k]; res.b1 = cold.park_b1[k]; res.b2 = cold.park_b2[k];
@@ -373,18 +409,14 @@ namespace rzb
 		res.steps = 0u; res.tris = 0u;
 	}
 
-	// Which phase the warp runs this round: the one most lanes can serve. Fetch / write-back (F) and the heavy phase are
-	// rare per ray and long, so they wait until many lanes want them -- unless nothing else is left to do.
+	// Which phase the warp runs this round: the one most lanes can serve (ties: node, leaf, heavy, fetch).
 	__device__ __forceinline__ uint32_t mr_vote(const MrLane& lane, const bool work_left)
 	{
-		uint32_t has = 0u; // bit t: this lane has a ray in phase t
-#pragma unroll
-		for (int k = 0; k < kMrRays; ++k) has |= 1u << lane.tag(k);
-		if (!work_left && (has & (1u << kMrEmpty))) has &= ~(1u << kMrEmpty);
-		const int cn = __popc(__ballot_sync(0xFFFFFFFFu, (has >> kMrNode) & 1u));
-		const int cl = __popc(__ballot_sync(0xFFFFFFFFu, (has >> kMrLeaf) & 1u));
-		const int ch = __popc(__ballot_sync(0xFFFFFFFFu, (has >> kMrHeavy) & 1u));
-		const int cf = __popc(__ballot_sync(0xFFFFFFFFu, ((has >> kMrEmpty) | (has >> kMrDone)) & 1u));
+		const uint32_t fetchable = lane.mask(kMrDone) | (work_left ? lane.mask(kMrEmpty) : 0u);
+		const int cn = __popc(__ballot_sync(0xFFFFFFFFu, lane.mask(kMrNode) != 0u));
+		const int cl = __popc(__ballot_sync(0xFFFFFFFFu, lane.mask(kMrLeaf) != 0u));
+		const int ch = __popc(__ballot_sync(0xFFFFFFFFu, lane.mask(kMrHeavy) != 0u));
+		const int cf = __popc(__ballot_sync(0xFFFFFFFFu, fetchable != 0u));
 		if (cn >= cl && cn >= ch && cn >= cf && cn > 0) return kMrNode;
 		if (cl >= ch && cl >= cf && cl > 0) return kMrLeaf;
 		if (ch >= cf && ch > 0) return kMrHeavy;

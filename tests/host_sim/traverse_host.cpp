@@ -19,6 +19,7 @@ template <typename T> static inline T __ldg(const T* p) { return *p; }
 static inline int __any_sync(unsigned, int p) { return p; }
 static inline unsigned __ballot_sync(unsigned, int p) { return p ? 1u : 0u; }
 static inline int __popc(unsigned v) { return __builtin_popcount(v); }
+static inline int __ffs(unsigned v) { return __builtin_ffs(int(v)); }
 struct { unsigned x = 0; } threadIdx;
 #define RZB_HOST_SIM 1
 #ifndef __noinline__
@@ -120,15 +121,17 @@ static int trav_host_run_impl(const rzb_scene* s, const float* origins, const fl
 
 	if (mr)
 	{
-		std::vector<float4> smem(size_t(kMrFields) * kMrRays * kMrBlock);
-		MrHot hot{smem.data()};
-		static MrCold cold;
-		MrLane lane{0u, 0u};
+		constexpr int K = kMrMaxRays;
+		std::vector<float4> smem(size_t(kMrFields) * K * kMrBlock);
+		MrHot<K> hot{smem.data()};
+		static MrCold<K> cold;
+		MrLane lane;
+		lane.init(K);
 		TraceCounters cnt{0u, 0u, 0u, 0u};
 		uint32_t next_ray = 0;
 		auto write = [&](int k) {
 			RayResult r;
-			mr_result(hot, cold, k, r);
+			mr_result<K>(hot, cold, k, r);
 			const uint32_t i = cold.handle[k];
 			rzb_hit h{};
 			h.instance = RZB_NO_INDEX; h.triangle = RZB_NO_INDEX;
@@ -146,22 +149,23 @@ static int trav_host_run_impl(const rzb_scene* s, const float* origins, const fl
 			const bool work_left = next_ray < n;
 			const uint32_t phase = mr_vote(lane, work_left);
 			if (phase == kMrDead) break;
-			if (phase == kMrNode) mr_node<false, true>(sc, hot, cold, lane, lane.pick(kMrNode), cnt);
-			else if (phase == kMrLeaf) mr_leaf<false, true>(sc, hot, cold, lane, lane.pick(kMrLeaf), cnt);
-			else if (phase == kMrHeavy) mr_heavy<false, true>(sc, hot, cold, lane, lane.pick(kMrHeavy), cnt);
+			if (phase == kMrNode) mr_node<K, false, true, 2>(sc, hot, cold, lane, lane.pick(kMrNode), cnt);
+			else if (phase == kMrLeaf) mr_leaf<K, false, true>(sc, hot, cold, lane, lane.pick(kMrLeaf), cnt);
+			else if (phase == kMrHeavy) mr_heavy<K, false, true>(sc, hot, cold, lane, lane.pick(kMrHeavy), cnt);
 			else
 			{
 				int k = lane.pick(kMrDone);
-				if (k >= 0) { write(k); lane.set_tag(k, kMrEmpty); }
+				if (k >= 0) { write(k); lane.move(k, kMrDone, kMrEmpty); }
 				else if (work_left) k = lane.pick(kMrEmpty);
 				if (k >= 0 && work_left)
 				{
 					const uint32_t i = next_ray++;
 					cold.handle[k] = i; cold.user[k] = 0u;
-					mr_begin<false, true>(sc, hot, cold, lane, k, v3(origins[3 * i], origins[3 * i + 1], origins[3 * i + 2]),
+					mr_begin<K, false, true>(sc, hot, cold, lane, k, v3(origins[3 * i], origins[3 * i + 1], origins[3 * i + 2]),
 						v3(dirs[3 * i], dirs[3 * i + 1], dirs[3 * i + 2]), near_far[2 * i], near_far[2 * i + 1], cnt);
 				}
 			}
+			lane.rr = (lane.rr + 1u) & 3u;
 		}
 		if (counters4)
 		{

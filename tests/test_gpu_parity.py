@@ -687,3 +687,35 @@ def test_converged_image_at_baseline_spp(name):
     assert rel(coarse(G2), coarse(M)) <= 1.1 * rel(coarse(A), coarse(B)) / 2.0 + 0.003, (rel(coarse(G2), coarse(M)), rel(coarse(A), coarse(B)))
     assert abs(m2 - ref_mean) / ref_mean < 0.01, (m2, ref_mean)
     assert abs(m1 - ref_mean) / ref_mean < 0.02, (m1, ref_mean)
+
+
+@pytest.mark.parametrize("rays_per_lane", [2, 4])
+def test_multi_ray_lane_kernels_bit_exact(rays_per_lane, golden, flats, monkeypatch):
+    """The measured alternative closest-hit kernels (several rays per lane with phase voting, rzb_traverse_mr.cuh;
+    selected with RZB200_TRACE=mr, not the default: DESIGN.md section 4) produce byte-identical records to the oracle on
+    every golden scene -- each ray performs the same operation sequence, only the lane-round that executes a step differs --
+    and the renderer's accumulator does not depend on which kernel traced it."""
+    monkeypatch.setenv("RZB200_TRACE", "mr")
+    monkeypatch.setenv("RZB200_MR_RAYS", str(rays_per_lane))
+    for name in NAMES:
+        g = golden[name]
+        with capi.Context(0) as c:
+            c.set_scene(flats[name])
+            hits = c.trace_closest(g["ray_origins"], g["ray_directions"], g["ray_near_far"])
+        ref = O.trace_closest(O.Scene(flats[name]), g["ray_origins"], g["ray_directions"], g["ray_near_far"],
+                              order=O.ORDER_CUDA, minmax=O.MINMAX_FMINF)
+        assert np.array_equal(hits.view(np.uint8), ref.view(np.uint8)), name
+    w = GOLDEN_SCENES["cornell"]()  # no lights: no atomic adds, the accumulator is deterministic
+
+    def render():
+        with capi.Context(0) as c:
+            c.set_scene(w.flatten())
+            c.set_camera(w.camera_struct())
+            c.set_config(max_depth=6, seed=3)
+            c.reset()
+            c.render(12)
+            return c.read_accum()
+
+    a = render()
+    monkeypatch.setenv("RZB200_TRACE", "lane")
+    assert np.array_equal(a, render())
