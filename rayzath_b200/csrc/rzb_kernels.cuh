@@ -265,7 +265,7 @@ namespace rzb
 		}
 	}
 
-	template <bool STATS, bool FAST>
+	template <bool STATS, bool FAST, bool SYNC = false>
 	__global__ void __launch_bounds__(kTraceBlock, FAST ? 8 : 6) k_trace_paths(DScene sc, DFrame f)
 	{
 		__shared__ uint2 smem_stack[kSmemStack * kTraceBlock];
@@ -300,7 +300,7 @@ namespace rzb
 				}
 			}
 			RayResult r;
-			trace_ray<false, STATS, false, FAST>(sc, active, v3(so.x, so.y, so.z), v3(sd.x, sd.y, sd.z), near_, far_, st, park, cnt, r);
+			trace_ray<false, STATS, SYNC, FAST>(sc, active, v3(so.x, so.y, so.z), v3(sd.x, sd.y, sd.z), near_, far_, st, park, cnt, r);
 			if (STATS) batch_utilisation(active ? r.steps + r.tris : 0u, f.work + 10);
 			if (!active) continue;
 			uint32_t tri_bits = flags | (r.external ? kHitExternalBit : 0u);

@@ -639,12 +639,15 @@ def test_converged_image_at_baseline_spp(name):
     """BASELINE.json configs 1-3 at their own resolution and sample count (64 / 256 / 64 spp) against the reference CPU
     engine. The fixture tests/golden/converged_<name>.npz holds k x k block means (k = 4 for 512x512, 8 for 1080p) of
     TWO independent reference renders A and B (tests/tools/make_golden_images.py, generated where /root/reference
-    exists), i.e. its own Monte-Carlo noise floor. Stated tolerances, all on radiance = rgb sum / sample count:
-      equal spp      block relRMSE(GPU at the BASELINE spp, A) <= 1.1 x block relRMSE(A, B): the GPU estimator is
-                     indistinguishable from a third run of the reference's;
-      converged      GPU at 16x the spp against the mean of A and B: block relRMSE <= 1.1 x relRMSE(A, B) / 2 + 0.003
-                     (what is left is the reference's own noise, halved by averaging), on these blocks and on 4x coarser ones;
-      mean           image mean within 1 % of the reference's."""
+    exists), i.e. its own Monte-Carlo noise floor, and the pass count they ran for. radiance = rgb sum / completed paths is
+    a ratio estimator: paths still in flight have added light but are not counted, so every finite render is biased high by
+    O(1 / passes) -- in the reference and here alike (measured: +0.9 % at 69 spp on config 1) -- and the comparison is made
+    at EQUAL PASSES. Stated tolerances, all on block means of radiance:
+      one render     block relRMSE(GPU, A) <= 1.1 x block relRMSE(A, B): indistinguishable from a third run of the reference;
+      converged      the mean of 16 independent GPU renders (noise / 4, same bias) against the mean of A and B:
+                     block relRMSE <= 1.1 x sqrt(1/32 + 1/4) x relRMSE(A, B) + 0.003 on these blocks and on 4x coarser
+                     ones -- what is left is the reference's own noise;
+      mean           image mean of the 16 renders within 1 % of the reference's, of one render within 2 %."""
     path = os.path.join(ROOT, "tests", "golden", "converged_%s.npz" % name)
     if not os.path.exists(path):
         pytest.skip("fixture not generated")
@@ -663,29 +666,33 @@ def test_converged_image_at_baseline_spp(name):
         h, wd = img.shape[0] // 4 * 4, img.shape[1] // 4 * 4
         return img[:h, :wd].reshape(h // 4, 4, wd // 4, 4, 3).mean(axis=(1, 3))
 
+    passes = int(fx["passes"][0])
     with capi.Context(0) as c:
         c.set_scene(w.flatten())
         c.set_camera(w.camera_struct())
-        c.set_config(1, 1, depth, capi.FLAG_CPU_SEMANTICS, 77)
-        c.reset()
-        target, results = spp_ref, []
-        for factor in (1.0, 16.0):
-            while c.mean_samples() < spp_ref * factor:
-                c.render(max(8, int(0.25 * int(fx["passes"][0]) * factor)))
+        renders = []
+        for r in range(16):
+            c.set_config(1, 1, depth, capi.FLAG_CPU_SEMANTICS, 77 + 1000 * r)
+            c.reset()
+            c.render(passes)
             acc = c.read_accum()
             rad = acc[..., :3] / np.maximum(acc[..., 3:4], 1.0)
-            results.append((float(acc[..., 3].mean()), _block_mean(rad, H, W, k).astype(np.float64), float(rad.mean())))
+            renders.append((float(acc[..., 3].mean()), _block_mean(rad, H, W, k).astype(np.float64), float(rad.mean())))
     floor = rel(A, B)
-    (spp1, G1, m1), (spp2, G2, m2) = results
+    spp1, G1, m1 = renders[0]
+    G16 = np.mean([r[1] for r in renders], axis=0)
+    m16 = float(np.mean([r[2] for r in renders]))
     ref_mean = 0.5 * (float(fx["mean_a"][0]) + float(fx["mean_b"][0]))
-    print("%s: ref spp %.1f, block-%d relRMSE A-vs-B %.4f | GPU %.0f spp vs A %.4f | GPU %.0f spp vs mean(A,B) %.4f (coarse x4: %.4f) | "
-          "means %.6g / %.6g / %.6g" % (name, spp_ref, k, floor, spp1, rel(G1, A), spp2, rel(G2, M), rel(coarse(G2), coarse(M)),
-                                        ref_mean, m1, m2))
-    assert spp1 < 1.6 * spp_ref
-    assert rel(G1, A) <= 1.1 * floor * np.sqrt(max(spp_ref / spp1, 0.5) * 0.5 + 0.5), (rel(G1, A), floor)
-    assert rel(G2, M) <= 1.1 * floor / 2.0 + 0.003, (rel(G2, M), floor)
-    assert rel(coarse(G2), coarse(M)) <= 1.1 * rel(coarse(A), coarse(B)) / 2.0 + 0.003, (rel(coarse(G2), coarse(M)), rel(coarse(A), coarse(B)))
-    assert abs(m2 - ref_mean) / ref_mean < 0.01, (m2, ref_mean)
+    k16 = float(np.sqrt(1.0 / 32.0 + 0.25))
+    print("%s: %d passes, ref spp %.1f / GPU spp %.1f, block-%d relRMSE A-vs-B %.4f | one GPU render vs A %.4f | mean of 16 vs "
+          "mean(A,B) %.4f (expected %.4f; coarse x4: %.4f vs A-vs-B %.4f) | means ref %.6g, one %.6g, sixteen %.6g" % (
+              name, passes, spp_ref, spp1, k, floor, rel(G1, A), rel(G16, M), k16 * floor, rel(coarse(G16), coarse(M)),
+              rel(coarse(A), coarse(B)), ref_mean, m1, m16))
+    assert abs(spp1 - spp_ref) / spp_ref < 0.02, (spp1, spp_ref)
+    assert rel(G1, A) <= 1.1 * floor, (rel(G1, A), floor)
+    assert rel(G16, M) <= 1.1 * k16 * floor + 0.003, (rel(G16, M), floor)
+    assert rel(coarse(G16), coarse(M)) <= 1.1 * k16 * rel(coarse(A), coarse(B)) + 0.003, (rel(coarse(G16), coarse(M)), rel(coarse(A), coarse(B)))
+    assert abs(m16 - ref_mean) / ref_mean < 0.01, (m16, ref_mean)
     assert abs(m1 - ref_mean) / ref_mean < 0.02, (m1, ref_mean)
 
 

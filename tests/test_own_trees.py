@@ -101,6 +101,48 @@ def test_sah_tree_same_hits_as_reference_tree_oracle(name, golden, flats):
         _assert_equal_except_ties(own, ref)
 
 
+def test_refit_keeps_topology_and_bounds_the_deformed_mesh():
+    """rzb_refit_mesh_bvh: after the vertices move, the refitted tree keeps children / ranges / order,
+    every leaf box is the exact min / max of its triangles, every inner box the union of its children -- and the oracle
+    finds the same closest hits on it as on a tree built from scratch for the deformed mesh (exact ties excepted)."""
+    v, t, uv, n = scenes.heightfield_mesh(60, 50)
+    rng = np.random.default_rng(8)
+    v2 = v.copy()
+    v2[:, 1] += (0.4 * np.sin(v[:, 0] * 1.7) * np.cos(v[:, 2] * 1.3) + 0.05 * rng.standard_normal(v.shape[0])).astype(np.float32)
+    v2[:, 0] += (0.03 * rng.standard_normal(v.shape[0])).astype(np.float32)
+    for build in (capi.build_mesh_bvh, lambda a, b: capi.build_mesh_bvh_sah(a, b, 4)):
+        nodes, order = build(v, t)
+        refit = capi.refit_mesh_bvh(v2, t, nodes, order)
+        assert np.array_equal(refit["begin"], nodes["begin"]) and np.array_equal(refit["type_count"], nodes["type_count"])
+        count = refit["type_count"] & 0x3FFFFFFF
+        tri_v = v2[t[order]]
+        for i in range(refit.shape[0]):
+            if count[i]:
+                pts = tri_v[refit["begin"][i]:refit["begin"][i] + count[i]].reshape(-1, 3)
+                assert np.array_equal(refit["bb_min"][i], pts.min(axis=0)) and np.array_equal(refit["bb_max"][i], pts.max(axis=0))
+            else:
+                a, b = refit[refit["begin"][i]], refit[refit["begin"][i] + 1]
+                assert np.array_equal(refit["bb_min"][i], np.minimum(a["bb_min"], b["bb_min"]))
+                assert np.array_equal(refit["bb_max"][i], np.maximum(a["bb_max"], b["bb_max"]))
+        # the same hits as a fresh build of the deformed mesh
+        from rayzath_b200.world import World
+        worlds = []
+        for custom in (None, (refit, order)):
+            w = World()
+            mat = w.create_material("m", color=(200, 200, 200, 255))
+            m = w.create_mesh("terrain", v2, t)
+            if custom is not None:
+                m.bvh_builder = "refit"
+                m._bvh = ("refit", custom)
+            w.create_instance("terrain", m, [mat])
+            w.create_camera(name="cam", position=(0.0, 4.5, -11.0), rotation=(-0.3, 0.0, 0.0), resolution=(48, 27))
+            worlds.append(w.flatten())
+        rays = _incoherent_rays(4000)
+        _assert_equal_except_ties(O.trace_closest(O.Scene(worlds[1]), *rays), O.trace_closest(O.Scene(worlds[0]), *rays))
+    with pytest.raises(capi.RzbError):
+        capi.refit_mesh_bvh(v2[:10], t, nodes, order)  # vertex ids out of range
+
+
 # ---------------------------------------------------------------------------------------------- GPU
 @pytest.mark.gpu
 @pytest.mark.parametrize("name", NAMES)

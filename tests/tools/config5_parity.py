@@ -87,6 +87,20 @@ def main():
     rays = torch.tensor([float(passes) * float(ctx.render_stats()["ray_count"]) / max(passes, 1)], dtype=torch.float64, device="cuda")
     if dist is not None:
         dist.all_reduce(rays, op=dist.ReduceOp.SUM)
+    # ---- the same estimator at EQUAL PASSES: radiance = rgb sum / completed paths is a ratio estimator -- paths still in
+    # flight have added light but are not counted yet, which biases every finite render high by O(1 / passes), in the
+    # reference and here alike. So next to the 4096-spp image every rank also renders the whole frame with its own seed
+    # for exactly the reference's pass count; the mean of these `world` independent renders has the reference's bias and
+    # 1/sqrt(world) of its noise.
+    ctx.set_row_interleave(0, 1)
+    ctx.set_config(1, 1, 16, capi.FLAG_CPU_SEMANTICS, parallel.stream_seed(777, rank))
+    ctx.reset()
+    ctx.render(a.ref_passes)
+    eq = ctx.accum_tensor().clone()
+    eq_rad = eq[..., :3] / torch.clamp(eq[..., 3:4], min=1.0)
+    if dist is not None:
+        dist.reduce(eq_rad, dst=0, op=dist.ReduceOp.SUM)
+    eq_rad = (eq_rad / float(max(world, 1))).cpu().numpy() if rank == 0 else None
     if rank == 0:
         acc = total.cpu().numpy()
         tmp = tempfile.mkdtemp(prefix="rzb_cfg5_")
@@ -114,13 +128,30 @@ def main():
             "rel_rmse_block8_ref_a_vs_b": rel_rmse(block_mean(A, 8), block_mean(B, 8)),
             "rel_rmse_block32_gpu_vs_refmean": rel_rmse(block_mean(G, 32), block_mean(M, 32)),
             "rel_rmse_block32_ref_a_vs_b": rel_rmse(block_mean(A, 32), block_mean(B, 32)),
-            "expected": "the GPU image is converged (4096 spp), so relRMSE(GPU, mean of A and B) should be the reference's own "
-                        "noise / sqrt(2): relRMSE(A, B) / 2",
+            "note": "the 4096-spp image differs from the short reference renders by the reference's noise AND by the finite-pass "
+                    "bias of the ratio estimator (rgb sum / completed paths: in-flight paths have added light but are not "
+                    "counted), which both engines share -- parity is judged at equal passes below",
         }
-        res["within_tolerance"] = bool(res["mean_rel_diff"] < 0.01 and
-                                       res["rel_rmse_block8_gpu_vs_refmean"] <= 0.5 * res["rel_rmse_block8_ref_a_vs_b"] * 1.15 + 0.005 and
-                                       res["rel_rmse_block32_gpu_vs_refmean"] <= 0.5 * res["rel_rmse_block32_ref_a_vs_b"] * 1.15 + 0.005)
-        res["tolerance"] = "mean within 1 %; block-8 and block-32 relRMSE vs the reference mean <= 1.15 x (reference A-vs-B / 2) + 0.005"
+        E = eq_rad
+        k_noise = float(np.sqrt(0.25 + 0.5 / max(world, 1)))  # relRMSE(mean of `world` renders, mean(A, B)) / relRMSE(A, B) for one estimator
+        res.update({
+            "equal_passes": a.ref_passes, "equal_passes_renders": world,
+            "mean_radiance_gpu_equal_passes": float(E.mean()),
+            "mean_rel_diff_equal_passes": float(abs(E.mean() - M.mean()) / M.mean()),
+            "finite_pass_bias_of_the_estimator (gpu equal passes vs gpu 4096 spp)": float(E.mean() / G.mean() - 1.0),
+            "rel_rmse_pixel_equal_passes_vs_refmean": rel_rmse(E, M),
+            "rel_rmse_block8_equal_passes_vs_refmean": rel_rmse(block_mean(E, 8), block_mean(M, 8)),
+            "rel_rmse_block32_equal_passes_vs_refmean": rel_rmse(block_mean(E, 32), block_mean(M, 32)),
+            "expected_ratio_to_ref_a_vs_b": k_noise,
+        })
+        res["within_tolerance"] = bool(
+            res["mean_rel_diff_equal_passes"] < 0.01 and
+            res["rel_rmse_pixel_equal_passes_vs_refmean"] <= 1.15 * k_noise * res["rel_rmse_pixel_ref_a_vs_b"] + 0.005 and
+            res["rel_rmse_block8_equal_passes_vs_refmean"] <= 1.15 * k_noise * res["rel_rmse_block8_ref_a_vs_b"] + 0.005 and
+            res["rel_rmse_block32_equal_passes_vs_refmean"] <= 1.15 * k_noise * res["rel_rmse_block32_ref_a_vs_b"] + 0.005)
+        res["tolerance"] = ("equal passes (same finite-pass bias on both sides): mean within 1 %; per-pixel, block-8 and block-32 "
+                            "relRMSE of the mean of %d GPU renders vs the mean of the two reference renders <= 1.15 x %.3f x "
+                            "(reference A-vs-B) + 0.005" % (world, k_noise))
         print(json.dumps(res), flush=True)
     ctx.close()
     if dist is not None:
