@@ -118,6 +118,7 @@ struct rzb_ctx
 	uint32_t sort_dir_bits = 3;    // RZB200_SORT_DIRBITS: 0 = direction octant (8 bins), n = octahedral map with 2^n x 2^n bins
 	bool sort_shadow = true;       // RZB200_SORT_SHADOW=0: leave the shadow queue in append order
 	uint32_t sort_shadow_bits = 6; // RZB200_SORT_SHADOW_BITS: Morton cells per axis of the shadow-ray bins
+	bool order_reversed = true;    // RZB200_SORT_REVERSE=0: hand the ordered batches out front to back
 	bool sort_dir_major = false;   // RZB200_SORT_MAJOR=1: direction bin is the major key, origin cell the minor one
 	bool order_valid = false;      // false until the first ordering after a reset
 	enum { kSortKeys, kSortRank, kSortOrder, kSortBins, kSortOffsets, kSortTemp, kSortShKeys, kSortShRank, kSortShOrder, kSortBufCount };
@@ -381,6 +382,7 @@ extern "C" int rzb_create(int device, rzb_ctx** out)
 	if (const char* env = std::getenv("RZB200_SORT_SHADOW")) ctx->sort_shadow = std::atoi(env) != 0;
 	if (const char* env = std::getenv("RZB200_SORT_SHADOW_BITS")) ctx->sort_shadow_bits = uint32_t(std::min(std::max(std::atoi(env), 1), 7));
 	if (const char* env = std::getenv("RZB200_SORT_MAJOR")) ctx->sort_dir_major = std::atoi(env) != 0;
+	if (const char* env = std::getenv("RZB200_SORT_REVERSE")) ctx->order_reversed = std::atoi(env) != 0;
 	// any-hit walks visit the nearer-entry child first (measured: shadow kernel 0.240 -> 0.220 ms per pass on the
 	// 1M-triangle scene, 0.677 -> 0.670 on the materials scene; the result does not depend on the order)
 	ctx->x_flags |= kFlagAnyHitNearFirst;
@@ -926,6 +928,7 @@ extern "C" int rzb_render(rzb_ctx* ctx, uint32_t passes)
 		f.sort_bounce_bins = 1u << (3u * ctx->sort_bits + dir_bins_log2);
 		f.sort_shadow_base = f.sort_camera_bins + f.sort_bounce_bins + 1u;
 		f.sort_shadow_bits = ctx->sort_shadow_bits;
+		f.order_reversed = ctx->order_reversed ? 1u : 0u;
 		f.sort_dir_major = ctx->sort_dir_major ? 1u : 0u;
 		const uint32_t shadow_bins = (lights && ctx->sort_shadow) ? (1u << (3u * ctx->sort_shadow_bits + 2u)) : 0u;
 		n_bins = f.sort_shadow_base + shadow_bins;

@@ -10,7 +10,7 @@
 // and emits nodes/objects in the order of
 //   Mesh::reconstruct              /root/reference/RayZath/cuda_instance.cu:161-220  (siblings adjacent, breadth pair first)
 //   ObjectContainerWithBVH::constructNode  /root/reference/RayZath/cuda_bvh.cuh:86-111 (pre-order pairs)
-// tests/test_bvh_build.py checks the output byte-for-byte against the reference builder (oracle/_ref).
+// tests/test_flatten.py checks the output byte-for-byte against the reference builder (oracle/_ref).
 //
 // Floating-point notes: every operation is single precision in the reference's order; this file must
 // be compiled with -ffp-contract=off (no FMA contraction) — see csrc/Makefile.

@@ -74,6 +74,7 @@ namespace rzb
 		uint32_t sort_dir_major;       // 1: direction bin major, origin cell minor
 		uint32_t sort_dir_bits;        // 0: direction octant; n: octahedral map, 2^n x 2^n bins
 		uint32_t sort_camera_bins, sort_bounce_bins, sort_shadow_base;
+		uint32_t order_reversed;       // k_trace_paths hands the ordered batches out back to front
 	};
 
 	// Bin of a ray for the order pass. Regenerated camera rays keep their tile order (one bin per 32 slots: they are
@@ -275,8 +276,11 @@ namespace rzb
 		TraceCounters cnt{0u, 0u, 0u, 0u};
 		for (;;)
 		{
-			const uint32_t base = f.slot_begin + warp_batch(&f.counters[0]);
+			uint32_t base = f.slot_begin + warp_batch(&f.counters[0]);
 			if (base >= f.slot_end) break;
+			// with ray ordering the bounce rays (the long walks) sit behind the camera rays in the order: hand the batches
+			// out from the back, so that the kernel's tail consists of short walks
+			if (f.order != nullptr && f.order_reversed) base = f.slot_begin + ((f.slot_end - f.slot_begin - 1u) & ~31u) - (base - f.slot_begin);
 			uint32_t slot = base + (threadIdx.x & 31u);
 			if (f.order != nullptr && slot < f.slot_end) slot = f.order[slot - f.slot_begin];
 			uint32_t x, y;
