@@ -349,7 +349,7 @@ def main():
     ap.add_argument("--split", default="samples", choices=["samples", "tiles", "hybrid"],
                     help="N>1: samples = every rank renders the whole frame with its own RNG stream (weak scaling, default); "
                          "tiles = rank r renders row band r of N (strong scaling); hybrid = N/2 bands x 2 streams")
-    ap.add_argument("--bvh", default="reference", choices=["reference", "sah", "lbvh"],
+    ap.add_argument("--bvh", default="reference", choices=["reference", "sah", "sah4", "lbvh"],
                     help="triangle trees: the reference's own (parity mode, default), the optional SAH builder (host) or the "
                          "optional linear-BVH builder (GPU)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -583,6 +583,7 @@ def main():
             "value": value, "ms_per_step": ms_max / args.steps,
             "config": describe_config(args.workload, world_obj, ((W + 15) // 16) * ((H + 15) // 16) * 256),
             "run": {"bvh": {"reference": "reference trees", "sah": "optional SAH builder (leaf <= 4)",
+                            "sah4": "optional SAH builder (leaf <= 4), collapsed to 4-ary trees",
                             "lbvh": "optional GPU linear-BVH builder (leaf <= 4)"}[BVH],
                     "sharding": ("%d row band(s) x %d sample stream(s)" % (bands, streams)) if world > 1 else "single GPU",
                     "reduce": args.reduce if world > 1 else None, "spp_per_s": spp_per_s,

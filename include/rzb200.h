@@ -169,6 +169,11 @@ enum
 	                                  materials, maps and lights are replaced. Instances may only reference the meshes of that
 	                                  upload. Fails with RZB_ERR_STATE when there is no previous full upload or the instance
 	                                  tree outgrew the space reserved for it (then upload the whole scene). */
+	RZB_SCENE_WIDE_TREES = 4,      /* with RZB_SCENE_OWN_TREES (wide collapse): rzb_set_scene collapses the
+	                                  uploaded binary mesh trees into 4-ary ones (a node's children are replaced by its
+	                                  grandchildren, largest box first) and the own-tree kernels walk those: one 112-byte fetch and
+	                                  four conservative box tests per step, nearest hit first. Same hit records as the binary
+	                                  trees except exact ties. At most 2^25 triangles and 15 triangles per leaf. */
 	RZB_SCENE_OWN_TREES = 1        /* the mesh trees come from another builder (rzb_build_mesh_bvh_sah): nothing has to
 	                                  follow the reference's box decisions, so the kernels use a cheaper conservative
 	                                  box test; closest-hit records still equal the reference's except on exact ties */

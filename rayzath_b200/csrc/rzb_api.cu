@@ -4,6 +4,7 @@
 //   Renderer::renderFunction     /root/reference/RayZath/cuda_engine_renderer.cu:73-262 (kernel sequence)
 //   World/Mesh/Instance/...::reconstruct  (chunked pinned-memory mirroring -> one flattened upload here)
 #include "rzb_kernels.cuh"
+#include "rzb_wide.hpp"
 
 #include <algorithm>
 #include <cmath>
@@ -73,7 +74,7 @@ struct rzb_ctx
 	// scene mirror: grow-only device buffers, reused across rzb_set_scene calls (no cudaMalloc/cudaFree when the
 	// world keeps its size, which is the per-frame case of a host that re-sends a dirty world)
 	enum { kBufNodes, kBufTriRaw, kBufHot, kBufCold, kBufMeshNodesRaw, kBufMeshTable, kBufInstances, kBufInstHost,
-		kBufTriHost, kBufInstMats, kBufMaterials, kBufMaps, kBufDirect, kBufSpot, kBufCount };
+		kBufTriHost, kBufInstMats, kBufMaterials, kBufMaps, kBufDirect, kBufSpot, kBufNodes4, kBufInstRoot4, kBufCount };
 	DeviceBuffer scene_buf[kBufCount];
 	std::vector<DeviceBuffer> map_pixel_buf;
 	DScene sc{};
@@ -95,7 +96,7 @@ struct rzb_ctx
 
 	uint64_t passes = 0, launches = 0;
 	float last_render_ms = 0.0f, last_trace_ms = 0.0f, last_shade_ms = 0.0f, last_shadow_ms = 0.0f;
-	int trace_grid = 0, shadow_grid = 0, rays_grid = 0, any_grid = 0, trace_grid_fast = 0;
+	int trace_grid = 0, shadow_grid = 0, rays_grid = 0, any_grid = 0, trace_grid_fast = 0, wide_grid = 0;
 	// temporal reprojection history (RZB_FLAG_TEMPORAL_REPROJECTION)
 	float4* d_prev_accum = nullptr;
 	float* d_prev_depth = nullptr;
@@ -107,6 +108,9 @@ struct rzb_ctx
 	std::vector<uint32_t> geom_mesh_base;
 	uint32_t geom_top_base = 0, geom_top_capacity = 0, geom_triangle_count = 0, geom_mesh_depth = 0;
 	bool geom_own_trees = false;
+	bool geom_wide = false;                    // RZB_SCENE_WIDE_TREES: 4-ary mesh trees built by rzb_set_scene
+	std::vector<uint32_t> geom_mesh_root4;     // per mesh: reference of its wide root (kWideEmpty = no tree)
+	uint32_t geom_wide_depth = 0;
 	bool set_carveout = true;      // RZB200_CARVEOUT=0 disables the shared-memory carve-out hint
 	bool own_trees = false;        // rzb_scene::flags & RZB_SCENE_OWN_TREES: conservative box tests
 	bool debug_sync = false;       // RZB200_DEBUG_SYNC: synchronise after every kernel of rzb_render and name the one that faulted
@@ -391,7 +395,9 @@ extern "C" int rzb_create(int device, rzb_ctx** out)
 	ctx->shadow_grid = gridFor(ctx, reinterpret_cast<const void*>(&k_trace_shadow<false>), kTraceBlock);
 	ctx->trace_grid_fast = gridFor(ctx, reinterpret_cast<const void*>(&k_trace_paths<false, true>), kTraceBlock);
 	ctx->rays_grid = gridFor(ctx, reinterpret_cast<const void*>(&k_trace_rays<false, false>), kTraceBlock);
-	ctx->any_grid = gridFor(ctx, reinterpret_cast<const void*>(&k_trace_any_rays), kTraceBlock);
+	ctx->any_grid = gridFor(ctx, reinterpret_cast<const void*>(&k_trace_any_rays<false>), kTraceBlock);
+	ctx->wide_grid = gridFor(ctx, reinterpret_cast<const void*>(&k_trace_paths<false, true, false, true>), kTraceBlock);
+	gridFor(ctx, reinterpret_cast<const void*>(&k_trace_rays<false, true, true>), kTraceBlock);
 	if (const char* env = std::getenv("RZB200_MR_RAYS")) ctx->mr_k = std::atoi(env) <= 2 ? 2 : 4;
 	if (const char* env = std::getenv("RZB200_MR_STEPS")) ctx->mr_steps = std::min(std::max(std::atoi(env), 1), 2);
 	{
@@ -557,6 +563,7 @@ extern "C" int rzb_set_scene(rzb_ctx* ctx, const rzb_scene* s)
 
 	// ---- node placement: every tree is placed so that its root sits at an odd global index; sibling pairs (odd
 	// local index, next even) then start at even global indices = 64-byte aligned
+	std::vector<WideNode> wide_nodes; // RZB_SCENE_WIDE_TREES: the collapsed mesh trees of a full upload
 	std::vector<MeshEntry> table; // non-empty meshes only, ascending node_offset
 	std::vector<uint32_t> mesh_base(mesh_count, kNoIndex);
 	uint32_t top_base = 0;
@@ -612,7 +619,26 @@ extern "C" int rzb_set_scene(rzb_ctx* ctx, const rzb_scene* s)
 			mesh_depth = std::max(mesh_depth, depth);
 		}
 		ctx->geom_mesh_depth = mesh_depth;
+		// ---- optional wide collapse of the own trees
+		ctx->geom_wide = false;
+		wide_nodes.clear();
+		if ((s->flags & RZB_SCENE_WIDE_TREES) != 0u)
+		{
+			if ((s->flags & RZB_SCENE_OWN_TREES) == 0u)
+				return fail(ctx, RZB_ERR_INVALID, "rzb_set_scene: RZB_SCENE_WIDE_TREES needs RZB_SCENE_OWN_TREES (the reference's trees are walked as they are)");
+			ctx->geom_mesh_root4.assign(s->mesh_count, kWideEmpty);
+			ctx->geom_wide_depth = 0;
+			bool ok = true;
+			for (uint32_t m = 0; m < s->mesh_count && ok; ++m)
+				if (mesh_base[m] != kNoIndex)
+					ctx->geom_mesh_root4[m] = collapseWide(s->mesh_nodes + s->meshes[m].node_offset, 0u, s->meshes[m].tri_offset, wide_nodes, 0u,
+						ctx->geom_wide_depth, ok);
+			if (!ok) return fail(ctx, RZB_ERR_INVALID, "rzb_set_scene: RZB_SCENE_WIDE_TREES supports at most 2^25 triangles and 15 triangles per leaf");
+			ctx->geom_wide = true;
+		}
 	}
+	if (ctx->geom_wide && 3u * ctx->geom_wide_depth + 4u > uint32_t(kSmemStack + kLocalStack))
+		return fail(ctx, RZB_ERR_INVALID, "rzb_set_scene: wide trees too deep for the traversal stack");
 	// instance tree (small): fixed up on the host
 	// (a world without instances has no tree to walk: its nodes, if any, are not looked at)
 	const uint32_t top_node_count = s->instance_count ? s->instance_node_count : 0u;
@@ -739,6 +765,11 @@ extern "C" int rzb_set_scene(rzb_ctx* ctx, const rzb_scene* s)
 				k_iota<<<(s->triangle_count + 255) / 256, 256, 0, ctx->stream>>>(static_cast<uint32_t*>(B[rzb_ctx::kBufTriHost].ptr), s->triangle_count);
 		}
 	}
+	if (!keep_geometry && ctx->geom_wide)
+	{
+		const WideNode* d_wide = nullptr;
+		if ((rc = uploadTo(ctx, B[rzb_ctx::kBufNodes4], wide_nodes.data(), wide_nodes.size(), &d_wide))) return rc;
+	}
 	if (top_node_count)
 		RZB_CUDA(ctx, cudaMemcpyAsync(d_nodes + 2 * size_t(top_base), top_nodes.data(), top_nodes.size() * 32, cudaMemcpyHostToDevice, ctx->stream));
 	RZB_CUDA(ctx, cudaGetLastError());
@@ -753,6 +784,16 @@ extern "C" int rzb_set_scene(rzb_ctx* ctx, const rzb_scene* s)
 	if ((rc = uploadTo(ctx, B[rzb_ctx::kBufMaps], maps.data(), maps.size(), &sc.maps))) return rc;
 	if ((rc = uploadTo(ctx, B[rzb_ctx::kBufDirect], s->direct_lights, s->direct_light_count, &sc.direct_lights))) return rc;
 	if ((rc = uploadTo(ctx, B[rzb_ctx::kBufSpot], s->spot_lights, s->spot_light_count, &sc.spot_lights))) return rc;
+	std::vector<uint32_t> inst_root4;
+	if (ctx->geom_wide)
+	{
+		inst_root4.resize(s->instance_count, kWideEmpty);
+		for (uint32_t i = 0; i < s->instance_count; ++i)
+			if (s->instances[i].mesh != RZB_NO_INDEX && s->instances[i].mesh < ctx->geom_mesh_root4.size())
+				inst_root4[i] = ctx->geom_mesh_root4[s->instances[i].mesh];
+		if ((rc = uploadTo(ctx, B[rzb_ctx::kBufInstRoot4], inst_root4.data(), inst_root4.size(), &sc.inst_root4))) return rc;
+		sc.nodes4 = static_cast<const float4*>(B[rzb_ctx::kBufNodes4].ptr);
+	}
 	sc.top_root = top_base;
 	sc.instance_count = s->instance_count;
 	sc.material_count = s->material_count;
@@ -971,7 +1012,12 @@ extern "C" int rzb_render(rzb_ctx* ctx, uint32_t passes)
 		RZB_CUDA(ctx, cudaMemsetAsync(ctx->d_counters, 0, 12, ctx->stream));
 		f.order = (ctx->sort_enabled && ctx->order_valid) ? static_cast<const uint32_t*>(ctx->sort_buf[rzb_ctx::kSortOrder].ptr) : nullptr;
 		if (timed) cudaEventRecord(ev[0], ctx->stream);
-		if (ctx->trace_mr)
+		if (fast && ctx->geom_wide)
+		{
+			if (count) k_trace_paths<true, true, false, true><<<ctx->wide_grid, kTraceBlock, 0, ctx->stream>>>(ctx->sc, f);
+			else k_trace_paths<false, true, false, true><<<ctx->wide_grid, kTraceBlock, 0, ctx->stream>>>(ctx->sc, f);
+		}
+		else if (ctx->trace_mr)
 		{
 			const MrPathKernel kernel = reinterpret_cast<MrPathKernel>(const_cast<void*>(mrPathKernel(ctx->mr_k, ctx->mr_steps, count, fast)));
 			kernel<<<ctx->mr_grid[fast ? 1 : 0], kMrBlock, ctx->mr_smem, ctx->stream>>>(ctx->sc, f);
@@ -1015,6 +1061,8 @@ extern "C" int rzb_render(rzb_ctx* ctx, uint32_t passes)
 		if (timed) cudaEventRecord(ev[4], ctx->stream);
 		if (lights)
 		{
+			// (wide trees: the any-hit walk stays on the binary trees, which are on the device too -- measured faster there:
+			// 64 registers / 8 blocks per SM against 72 / 7, and an any-hit walk gains nothing from nearest-of-four ordering)
 			if (count) k_trace_shadow<true><<<ctx->shadow_grid, kTraceBlock, 0, ctx->stream>>>(ctx->sc, f);
 			else k_trace_shadow<false><<<ctx->shadow_grid, kTraceBlock, 0, ctx->stream>>>(ctx->sc, f);
 			ctx->launches += 1;
@@ -1469,7 +1517,11 @@ extern "C" int rzb_trace_closest_device(rzb_ctx* ctx, const void* rays_o_near, c
 	DeviceGuard guard(ctx->device);
 	RZB_CUDA(ctx, cudaMemsetAsync(ctx->d_counters + 8, 0, 4, ctx->stream));
 	if (elapsed_ms) RZB_CUDA(ctx, cudaEventRecord(ctx->ev_begin, ctx->stream));
-	if (ctx->trace_mr)
+	if (ctx->own_trees && ctx->geom_wide)
+		k_trace_rays<false, true, true><<<ctx->rays_grid, kTraceBlock, 0, ctx->stream>>>(ctx->sc,
+			static_cast<const float4*>(rays_o_near), static_cast<const float4*>(rays_d_far), n,
+			static_cast<DHit*>(hits_out_device), ctx->d_counters + 8, nullptr);
+	else if (ctx->trace_mr)
 		reinterpret_cast<MrRaysKernel>(const_cast<void*>(mrRaysKernel(ctx->mr_k, ctx->mr_steps, ctx->own_trees)))<<<ctx->mr_grid[ctx->own_trees ? 1 : 0], kMrBlock, ctx->mr_smem, ctx->stream>>>(ctx->sc,
 			static_cast<const float4*>(rays_o_near), static_cast<const float4*>(rays_d_far), n,
 			static_cast<DHit*>(hits_out_device), ctx->d_counters + 8, nullptr);
@@ -1496,7 +1548,7 @@ extern "C" int rzb_trace_closest_device_counted(rzb_ctx* ctx, const void* rays_o
 	DeviceGuard guard(ctx->device);
 	unsigned long long* d_stats = reinterpret_cast<unsigned long long*>(ctx->d_counters + 10);
 	RZB_CUDA(ctx, cudaMemsetAsync(ctx->d_counters + 8, 0, 40, ctx->stream));
-	(ctx->own_trees ? k_trace_rays<true, true> : k_trace_rays<true, false>)<<<ctx->rays_grid, kTraceBlock, 0, ctx->stream>>>(ctx->sc,
+	(ctx->own_trees ? (ctx->geom_wide ? k_trace_rays<true, true, true> : k_trace_rays<true, true, false>) : k_trace_rays<true, false, false>)<<<ctx->rays_grid, kTraceBlock, 0, ctx->stream>>>(ctx->sc,
 		static_cast<const float4*>(rays_o_near), static_cast<const float4*>(rays_d_far), n,
 		static_cast<DHit*>(hits_out_device), ctx->d_counters + 8, d_stats);
 	ctx->launches += 1;
@@ -1519,9 +1571,13 @@ extern "C" int rzb_trace_closest(rzb_ctx* ctx, const float* origins, const float
 	unsigned long long* d_stats = reinterpret_cast<unsigned long long*>(ctx->d_counters + 10);
 	RZB_CUDA(ctx, cudaMemsetAsync(ctx->d_counters + 8, 0, 40, ctx->stream));
 	if (stats)
-		(ctx->own_trees ? k_trace_rays<true, true> : k_trace_rays<true, false>)<<<ctx->rays_grid, kTraceBlock, 0, ctx->stream>>>(ctx->sc,
+		(ctx->own_trees ? (ctx->geom_wide ? k_trace_rays<true, true, true> : k_trace_rays<true, true, false>) : k_trace_rays<true, false, false>)<<<ctx->rays_grid, kTraceBlock, 0, ctx->stream>>>(ctx->sc,
 			static_cast<const float4*>(ctx->scratch[0].ptr), static_cast<const float4*>(ctx->scratch[1].ptr), n,
 			static_cast<DHit*>(ctx->scratch[2].ptr), ctx->d_counters + 8, d_stats);
+	else if (ctx->own_trees && ctx->geom_wide)
+		k_trace_rays<false, true, true><<<ctx->rays_grid, kTraceBlock, 0, ctx->stream>>>(ctx->sc,
+			static_cast<const float4*>(ctx->scratch[0].ptr), static_cast<const float4*>(ctx->scratch[1].ptr), n,
+			static_cast<DHit*>(ctx->scratch[2].ptr), ctx->d_counters + 8, nullptr);
 	else if (ctx->trace_mr)
 		reinterpret_cast<MrRaysKernel>(const_cast<void*>(mrRaysKernel(ctx->mr_k, ctx->mr_steps, ctx->own_trees)))<<<ctx->mr_grid[ctx->own_trees ? 1 : 0], kMrBlock, ctx->mr_smem, ctx->stream>>>(ctx->sc,
 			static_cast<const float4*>(ctx->scratch[0].ptr), static_cast<const float4*>(ctx->scratch[1].ptr), n,
@@ -1557,7 +1613,7 @@ extern "C" int rzb_trace_any(rzb_ctx* ctx, const float* origins, const float* di
 	if ((rc = packRays(ctx, origins, directions, near_far, n))) return rc;
 	if ((rc = ensureScratch(ctx, 2, size_t(n) * 16))) return rc;
 	RZB_CUDA(ctx, cudaMemsetAsync(ctx->d_counters + 8, 0, 4, ctx->stream));
-	k_trace_any_rays<<<ctx->any_grid, kTraceBlock, 0, ctx->stream>>>(ctx->sc,
+	k_trace_any_rays<false><<<ctx->any_grid, kTraceBlock, 0, ctx->stream>>>(ctx->sc,
 		static_cast<const float4*>(ctx->scratch[0].ptr), static_cast<const float4*>(ctx->scratch[1].ptr), n,
 		static_cast<float4*>(ctx->scratch[2].ptr), ctx->d_counters + 8);
 	ctx->launches += 1;

@@ -82,6 +82,8 @@ namespace rzb
 	struct DScene
 	{
 		const float4* nodes;    // 2 x float4 per node: {min.xyz, max.x}, {max.y, max.z, begin, type_count}; global indices
+		const float4* nodes4;   // wide (4-ary) mesh nodes, 8 x float4 each (RZB_SCENE_WIDE_TREES), else NULL
+		const uint32_t* inst_root4; // per instance: reference of its mesh's wide root (rzb_traverse.cuh: wide_decode)
 		const float4* tri_hot;  // 3 x float4 per triangle: {v1.xyz, e1.x}, {e1.yz, e2.xy}, {e2.z, slot, -, -}
 		const float4* tri_cold; // 5 x float4 per triangle: n1, n2, n3, face normal, uvs
 		const DInstance* instances;

@@ -266,8 +266,8 @@ namespace rzb
 		}
 	}
 
-	template <bool STATS, bool FAST, bool SYNC = false>
-	__global__ void __launch_bounds__(kTraceBlock, FAST ? 8 : 6) k_trace_paths(DScene sc, DFrame f)
+	template <bool STATS, bool FAST, bool SYNC = false, bool WIDE = false>
+	__global__ void __launch_bounds__(kTraceBlock, (FAST && !WIDE) ? 8 : 6) k_trace_paths(DScene sc, DFrame f)
 	{
 		__shared__ uint2 smem_stack[kSmemStack * kTraceBlock];
 		__shared__ ParkedRay smem_park[kTraceBlock];
@@ -304,7 +304,7 @@ namespace rzb
 				}
 			}
 			RayResult r;
-			trace_ray<false, STATS, SYNC, FAST>(sc, active, v3(so.x, so.y, so.z), v3(sd.x, sd.y, sd.z), near_, far_, st, park, cnt, r);
+			trace_ray<false, STATS, SYNC, FAST, WIDE>(sc, active, v3(so.x, so.y, so.z), v3(sd.x, sd.y, sd.z), near_, far_, st, park, cnt, r);
 			if (STATS) batch_utilisation(active ? r.steps + r.tris : 0u, f.work + 10);
 			if (!active) continue;
 			uint32_t tri_bits = flags | (r.external ? kHitExternalBit : 0u);
@@ -767,8 +767,8 @@ namespace rzb
 	// 0.43; conservative + synchronised 1.12 / 0.35; conservative + free-running 0.77 / 0.25 (kept).
 	// Dropped: giving finished lanes new rays between synchronised rounds (threshold 1..24 idle lanes) raised the
 	// share of busy lane-rounds from 0.44 to 0.70-0.88 but not the speed (1.28..1.41 ms).
-	template <bool STATS>
-	__global__ void __launch_bounds__(kTraceBlock, 8) k_trace_shadow(DScene sc, DFrame f)
+	template <bool STATS, bool WIDE = false>
+	__global__ void __launch_bounds__(kTraceBlock, WIDE ? 6 : 8) k_trace_shadow(DScene sc, DFrame f)
 	{
 		__shared__ uint2 smem_stack[kSmemStack * kTraceBlock];
 		__shared__ ParkedRay smem_park[kTraceBlock];
@@ -787,7 +787,7 @@ namespace rzb
 			float4 o = make_float4(0.0f, 0.0f, 0.0f, 0.0f), d = make_float4(0.0f, 0.0f, 1.0f, 0.0f);
 			if (active) { o = f.sh_o[i]; d = f.sh_d[i]; }
 			RayResult r;
-			trace_ray<true, STATS, false, true>(sc, active, v3(o.x, o.y, o.z), v3(d.x, d.y, d.z), 0.0f, o.w, st, park, cnt, r);
+			trace_ray<true, STATS, false, true, WIDE>(sc, active, v3(o.x, o.y, o.z), v3(d.x, d.y, d.z), 0.0f, o.w, st, park, cnt, r);
 			if (STATS) batch_utilisation(active ? r.steps + r.tris : 0u, f.work + 12);
 			const float w = r.mask.w;
 			if (!active || w <= 0.0f) continue;
@@ -958,7 +958,7 @@ namespace rzb
 	};
 	static_assert(sizeof(DHit) == 32, "DHit");
 
-	template <bool STATS, bool FAST>
+	template <bool STATS, bool FAST, bool WIDE = false>
 	__global__ void __launch_bounds__(kTraceBlock, 6) k_trace_rays(DScene sc, const float4* __restrict__ ray_o_near,
 		const float4* __restrict__ ray_d_far, uint32_t n, DHit* __restrict__ hits, uint32_t* counter,
 		unsigned long long* stats)
@@ -977,7 +977,7 @@ namespace rzb
 			float4 o = make_float4(0.0f, 0.0f, 0.0f, 0.0f), d = make_float4(0.0f, 0.0f, 1.0f, 0.0f);
 			if (active) { o = __ldg(ray_o_near + i); d = __ldg(ray_d_far + i); }
 			RayResult r;
-			trace_ray<false, STATS, false, FAST>(sc, active, v3(o.x, o.y, o.z), v3(d.x, d.y, d.z), o.w, d.w, st, park, cnt, r);
+			trace_ray<false, STATS, false, FAST, WIDE>(sc, active, v3(o.x, o.y, o.z), v3(d.x, d.y, d.z), o.w, d.w, st, park, cnt, r);
 			if (!active) continue;
 			const uint32_t tri_bits = (r.tri == kNoIndex ? kHitTriMask : (r.tri & kHitTriMask)) | (r.external ? kHitExternalBit : 0u);
 			float4* dst = reinterpret_cast<float4*>(hits + i);
@@ -1044,7 +1044,8 @@ namespace rzb
 	}
 
 	// the shadow kernel's traversal flavour (conservative boxes, free-running) over a caller's ray set
-	__global__ void __launch_bounds__(kTraceBlock, 8) k_trace_any_rays(DScene sc, const float4* __restrict__ ray_o_near,
+	template <bool WIDE = false>
+	__global__ void __launch_bounds__(kTraceBlock, WIDE ? 6 : 8) k_trace_any_rays(DScene sc, const float4* __restrict__ ray_o_near,
 		const float4* __restrict__ ray_d_far, uint32_t n, float4* __restrict__ masks, uint32_t* counter)
 	{
 		__shared__ uint2 smem_stack[kSmemStack * kTraceBlock];
@@ -1061,7 +1062,7 @@ namespace rzb
 			float4 o = make_float4(0.0f, 0.0f, 0.0f, 0.0f), d = make_float4(0.0f, 0.0f, 1.0f, 0.0f);
 			if (active) { o = __ldg(ray_o_near + i); d = __ldg(ray_d_far + i); }
 			RayResult r;
-			trace_ray<true, false, false, true>(sc, active, v3(o.x, o.y, o.z), v3(d.x, d.y, d.z), o.w, d.w, st, park, cnt, r);
+			trace_ray<true, false, false, true, WIDE>(sc, active, v3(o.x, o.y, o.z), v3(d.x, d.y, d.z), o.w, d.w, st, park, cnt, r);
 			if (active) masks[i] = r.mask;
 		}
 	}

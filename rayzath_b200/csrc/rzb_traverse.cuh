@@ -31,6 +31,18 @@ namespace rzb
 {
 	constexpr float kSlabMargin = 4.0e-7f; // > 2 ulp relative (2^-22 = 2.4e-7)
 	constexpr float kInf = __builtin_huge_valf();
+	// ---- wide (4-ary) mesh trees of the own-tree mode (RZB_SCENE_WIDE_TREES; built by rzb_set_scene from the uploaded
+	// binary trees). A node is 8 x float4: min.x[4], min.y[4], min.z[4], max.x[4], max.y[4], max.z[4], ref[4], spare.
+	// ref (30 bits, also what a deferred-node stack entry holds): leaf = bit 29 | count << 25 | first triangle (global,
+	// < 2^25); inner = index of the wide node; kWideEmpty = no child.
+	constexpr uint32_t kWideLeafBit = 1u << 29;
+	constexpr uint32_t kWideEmpty = 0x3FFFFFFFu;
+	__device__ __forceinline__ void wide_decode(const uint32_t ref, uint32_t& cur_begin, uint32_t& cur_tc)
+	{
+		const bool leaf = (ref & kWideLeafBit) != 0u;
+		cur_tc = leaf ? (ref >> 25) & 15u : 0u;
+		cur_begin = leaf ? ref & 0x1FFFFFFu : ref;
+	}
 	// internal bits of DScene::flags (above the public RZB_FLAG_* bits)
 	constexpr uint32_t kFlagAnyHitNearFirst = 1u << 16;
 
@@ -172,7 +184,7 @@ namespace rzb
 
 	// One round: descend from the current node to a leaf, intersect it, pop until a node with a passed box is current
 	// (or the ray is finished). Invariant: an alive lane has a current node whose box test has passed.
-	template <bool ANY, bool STATS, bool FAST>
+	template <bool ANY, bool STATS, bool FAST, bool WIDE = false>
 	__device__ __forceinline__ void trav_round(const DScene& sc, Trav& t, Stack& st, ParkedRay& park, TraceCounters& cnt)
 	{
 		const float4* __restrict__ nodes = sc.nodes;
@@ -182,6 +194,58 @@ namespace rzb
 		{
 			while ((t.cur_tc & 0x3FFFFFFFu) == 0u)
 			{
+				if (WIDE && t.in_mesh)
+				{
+					// one 4-ary step: 7 x LDG.128, four conservative slab tests, nearest hit first, the others deferred
+					const float4* q = sc.nodes4 + 8 * size_t(t.cur_begin);
+					const float4 mnx = __ldg(q), mny = __ldg(q + 1), mnz = __ldg(q + 2), mxx = __ldg(q + 3), mxy = __ldg(q + 4), mxz = __ldg(q + 5);
+					const float4 rf = __ldg(q + 6);
+					if (STATS) { cnt.mesh_nodes += 4; t.steps++; }
+					float tm[4];
+					uint32_t rr[4] = {__float_as_uint(rf.x), __float_as_uint(rf.y), __float_as_uint(rf.z), __float_as_uint(rf.w)};
+					const float bx0[4] = {mnx.x, mnx.y, mnx.z, mnx.w}, bx1[4] = {mxx.x, mxx.y, mxx.z, mxx.w};
+					const float by0[4] = {mny.x, mny.y, mny.z, mny.w}, by1[4] = {mxy.x, mxy.y, mxy.z, mxy.w};
+					const float bz0[4] = {mnz.x, mnz.y, mnz.z, mnz.w}, bz1[4] = {mxz.x, mxz.y, mxz.z, mxz.w};
+#pragma unroll
+					for (int c = 0; c < 4; ++c)
+					{
+						const float t1 = fmul(fsub(bx0[c], t.o.x), t.rcp.x), t2 = fmul(fsub(bx1[c], t.o.x), t.rcp.x);
+						const float t3 = fmul(fsub(by0[c], t.o.y), t.rcp.y), t4 = fmul(fsub(by1[c], t.o.y), t.rcp.y);
+						const float t5 = fmul(fsub(bz0[c], t.o.z), t.rcp.z), t6 = fmul(fsub(bz1[c], t.o.z), t.rcp.z);
+						const float tmin = fmaxf(fmaxf(fminf(t1, t2), fminf(t3, t4)), fminf(t5, t6));
+						const float tmax = fminf(fminf(fmaxf(t1, t2), fmaxf(t3, t4)), fmaxf(t5, t6));
+						const float lo = tmin * 0.9999995f, hi = tmax * 1.0000005f;
+						// (a slab test cannot tell an inverted box from a real one: empty slots are recognised by their reference)
+						tm[c] = (rr[c] != kWideEmpty && !(hi < t.near_ || lo > hi || lo > t.far_)) ? lo : kInf;
+					}
+					if (!ANY)
+					{
+						// ascending entry distance (5-comparator network); misses (inf) sink to the end
+#define RZB_CSWAP(a, b) { const bool sw = tm[b] < tm[a]; const float ta = sw ? tm[b] : tm[a], tb = sw ? tm[a] : tm[b]; \
+	const uint32_t ra = sw ? rr[b] : rr[a], rb = sw ? rr[a] : rr[b]; tm[a] = ta; tm[b] = tb; rr[a] = ra; rr[b] = rb; }
+						RZB_CSWAP(0, 1) RZB_CSWAP(2, 3) RZB_CSWAP(0, 2) RZB_CSWAP(1, 3) RZB_CSWAP(1, 2)
+#undef RZB_CSWAP
+						if (!(tm[0] < kInf)) { have_cur = false; break; }
+						if (tm[3] < kInf) st.push(kEntryMeshNode | rr[3], __float_as_uint(tm[3]));
+						if (tm[2] < kInf) st.push(kEntryMeshNode | rr[2], __float_as_uint(tm[2]));
+						if (tm[1] < kInf) st.push(kEntryMeshNode | rr[1], __float_as_uint(tm[1]));
+						wide_decode(rr[0], t.cur_begin, t.cur_tc);
+					}
+					else
+					{
+						uint32_t first = kWideEmpty;
+#pragma unroll
+						for (int c = 0; c < 4; ++c)
+							if (tm[c] < kInf)
+							{
+								if (first == kWideEmpty) first = rr[c];
+								else st.push(kEntryMeshNode | rr[c], __float_as_uint(tm[c]));
+							}
+						if (first == kWideEmpty) { have_cur = false; break; }
+						wide_decode(first, t.cur_begin, t.cur_tc);
+					}
+					continue;
+				}
 				const float4* pair = nodes + 2 * size_t(t.cur_begin); // 64-byte aligned sibling pair
 				const float4 p0 = __ldg(pair), p1 = __ldg(pair + 1), p2 = __ldg(pair + 2), p3 = __ldg(pair + 3);
 				if (STATS) { if (t.in_mesh) cnt.mesh_nodes += 2; else cnt.top_nodes += 2; t.steps++; }
@@ -316,6 +380,7 @@ namespace rzb
 				t.near_ = lnear; t.far_ = lfar;
 				t.cur_begin = __float_as_uint(r1.z);
 				t.cur_tc = __float_as_uint(r1.w);
+				if (WIDE) wide_decode(__ldg(sc.inst_root4 + idx), t.cur_begin, t.cur_tc);
 				break;
 			}
 			// a deferred node of the current level
@@ -337,6 +402,11 @@ namespace rzb
 					float texact;
 					if (!(slab_exact(x0, x1, t.o, t.d, t.near_, t.far_, texact) & 2u)) continue;
 				}
+			}
+			if (WIDE && t.in_mesh)
+			{
+				wide_decode(idx, t.cur_begin, t.cur_tc); // the entry IS the child reference: no node fetch at pop time
+				break;
 			}
 			const float4 n1 = __ldg(nodes + 2 * size_t(idx) + 1);
 			t.cur_begin = __float_as_uint(n1.z);
@@ -368,14 +438,14 @@ namespace rzb
 	// with the conservative test (64 registers, 8 blocks per SM): 0.25 free-running vs 0.35 synchronised -- every
 	// render kernel now instantiates SYNC = false, only the one-warp k_raycast keeps SYNC = true.
 	// FAST = true selects the conservative box test (slab_hit) and nearer-entry-first child order.
-	template <bool ANY, bool STATS, bool SYNC = ANY, bool FAST = false>
+	template <bool ANY, bool STATS, bool SYNC = ANY, bool FAST = false, bool WIDE = false>
 	__device__ __forceinline__ void trace_ray(const DScene& sc, const bool active, const V3 origin, const V3 direction,
 		const float near_in, const float far_in, Stack& st, ParkedRay& park, TraceCounters& cnt, RayResult& res)
 	{
 		Trav t;
 		trav_begin<ANY, STATS, FAST>(sc, t, active, origin, direction, near_in, far_in, st, park, cnt);
 		while (SYNC ? __any_sync(0xFFFFFFFFu, t.alive) != 0 : t.alive)
-			trav_round<ANY, STATS, FAST>(sc, t, st, park, cnt);
+			trav_round<ANY, STATS, FAST, WIDE>(sc, t, st, park, cnt);
 		trav_end(t, active, near_in, far_in, park, res);
 	}
 }

@@ -64,7 +64,8 @@ namespace RayZath::Cuda
 		uint64_t m_scene_version = 0;
 		uint64_t m_geometry_version = 0; // bumped when the Mesh container changed: everything else updates incrementally
 		bool m_full_upload = false; // RZB200_FULL_UPLOAD=1: re-upload the geometry on every world change (test aid)
-		bool m_own_trees = false; // RZB200_BVH=sah: this repo's SAH triangle trees instead of the host World's
+		bool m_own_trees = false; // RZB200_BVH=sah | sah4: this repo's SAH triangle trees instead of the host World's
+		bool m_wide_trees = false; // RZB200_BVH=sah4: ... collapsed to 4-ary trees by rzb_set_scene (RZB_SCENE_WIDE_TREES)
 		rzb_host::FlatScene m_flat;
 		std::string m_timings;
 
@@ -87,7 +88,11 @@ namespace RayZath::Cuda
 					if (!tok.empty()) m_devices.push_back(std::atoi(tok.c_str()));
 			}
 			if (m_devices.empty()) m_devices.push_back(0);
-			if (const char* env = std::getenv("RZB200_BVH")) m_own_trees = std::string(env) == "sah";
+			if (const char* env = std::getenv("RZB200_BVH"))
+			{
+				m_own_trees = std::string(env) == "sah" || std::string(env) == "sah4";
+				m_wide_trees = std::string(env) == "sah4";
+			}
 			if (const char* env = std::getenv("RZB200_FULL_UPLOAD")) m_full_upload = std::string(env) == "1";
 			if (const char* env = std::getenv("RZB200_SEED")) m_seed = std::strtoull(env, nullptr, 0);
 			else
@@ -196,6 +201,7 @@ namespace RayZath::Cuda
 				// container changed (the reference re-mirrors per container too, cuda_world.cu:40-76)
 				const bool geometry_dirty = m_scene_version == 0 || m_full_upload || containerModified<RZ::ObjectType::Mesh>(hWorld);
 				rzb_host::WorldFlattener(hWorld, m_flat, m_own_trees).run(!geometry_dirty);
+				if (m_wide_trees && (m_flat.scene_flags & RZB_SCENE_OWN_TREES)) m_flat.scene_flags |= RZB_SCENE_WIDE_TREES;
 				if (geometry_dirty) ++m_geometry_version;
 				++m_scene_version;
 				for (auto& [idx, cam] : m_cameras) cam.scene_current = false;

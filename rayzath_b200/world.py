@@ -81,7 +81,8 @@ class Mesh:
     normals_input: Optional[np.ndarray] = None  # what was passed to createNormal (written to scene files)
     _bvh: Optional[tuple] = None
     # "reference" = the reference's own tree (parity mode); ("sah", max_leaf) = the optional SAH builder;
-    # ("lbvh", max_leaf) = the optional GPU linear-BVH builder
+    # ("lbvh", max_leaf) = the optional GPU linear-BVH builder; ("sah4", max_leaf) = the SAH tree, collapsed to a 4-ary
+    # tree by rzb_set_scene (RZB_SCENE_WIDE_TREES)
     bvh_builder: object = "reference"
 
     def bvh(self):
@@ -287,7 +288,9 @@ class World:
         out["tri_host_index"] = np.concatenate(all_thi) if all_thi else np.zeros(0, dtype=np.uint32)
         out["meshes"] = np.array(mesh_recs, dtype=capi.mesh_dtype) if mesh_recs else np.zeros(0, dtype=capi.mesh_dtype)
         if any(m.bvh_builder != "reference" for m in self.meshes):
-            out["scene_flags"] = np.array([capi.SCENE_OWN_TREES], dtype=np.uint32)  # absent = the reference's trees
+            wide = any(isinstance(m.bvh_builder, tuple) and m.bvh_builder[0] == "sah4" for m in self.meshes)
+            out["scene_flags"] = np.array([capi.SCENE_OWN_TREES | (capi.SCENE_WIDE_TREES if wide else 0)],
+                                          dtype=np.uint32)  # absent = the reference's trees
 
         # lights
         dl = np.zeros(len(self.direct_lights), dtype=capi.direct_light_dtype)

@@ -27,6 +27,7 @@ struct { unsigned x = 0; } threadIdx;
 #endif
 #include "../../rayzath_b200/csrc/rzb_traverse.cuh"
 #include "../../rayzath_b200/csrc/rzb_traverse_mr.cuh"
+#include "../../rayzath_b200/csrc/rzb_wide.hpp"
 
 using namespace rzb;
 
@@ -46,6 +47,12 @@ extern "C" int trav_host_run(const rzb_scene* s, const float* origins, const flo
 	int any, rzb_hit* hits_out, float* masks_out, uint64_t* counters4)
 {
 	return trav_host_run_impl(s, origins, dirs, near_far, n, any, hits_out, masks_out, counters4, 0);
+}
+// the own-tree kernels' walk on 4-ary trees (RZB_SCENE_WIDE_TREES): conservative boxes, wide collapse of the given trees
+extern "C" int trav_host_run_wide(const rzb_scene* s, const float* origins, const float* dirs, const float* near_far, uint32_t n,
+	rzb_hit* hits_out, uint64_t* counters4)
+{
+	return trav_host_run_impl(s, origins, dirs, near_far, n, 0, hits_out, nullptr, counters4, 2);
 }
 // the multi-ray-per-lane walk (rzb_traverse_mr.cuh): ONE lane with kMrRays rays in flight, phases chosen by mr_vote
 extern "C" int trav_host_run_mr(const rzb_scene* s, const float* origins, const float* dirs, const float* near_far, uint32_t n,
@@ -119,7 +126,24 @@ static int trav_host_run_impl(const rzb_scene* s, const float* origins, const fl
 	sc.instance_count = s->instance_count;
 	sc.flags = RZB_FLAG_CPU_SEMANTICS;
 
-	if (mr)
+	std::vector<WideNode> wide;
+	std::vector<uint32_t> inst_root4(s->instance_count + 1, kWideEmpty);
+	if (mr == 2)
+	{
+		std::vector<uint32_t> root4(s->mesh_count, kWideEmpty);
+		uint32_t depth = 0;
+		bool ok = true;
+		for (uint32_t m = 0; m < s->mesh_count; ++m)
+			if (mesh_base[m] != kNoIndex)
+				root4[m] = collapseWide(s->mesh_nodes + s->meshes[m].node_offset, 0u, s->meshes[m].tri_offset, wide, 0u, depth, ok);
+		if (!ok) return 1;
+		for (uint32_t i = 0; i < s->instance_count; ++i)
+			if (s->instances[i].mesh != RZB_NO_INDEX) inst_root4[i] = root4[s->instances[i].mesh];
+		wide.emplace_back();
+		sc.nodes4 = reinterpret_cast<const float4*>(wide.data());
+		sc.inst_root4 = inst_root4.data();
+	}
+	if (mr == 1)
 	{
 		constexpr int K = kMrMaxRays;
 		std::vector<float4> smem(size_t(kMrFields) * K * kMrBlock);
@@ -193,7 +217,8 @@ static int trav_host_run_impl(const rzb_scene* s, const float* origins, const fl
 		}
 		else
 		{
-			trace_ray<false, true>(sc, true, o, d, near_far[2 * i], near_far[2 * i + 1], st, park, cnt, r);
+			if (mr == 2) trace_ray<false, true, false, true, true>(sc, true, o, d, near_far[2 * i], near_far[2 * i + 1], st, park, cnt, r);
+			else trace_ray<false, true>(sc, true, o, d, near_far[2 * i], near_far[2 * i + 1], st, park, cnt, r);
 			rzb_hit h{};
 			h.instance = RZB_NO_INDEX; h.triangle = RZB_NO_INDEX;
 			h.t = r.t;

@@ -22,7 +22,8 @@ NAMES = list(GOLDEN_SCENES)
 @pytest.fixture(scope="module")
 def sim():
     os.makedirs(os.path.dirname(OUT), exist_ok=True)
-    deps = [SRC] + [os.path.join(ROOT, "rayzath_b200", "csrc", f) for f in ("rzb_traverse.cuh", "rzb_traverse_mr.cuh", "rzb_device.cuh")]
+    deps = [SRC] + [os.path.join(ROOT, "rayzath_b200", "csrc", f)
+                    for f in ("rzb_traverse.cuh", "rzb_traverse_mr.cuh", "rzb_device.cuh", "rzb_wide.hpp")]
     if not os.path.exists(OUT) or any(os.path.getmtime(d) > os.path.getmtime(OUT) for d in deps):
         subprocess.run(["g++", "-std=c++17", "-O1", "-fPIC", "-shared", "-ffp-contract=off", "-I/usr/local/cuda/include",
                         "-o", OUT, SRC], check=True)
@@ -30,6 +31,7 @@ def sim():
     P = C.c_void_p
     lib.trav_host_run.argtypes = [P, P, P, P, C.c_uint32, C.c_int, P, P, P]
     lib.trav_host_run_mr.argtypes = [P, P, P, P, C.c_uint32, P, P]
+    lib.trav_host_run_wide.argtypes = [P, P, P, P, C.c_uint32, P, P]
     return lib
 
 
@@ -116,3 +118,37 @@ def test_multi_ray_lane_walk_matches_oracle(name, sim, golden, flats):
     ref, rst = O.trace_closest(scene, o, d, nf, order=O.ORDER_CUDA, minmax=O.MINMAX_FMINF, stats=True)
     assert np.array_equal(hits.view(np.uint8), ref.view(np.uint8))
     assert cnt.tolist() == [int(rst[k]) for k in ("top_nodes", "instances_entered", "mesh_nodes", "triangles")]
+
+
+@pytest.mark.parametrize("name", NAMES)
+def test_wide_tree_walk_matches_oracle_except_ties(name, sim, golden, flats):
+    """RZB_SCENE_WIDE_TREES on the host: the SAH tree of every mesh collapsed to a 4-ary tree (rzb_wide.hpp, as
+    rzb_set_scene does) and walked by the own-tree traversal (conservative boxes, nearest of four first). Same closest
+    hits as the oracle on the REFERENCE tree except exact-distance ties."""
+    from tests.golden_scenes import GOLDEN_SCENES
+    w = GOLDEN_SCENES[name]()
+    for m in w.meshes:
+        m.bvh_builder = ("sah4", 4)
+    scene = O.Scene(w.flatten())
+    g = golden[name]
+    rng = np.random.default_rng(9)
+    n = 20000
+    io = rng.uniform(-3, 3, (n, 3)).astype(np.float32)
+    io[:, 1] = rng.uniform(0.05, 3, n)
+    idd = rng.normal(size=(n, 3)).astype(np.float32)
+    idd = (idd / np.sqrt((idd * idd).sum(axis=1, dtype=np.float32))[:, None]).astype(np.float32)
+    inf = np.tile(np.array([0.0, 3.0e38], dtype=np.float32), (n, 1))
+    o = np.ascontiguousarray(np.concatenate([g["ray_origins"], io]), dtype=np.float32)
+    d = np.ascontiguousarray(np.concatenate([g["ray_directions"], idd]), dtype=np.float32)
+    nf = np.ascontiguousarray(np.concatenate([g["ray_near_far"], inf]), dtype=np.float32)
+    hits = np.zeros(len(o), dtype=capi.hit_dtype)
+    cnt = np.zeros(4, np.uint64)
+    rc = sim.trav_host_run_wide(C.addressof(scene.struct), o.ctypes.data, d.ctypes.data, nf.ctypes.data, len(o), hits.ctypes.data,
+                                cnt.ctypes.data)
+    assert rc == 0
+    ref = O.trace_closest(O.Scene(flats[name]), o, d, nf, order=O.ORDER_CUDA, minmax=O.MINMAX_FMINF)
+    same = (hits["instance"] == ref["instance"]) & (hits["triangle"] == ref["triangle"])
+    ties = np.flatnonzero(~same)
+    assert (hits["t"][ties] == ref["t"][ties]).all(), "a different triangle at a different distance: %s" % ties[:10].tolist()
+    assert ties.size <= 0.001 * len(o) + 1
+    assert np.array_equal(hits[same].view(np.uint8).reshape(-1, 24), ref[same].view(np.uint8).reshape(-1, 24))

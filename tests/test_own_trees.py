@@ -12,10 +12,10 @@ from tests.golden_scenes import GOLDEN_SCENES, RENDER_SETTINGS, shadow_rays
 NAMES = list(GOLDEN_SCENES)
 
 
-def _sah_world(name, max_leaf=4):
+def _sah_world(name, max_leaf=4, builder="sah"):
     w = GOLDEN_SCENES[name]()
     for m in w.meshes:
-        m.bvh_builder = ("sah", max_leaf)
+        m.bvh_builder = (builder, max_leaf)
     return w
 
 
@@ -145,12 +145,15 @@ def test_refit_keeps_topology_and_bounds_the_deformed_mesh():
 
 # ---------------------------------------------------------------------------------------------- GPU
 @pytest.mark.gpu
+@pytest.mark.parametrize("builder", ["sah", "sah4"])
 @pytest.mark.parametrize("name", NAMES)
-def test_gpu_sah_tree_hits_vs_oracle_on_reference_tree(name, golden, flats):
+def test_gpu_sah_tree_hits_vs_oracle_on_reference_tree(name, builder, golden, flats):
+    """`sah4` = the same SAH tree collapsed into a 4-ary one by rzb_set_scene (RZB_SCENE_WIDE_TREES): one fetch and four
+    conservative box tests per step."""
     g = golden[name]
-    w = _sah_world(name)
+    w = _sah_world(name, builder=builder)
     flat = w.flatten()
-    assert int(flat["scene_flags"][0]) == capi.SCENE_OWN_TREES
+    assert int(flat["scene_flags"][0]) == capi.SCENE_OWN_TREES | (capi.SCENE_WIDE_TREES if builder == "sah4" else 0)
     with capi.Context(0) as c:
         c.set_scene(flat)
         c.set_camera(w.camera_struct())
@@ -173,16 +176,17 @@ def test_gpu_sah_tree_full_size_primary_rays():
     w = scenes.heightfield_scene(resolution=(1920, 1080))
     cam = w.camera_struct()
     res = {}
-    for builder in ("reference", ("sah", 4)):
+    for builder in ("reference", ("sah", 4), ("sah4", 4)):
         for m in w.meshes:
             m.bvh_builder = builder
         with capi.Context(0) as c:
             c.set_scene(w.flatten())
             c.set_camera(cam)
             o, d, nf = c.generate_camera_rays()
-            res[builder if builder == "reference" else "sah"] = c.trace_closest(o, d, nf)
+            res[builder if builder == "reference" else builder[0]] = c.trace_closest(o, d, nf)
     assert (res["reference"]["instance"] != capi.NO_INDEX).mean() > 0.5
     _assert_equal_except_ties(res["sah"], res["reference"], max_tie_fraction=1e-4)
+    _assert_equal_except_ties(res["sah4"], res["reference"], max_tie_fraction=1e-4)
 
 
 @pytest.mark.gpu
@@ -192,7 +196,7 @@ def test_gpu_sah_tree_same_image():
     name = "materials"
     passes, depth = RENDER_SETTINGS[name]
     acc = {}
-    for label, w in (("reference", GOLDEN_SCENES[name]()), ("sah", _sah_world(name))):
+    for label, w in (("reference", GOLDEN_SCENES[name]()), ("sah", _sah_world(name)), ("sah4", _sah_world(name, builder="sah4"))):
         with capi.Context(0) as c:
             c.set_scene(w.flatten())
             c.set_camera(w.camera_struct())
@@ -200,11 +204,12 @@ def test_gpu_sah_tree_same_image():
             c.reset()
             c.render(passes)
             acc[label] = c.read_accum()
-    a, b = acc["reference"], acc["sah"]
-    assert np.array_equal(a[..., 3], b[..., 3])  # the same paths ended in the same passes
-    close = np.isclose(a[..., :3], b[..., :3], rtol=1e-4, atol=1e-6).all(axis=2)
-    assert close.mean() > 0.999, close.mean()
-    assert abs(a[..., :3].mean() - b[..., :3].mean()) / a[..., :3].mean() < 1e-3
+    for other in ("sah", "sah4"):
+        a, b = acc["reference"], acc[other]
+        assert np.array_equal(a[..., 3], b[..., 3])  # the same paths ended in the same passes
+        close = np.isclose(a[..., :3], b[..., :3], rtol=1e-4, atol=1e-6).all(axis=2)
+        assert close.mean() > 0.999, (other, close.mean())
+        assert abs(a[..., :3].mean() - b[..., :3].mean()) / a[..., :3].mean() < 1e-3
 
 
 # ---------------------------------------------------------------------------------------------- GPU builder (linear BVH)
