@@ -3,22 +3,29 @@
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--workload NAME] [--impl ours|reference]
 
-A *step* is one pass of the hot path over one frame: one path segment per pixel (closest-hit trace, shade + NEE,
-shadow trace), W*H rays -- the reference's own unit (cuda_render_kernel.cu:122-129: ray_count += W*H per pass).
-One JSON line is printed by rank 0:
+Default workload: heightfield_1m_1080p -- the 1M-triangle scene (texture / normal / roughness maps, depth of field) that
+north_star's target is stated on; materials_1080p (BASELINE configs[1]) rides along under "aux".
+A *step* is one pass of the hot path over one frame: one path segment per pixel (closest-hit trace, shade + NEE, ray
+ordering, shadow trace), W*H rays -- the reference's own unit (cuda_render_kernel.cu:122-129: ray_count += W*H per pass).
+Before anything is timed the renderer runs 2 x max-depth untimed passes (pre-roll): the first passes after a reset trace
+only coherent camera rays. One JSON line is printed by rank 0:
   value      Mrays/s, whole job, scene and path state resident in HBM, K passes timed on the device (CUDA events on
              the launching stream), barrier + synchronize on both sides, max over ranks
   e2e        the same metric through the reference-facing boundary with HOST buffers: every e2e step is one
              Engine::renderWorld-equivalent frame = rzb_set_scene (host arrays -> device) + rzb_set_camera + rzb_reset
              + rzb_render(rpp passes) + rzb_resolve (tone map, RGBA8 + depth -> pinned host buffers)
-  roofline   HBM roofline from ALGORITHMIC bytes of both traversal kernels; the one with the larger share of
-             the step is reported at the top level
+  e2e_dropin the reference's OWN headless runner (Application/headless.cpp + json_loader + World, compiled in place) on this
+             engine (rayzath_b200/host/_build/rz_b200_headless), same workload: the rps of its own report.txt
+  roofline   both roofs of the dominant kernel: "issue" (warp instructions per launch from the committed ncu summary /
+             live kernel time against SMs x 4 x SM clock; lane_frac = x active threads per instruction / 32) -- the one
+             that binds -- and the HBM figure from ALGORITHMIC bytes, a throughput normalisation
   cpu_baseline  the reference's own CPU engine (oracle/_ref/rz_ref_tool, built from /root/reference) on this box's
              host cores on a bounded sample of the same workload
+  config     the workload alone, identical in both arms; "run" holds what is specific to this arm (sharding, reduce ...)
 `--impl reference` times that CPU engine alone and prints the same line with "impl": "reference".
 N > 1 (torchrun): sample streams are sharded over the ranks (same frame, disjoint RNG streams, weak scaling), no
-collective while rendering; the accumulators are combined once, inside the timed region, by the fused
-IPC/NVLink sum + tone-map kernel on rank 0 (NCCL reduce with --reduce nccl).
+collective while rendering; the accumulators are combined once, inside the timed region, by the sliced NVLink resolve
+(parallel.SlicedResolve: one kernel per rank, flag barriers in peer memory, no NCCL; NCCL reduce with --reduce nccl).
 """
 import argparse
 import json

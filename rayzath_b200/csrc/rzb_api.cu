@@ -240,6 +240,7 @@ namespace
 		f.cam = makeDeviceCamera(ctx->cam);
 		f.tiles_x = (ctx->cam.width + 15u) / 16u;  // 16x16-pixel chunks of 256 slots
 		f.tiles_y = (ctx->cam.height + 15u) / 16u;
+		f.tiles_x_magic = ((1ull << 40) + f.tiles_x - 1ull) / f.tiles_x;
 		f.n_slots = f.tiles_x * f.tiles_y * 256u;
 		ctx->row_begin = 0;
 		ctx->row_end = ctx->cam.height;
@@ -834,8 +835,9 @@ extern "C" int rzb_set_scene(rzb_ctx* ctx, const rzb_scene* s)
 extern "C" int rzb_set_camera(rzb_ctx* ctx, const rzb_camera* camera)
 {
 	if (!ctx || !camera) return fail(ctx, RZB_ERR_INVALID, "rzb_set_camera: NULL argument");
-	if (camera->width == 0 || camera->height == 0 || uint64_t(camera->width) * camera->height > (1ull << 28))
-		return fail(ctx, RZB_ERR_INVALID, "rzb_set_camera: bad resolution");
+	if (camera->width == 0 || camera->height == 0 || camera->width > 65536u || camera->height > 65536u ||
+		uint64_t(camera->width) * camera->height > (1ull << 28))
+		return fail(ctx, RZB_ERR_INVALID, "rzb_set_camera: bad resolution (1..65536 per side, at most 2^28 pixels)");
 	DeviceGuard guard(ctx->device);
 	RZB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
 	const bool resized = !ctx->has_camera || camera->width != ctx->cam.width || camera->height != ctx->cam.height;

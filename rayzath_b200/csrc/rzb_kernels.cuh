@@ -32,6 +32,7 @@ namespace rzb
 	{
 		DCamera cam;
 		uint32_t tiles_x, tiles_y, n_slots;
+		uint64_t tiles_x_magic;         // ceil(2^40 / tiles_x), see slot_to_pixel
 		uint32_t row_begin, row_end;    // tile split: this context renders image rows [row_begin, row_end)
 		uint32_t slot_begin, slot_end;  // the 256-slot chunks that cover those rows
 		uint32_t il_index, il_count;    // interleaved tile split: only 16-row chunk rows r with r % il_count == il_index
@@ -139,9 +140,12 @@ namespace rzb
 	__device__ __forceinline__ bool slot_to_pixel(const DFrame& f, uint32_t slot, uint32_t& x, uint32_t& y)
 	{
 		const uint32_t chunk = slot >> 8, tile = (slot >> 5) & 7u, within = slot & 31u;
-		x = (chunk % f.tiles_x) * 16u + (tile & 1u) * 8u + (within & 7u);
-		y = (chunk / f.tiles_x) * 16u + (tile >> 1) * 4u + (within >> 3);
-		return x < f.cam.width && y >= f.row_begin && y < f.row_end && (chunk / f.tiles_x) % f.il_count == f.il_index;
+		// chunk / tiles_x by a multiplication (tiles_x_magic = ceil(2^40 / tiles_x): exact while chunk * tiles_x < 2^40):
+		// ncu showed the emulated integer divisions of this function among the top stall sites of k_shade
+		const uint32_t cy = uint32_t((uint64_t(chunk) * f.tiles_x_magic) >> 40), cx = chunk - cy * f.tiles_x;
+		x = cx * 16u + (tile & 1u) * 8u + (within & 7u);
+		y = cy * 16u + (tile >> 1) * 4u + (within >> 3);
+		return x < f.cam.width && y >= f.row_begin && y < f.row_end && (f.il_count == 1u || cy % f.il_count == f.il_index);
 	}
 
 	__device__ __forceinline__ Stack make_stack(uint2* smem_base)
