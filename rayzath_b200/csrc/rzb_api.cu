@@ -946,6 +946,8 @@ extern "C" int rzb_render(rzb_ctx* ctx, uint32_t passes)
 	f.max_depth = ctx->cfg.max_depth;
 	f.direct_samples = ctx->cfg.direct_light_samples;
 	f.spot_samples = ctx->cfg.spot_light_samples;
+	f.inv_pdf_direct = f.direct_samples ? float(ctx->sc.direct_light_count) / float(f.direct_samples) : 0.0f;
+	f.inv_pdf_spot = f.spot_samples ? float(ctx->sc.spot_light_count) / float(f.spot_samples) : 0.0f;
 	f.seed = ctx->cfg.seed;
 	const bool lights = (ctx->sc.direct_light_count && f.direct_samples) || (ctx->sc.spot_light_count && f.spot_samples);
 	const bool count = (ctx->cfg.flags & RZB_FLAG_COUNT_WORK) != 0u;

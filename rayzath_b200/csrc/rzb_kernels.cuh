@@ -58,6 +58,7 @@ namespace rzb
 		float reproject_blend; // 0 = off
 
 		uint32_t max_depth, direct_samples, spot_samples;
+		float inv_pdf_direct, inv_pdf_spot; // light count / samples
 		uint64_t seed;
 		// ray ordering: k_shade bins the next pass's rays and the shadow rays it queues (one atomic each: bin counter ->
 		// rank inside the bin); after a prefix sum over the bins k_scatter_order writes slot / queue indices in bin
@@ -601,7 +602,7 @@ namespace rzb
 				const uint32_t pixel = y * f.cam.width + x;
 				if (do_direct)
 				{
-					const float inv_pdf = float(sc.direct_light_count) / float(f.direct_samples);
+					const float inv_pdf = f.inv_pdf_direct; // float(direct_light_count) / float(direct_samples), divided on the host
 					for (uint32_t i = 0; i < f.direct_samples; ++i)
 					{
 						const uint32_t li = min(uint32_t(rng.next() * float(sc.direct_light_count)), sc.direct_light_count - 1u);
@@ -631,7 +632,7 @@ namespace rzb
 				}
 				if (do_spot)
 				{
-					const float inv_pdf = float(sc.spot_light_count) / float(f.spot_samples);
+					const float inv_pdf = f.inv_pdf_spot;
 					const float med_scattering = sc.materials[medium].scattering;
 					for (uint32_t i = 0; i < f.spot_samples; ++i)
 					{

@@ -75,6 +75,7 @@ namespace rzb
 		switch (mode)
 		{
 			case RZB_ADDRESS_WRAP:
+				if (unsigned(i) < unsigned(n)) return i; // the common case without the emulated integer division
 				i %= n;
 				return i < 0 ? i + n : i;
 			case RZB_ADDRESS_MIRROR:
@@ -119,8 +120,11 @@ namespace rzb
 		if (m.filter == RZB_FILTER_POINT && m.address == RZB_ADDRESS_WRAP)
 		{
 			// the CPU engine's only mode (render_parts.hpp:215-220)
-			const float x = fmodf(fmodf(u, 1.0f) + 1.0f, 1.0f);
-			const float y = 1.0f - fmodf(fmodf(v, 1.0f) + 1.0f, 1.0f);
+			// fmodf(a, 1) == a - truncf(a) exactly (the difference is representable): same values as the CPU engine's
+			// fmodf chain without libdevice's iterative fmodf (ncu: 9 % of k_shade's instructions)
+			const float fu = u - truncf(u) + 1.0f, fv = v - truncf(v) + 1.0f;
+			const float x = fu - truncf(fu);
+			const float y = 1.0f - (fv - truncf(fv));
 			const int px = min(int(x * float(m.width)), int(m.width) - 1);
 			const int py = min(int(y * float(m.height)), int(m.height) - 1);
 			return load_texel(m, max(px, 0), max(py, 0));

@@ -101,6 +101,39 @@ namespace rzb
 		return !(tmax < near_ || tmin > tmax || tmin > far_);
 	}
 
+	// The two boxes of a sibling pair with ONE error-bound check (decision-exact mode): the approximate entry / exit
+	// distances of both boxes are formed first, then the smallest of the six compared gaps is set against the bound of the
+	// largest magnitude -- more cautious than checking each box on its own (a few more exact fallbacks, never a wrong
+	// decision), and 4 instructions per pair cheaper (ncu: the per-box check was 11 % of k_trace_paths' instructions).
+	__device__ __forceinline__ void slab_pair_exact(const float4 a0, const float4 a1, const float4 b0, const float4 b1, const V3& o,
+		const V3& d, const V3& rcp, const float near_, const float far_, const float margin, bool& ha, bool& hb, float& tma, float& tmb)
+	{
+		float tmin[2], tmax[2];
+#pragma unroll
+		for (int k = 0; k < 2; ++k)
+		{
+			const float4 n0 = k ? b0 : a0, n1 = k ? b1 : a1;
+			const float t1 = fmul(fsub(n0.x, o.x), rcp.x), t2 = fmul(fsub(n0.w, o.x), rcp.x);
+			const float t3 = fmul(fsub(n0.y, o.y), rcp.y), t4 = fmul(fsub(n1.x, o.y), rcp.y);
+			const float t5 = fmul(fsub(n0.z, o.z), rcp.z), t6 = fmul(fsub(n1.y, o.z), rcp.z);
+			tmin[k] = fmaxf(fmaxf(fminf(t1, t2), fminf(t3, t4)), fminf(t5, t6));
+			tmax[k] = fminf(fminf(fmaxf(t1, t2), fmaxf(t3, t4)), fmaxf(t5, t6));
+		}
+		const float gap = fminf(fminf(fminf(fabsf(tmax[0] - near_), fabsf(tmin[0] - tmax[0])), fabsf(tmin[0] - far_)),
+			fminf(fminf(fabsf(tmax[1] - near_), fabsf(tmin[1] - tmax[1])), fabsf(tmin[1] - far_)));
+		const float mag = fmaxf(fmaxf(fabsf(tmin[0]), fabsf(tmax[0])), fmaxf(fabsf(tmin[1]), fabsf(tmax[1])));
+		const float bound = margin * fmaxf(fminf(mag, 1.0e30f), 1.0e-30f);
+		tma = tmin[0]; tmb = tmin[1];
+		if (gap <= bound)
+		{
+			ha = slab_exact(a0, a1, o, d, near_, far_, tma) == 3u;
+			hb = slab_exact(b0, b1, o, d, near_, far_, tmb) == 3u;
+			return;
+		}
+		ha = !(tmax[0] < near_ || tmin[0] > tmax[0] || tmin[0] > far_);
+		hb = !(tmax[1] < near_ || tmin[1] > tmax[1] || tmin[1] > far_);
+	}
+
 	struct RayResult
 	{
 		// closest hit
@@ -250,8 +283,13 @@ namespace rzb
 				const float4 p0 = __ldg(pair), p1 = __ldg(pair + 1), p2 = __ldg(pair + 2), p3 = __ldg(pair + 3);
 				if (STATS) { if (t.in_mesh) cnt.mesh_nodes += 2; else cnt.top_nodes += 2; t.steps++; }
 				float tm0, tm1;
-				const bool h0 = slab_hit<FAST>(p0, p1, t.o, t.d, t.rcp, t.near_, t.far_, t.margin, tm0);
-				const bool h1 = slab_hit<FAST>(p2, p3, t.o, t.d, t.rcp, t.near_, t.far_, t.margin, tm1);
+				bool h0, h1;
+				if (FAST)
+				{
+					h0 = slab_hit<true>(p0, p1, t.o, t.d, t.rcp, t.near_, t.far_, t.margin, tm0);
+					h1 = slab_hit<true>(p2, p3, t.o, t.d, t.rcp, t.near_, t.far_, t.margin, tm1);
+				}
+				else slab_pair_exact(p0, p1, p2, p3, t.o, t.d, t.rcp, t.near_, t.far_, t.margin, h0, h1, tm0, tm1);
 				// near child first: `flip` = the second child is the near one
 				// own trees (FAST): nearer entry first; reference trees: by ray sign on the split axis, as the reference does
 				// any hit: the result does not depend on the order; RZB_FLAG_X_ANYHIT_NEAR_FIRST (experiment switch, set by the
