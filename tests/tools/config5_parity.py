@@ -149,7 +149,7 @@ def main():
             res["rel_rmse_pixel_equal_passes_vs_refmean"] <= 1.15 * k_noise * res["rel_rmse_pixel_ref_a_vs_b"] + 0.005 and
             res["rel_rmse_block8_equal_passes_vs_refmean"] <= 1.15 * k_noise * res["rel_rmse_block8_ref_a_vs_b"] + 0.005 and
             res["rel_rmse_block32_equal_passes_vs_refmean"] <= 1.15 * k_noise * res["rel_rmse_block32_ref_a_vs_b"] + 0.005)
-        res["tolerance"] = ("equal passes (same finite-pass bias on both sides): mean within 1 %; per-pixel, block-8 and block-32 "
+        res["tolerance"] = ("equal passes (same finite-pass bias on both sides): mean within 1 %%; per-pixel, block-8 and block-32 "
                             "relRMSE of the mean of %d GPU renders vs the mean of the two reference renders <= 1.15 x %.3f x "
                             "(reference A-vs-B) + 0.005" % (world, k_noise))
         print(json.dumps(res), flush=True)
