@@ -134,6 +134,8 @@ struct rzb_ctx
 	// (rzb_traverse_mr.cuh, RZB200_TRACE=mr: measured slower on B200, DESIGN.md section 4 -- kept as the measured
 	// alternative; RZB200_MR_RAYS = rays per lane, RZB200_MR_BLOCKS caps its resident blocks per SM)
 	bool trace_mr = false;
+	bool trace_refill = false;     // RZB200_TRACE=refill: lane refill at a threshold (experiment)
+	uint32_t refill_thresh = 16, refill_slice = 8;
 	bool trace_sync = false;       // RZB200_TRACE_SYNC=1: warp-synchronised rounds in the closest-hit kernel (experiment)
 	int mr_blocks = 0, mr_k = 2, mr_steps = 2;
 	int mr_grid[2] = {0, 0};       // [FAST]
@@ -370,8 +372,9 @@ extern "C" int rzb_create(int device, rzb_ctx** out)
 	cudaEventCreate(&ctx->ev_end);
 	cudaEventCreateWithFlags(&ctx->ev_resolve[0], cudaEventDisableTiming);
 	cudaEventCreateWithFlags(&ctx->ev_resolve[1], cudaEventDisableTiming);
-	if (cudaMallocHost(reinterpret_cast<void**>(&ctx->h_pick), 16) != cudaSuccess) ctx->h_pick = nullptr;
-	else std::memset(ctx->h_pick, 0, 16);
+	// pinned: [0..1] / [2..3] ray-cast pick of the two asynchronous-resolve slots, [4] "a peer never arrived" of the sliced resolve
+	if (cudaMallocHost(reinterpret_cast<void**>(&ctx->h_pick), 32) != cudaSuccess) ctx->h_pick = nullptr;
+	else std::memset(ctx->h_pick, 0, 32);
 	if ((e = cudaMalloc(reinterpret_cast<void**>(&ctx->d_work), 128)) != cudaSuccess) { delete ctx; return cudaFail(nullptr, e, "cudaMalloc(work)"); }
 	cudaMemsetAsync(ctx->d_work, 0, 128, ctx->stream);
 	if ((e = cudaMalloc(reinterpret_cast<void**>(&ctx->d_counters), 256)) != cudaSuccess) { delete ctx; return cudaFail(nullptr, e, "cudaMalloc(counters)"); }
@@ -380,6 +383,9 @@ extern "C" int rzb_create(int device, rzb_ctx** out)
 	if (const char* env = std::getenv("RZB200_CARVEOUT")) ctx->set_carveout = std::atoi(env) != 0;
 	if (const char* env = std::getenv("RZB200_TRACE")) ctx->trace_mr = std::string(env) == "mr";
 	if (const char* env = std::getenv("RZB200_TRACE_SYNC")) ctx->trace_sync = std::atoi(env) != 0;
+	if (const char* env = std::getenv("RZB200_TRACE")) ctx->trace_refill = std::string(env) == "refill";
+	if (const char* env = std::getenv("RZB200_REFILL_THRESH")) ctx->refill_thresh = uint32_t(std::min(std::max(std::atoi(env), 1), 32));
+	if (const char* env = std::getenv("RZB200_REFILL_SLICE")) ctx->refill_slice = uint32_t(std::max(std::atoi(env), 1));
 	if (const char* env = std::getenv("RZB200_MR_BLOCKS")) ctx->mr_blocks = std::atoi(env);
 	if (const char* env = std::getenv("RZB200_SORT")) ctx->sort_enabled = std::atoi(env) != 0;
 	if (const char* env = std::getenv("RZB200_SORT_BITS")) ctx->sort_bits = uint32_t(std::min(std::max(std::atoi(env), 1), 6));
@@ -1026,6 +1032,11 @@ extern "C" int rzb_render(rzb_ctx* ctx, uint32_t passes)
 			const MrPathKernel kernel = reinterpret_cast<MrPathKernel>(const_cast<void*>(mrPathKernel(ctx->mr_k, ctx->mr_steps, count, fast)));
 			kernel<<<ctx->mr_grid[fast ? 1 : 0], kMrBlock, ctx->mr_smem, ctx->stream>>>(ctx->sc, f);
 		}
+		else if (ctx->trace_refill && !count)
+		{
+			if (fast) k_trace_paths_refill<true><<<ctx->trace_grid_fast, kTraceBlock, 0, ctx->stream>>>(ctx->sc, f, ctx->refill_thresh, ctx->refill_slice);
+			else k_trace_paths_refill<false><<<ctx->trace_grid, kTraceBlock, 0, ctx->stream>>>(ctx->sc, f, ctx->refill_thresh, ctx->refill_slice);
+		}
 		else if (ctx->trace_sync && !count) { if (fast) k_trace_paths<false, true, true><<<ctx->trace_grid_fast, kTraceBlock, 0, ctx->stream>>>(ctx->sc, f); else k_trace_paths<false, false, true><<<ctx->trace_grid, kTraceBlock, 0, ctx->stream>>>(ctx->sc, f); }
 		else if (count) { if (fast) k_trace_paths<true, true><<<ctx->trace_grid_fast, kTraceBlock, 0, ctx->stream>>>(ctx->sc, f); else k_trace_paths<true, false><<<ctx->trace_grid, kTraceBlock, 0, ctx->stream>>>(ctx->sc, f); }
 		else { if (fast) k_trace_paths<false, true><<<ctx->trace_grid_fast, kTraceBlock, 0, ctx->stream>>>(ctx->sc, f); else k_trace_paths<false, false><<<ctx->trace_grid, kTraceBlock, 0, ctx->stream>>>(ctx->sc, f); }
@@ -1451,7 +1462,7 @@ extern "C" int rzb_resolve_sliced(rzb_ctx* ctx, uint32_t rank, uint32_t world, c
 	}
 	// completion + "a peer never arrived" travel through slot 0 of the asynchronous-resolve protocol
 	if (ctx->h_pick)
-		RZB_CUDA(ctx, cudaMemcpyAsync(ctx->h_pick + 3, &static_cast<ExchangeHeader*>(ctx->d_exchange)->timed_out, 4, cudaMemcpyDeviceToHost, ctx->stream));
+		RZB_CUDA(ctx, cudaMemcpyAsync(ctx->h_pick + 4, &static_cast<ExchangeHeader*>(ctx->d_exchange)->timed_out, 4, cudaMemcpyDeviceToHost, ctx->stream));
 	RZB_CUDA(ctx, cudaEventRecord(ctx->ev_resolve[0], ctx->stream));
 	return RZB_OK;
 }
@@ -1468,7 +1479,7 @@ extern "C" int rzb_resolve_sliced_wait(rzb_ctx* ctx, float* exchange_ms_or_null)
 		cudaGetLastError();
 	}
 	if (exchange_ms_or_null) *exchange_ms_or_null = ctx->last_exchange_ms;
-	if (ctx->h_pick && ctx->h_pick[3] != 0u)
+	if (ctx->h_pick && ctx->h_pick[4] != 0u)
 		return fail(ctx, RZB_ERR_STATE, "rzb_resolve_sliced: a peer rank never reached the exchange step (spin limit hit); the frame is incomplete");
 	return RZB_OK;
 }

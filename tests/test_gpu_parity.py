@@ -726,3 +726,130 @@ def test_multi_ray_lane_kernels_bit_exact(rays_per_lane, golden, flats, monkeypa
     a = render()
     monkeypatch.setenv("RZB200_TRACE", "lane")
     assert np.array_equal(a, render())
+
+
+# ------------------------------------------------------------------ round-2 additions: ordering, validation, spp
+def test_ray_ordering_does_not_change_the_result(monkeypatch):
+    """The order pass (bin sort between passes, default on) only changes WHICH rays share a warp: on a scene without
+    lights (no atomic adds) the accumulator is bit-identical with RZB200_SORT=0, with other bin resolutions and with the
+    batches handed out front to back."""
+    w = GOLDEN_SCENES["cornell"]()
+    flat, cam = w.flatten(), w.camera_struct()
+
+    def render():
+        with capi.Context(0) as c:
+            c.set_scene(flat)
+            c.set_camera(cam)
+            c.set_config(max_depth=8, seed=19)
+            c.reset()
+            c.render(24)
+            return c.read_accum()
+
+    ordered = render()
+    for env in ({"RZB200_SORT": "0"}, {"RZB200_SORT_BITS": "3", "RZB200_SORT_DIRBITS": "0"}, {"RZB200_SORT_REVERSE": "0"},
+                {"RZB200_TRACE": "refill", "RZB200_REFILL_THRESH": "12", "RZB200_REFILL_SLICE": "4"}):
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        assert np.array_equal(ordered, render()), env
+        for k in env:
+            monkeypatch.delenv(k)
+    # with lights the shadow kernel's atomic adds arrive in another order: equal up to float summation order
+    w2 = GOLDEN_SCENES["materials"]()
+    with capi.Context(0) as c:
+        c.set_scene(w2.flatten())
+        c.set_camera(w2.camera_struct())
+        c.set_config(max_depth=8, seed=19)
+        c.reset()
+        c.render(24)
+        a = c.read_accum()
+    monkeypatch.setenv("RZB200_SORT", "0")
+    with capi.Context(0) as c:
+        c.set_scene(w2.flatten())
+        c.set_camera(w2.camera_struct())
+        c.set_config(max_depth=8, seed=19)
+        c.reset()
+        c.render(24)
+        b = c.read_accum()
+    assert np.array_equal(a[..., 3], b[..., 3])
+    assert np.allclose(a, b, rtol=1e-4, atol=1e-5)
+
+
+def test_mean_samples_is_the_mean_alpha(contexts):
+    c = contexts["materials"]
+    c.set_config(max_depth=6, seed=2)
+    c.reset()
+    c.render(20)
+    acc = c.read_accum()
+    assert abs(c.mean_samples() - float(acc[..., 3].mean(dtype=np.float64))) < 1e-6 * max(1.0, float(acc[..., 3].mean()))
+    c.set_config()
+
+
+def test_set_scene_rejects_trees_the_traversal_cannot_walk(flats):
+    """caller-supplied trees are walked on the host before the upload -- a cycle, a shared subtree, a child index
+    at an even position or a tree deeper than the traversal stack would hang or corrupt the device walk, so they are
+    refused with RZB_ERR_INVALID; an instance-less world and a mesh without triangles are fine."""
+    base = flats["materials"]
+
+    def attempt(mutate):
+        s = {k: np.array(v, copy=True) for k, v in base.items()}
+        mutate(s)
+        with capi.Context(0) as c:
+            c.set_scene(s)
+
+    m0 = base["meshes"][0]
+    off = int(m0["node_offset"])
+    inner = [i for i in range(int(m0["node_count"])) if (int(base["mesh_nodes"][off + i]["type_count"]) & 0x3FFFFFFF) == 0]
+    assert inner
+
+    def cycle(s):
+        s["mesh_nodes"][off + inner[-1]]["begin"] = 1  # a deep inner node points back at the root's children
+
+    def even_child(s):
+        s["mesh_nodes"][off + inner[0]]["begin"] = 2
+
+    def top_cycle(s):
+        n = s["instance_nodes"]
+        k = [i for i in range(n.shape[0]) if (int(n[i]["type_count"]) & 0x3FFFFFFF) == 0]
+        if k:
+            n[k[-1]]["begin"] = 1
+
+    for bad in (cycle, even_child):
+        with pytest.raises(capi.RzbError) as e:
+            attempt(bad)
+        assert e.value.code == 1  # RZB_ERR_INVALID
+    n_top_inner = sum(1 for i in range(base["instance_nodes"].shape[0]) if (int(base["instance_nodes"][i]["type_count"]) & 0x3FFFFFFF) == 0)
+    if n_top_inner > 1:
+        with pytest.raises(capi.RzbError):
+            attempt(top_cycle)
+    # a chain deeper than the stack: 80 inner levels, every second child a one-triangle leaf
+    depth = 80
+    nodes = np.zeros(2 * depth + 1, dtype=capi.node_dtype)
+    for lvl in range(depth):
+        i = 0 if lvl == 0 else 2 * lvl - 1
+        nodes[i]["begin"] = 2 * lvl + 1
+        nodes[i]["type_count"] = 0
+        nodes[2 * lvl + 2]["begin"] = 0
+        nodes[2 * lvl + 2]["type_count"] = 1
+    nodes[2 * depth - 1]["begin"] = 0
+    nodes[2 * depth - 1]["type_count"] = 1
+    nodes["bb_min"][:] = -1.0
+    nodes["bb_max"][:] = 1.0
+
+    def deep(s):
+        s["mesh_nodes"] = nodes
+        s["meshes"] = np.array([(0, nodes.shape[0], 0, 1)], dtype=capi.mesh_dtype)
+        s["triangles"] = s["triangles"][:1]
+        s["tri_host_index"] = s["tri_host_index"][:1]
+        inst = s["instances"].copy()
+        inst["mesh"] = 0
+        s["instances"] = inst
+
+    with pytest.raises(capi.RzbError) as e:
+        attempt(deep)
+    assert "deep" in str(e.value)
+    # no instances at all: accepted, every ray misses
+    def empty(s):
+        s["instances"] = s["instances"][:0]
+        s["instance_nodes"] = s["instance_nodes"][:0]
+        s["instance_materials"] = s["instance_materials"][:0]
+    attempt(empty)
