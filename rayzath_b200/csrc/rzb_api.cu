@@ -134,8 +134,6 @@ struct rzb_ctx
 	// (rzb_traverse_mr.cuh, RZB200_TRACE=mr: measured slower on B200, DESIGN.md section 4 -- kept as the measured
 	// alternative; RZB200_MR_RAYS = rays per lane, RZB200_MR_BLOCKS caps its resident blocks per SM)
 	bool trace_mr = false;
-	bool trace_refill = false;     // RZB200_TRACE=refill: lane refill at a threshold (experiment)
-	uint32_t refill_thresh = 16, refill_slice = 8;
 	bool trace_sync = false;       // RZB200_TRACE_SYNC=1: warp-synchronised rounds in the closest-hit kernel (experiment)
 	int mr_blocks = 0, mr_k = 2, mr_steps = 2;
 	int mr_grid[2] = {0, 0};       // [FAST]
@@ -383,9 +381,6 @@ extern "C" int rzb_create(int device, rzb_ctx** out)
 	if (const char* env = std::getenv("RZB200_CARVEOUT")) ctx->set_carveout = std::atoi(env) != 0;
 	if (const char* env = std::getenv("RZB200_TRACE")) ctx->trace_mr = std::string(env) == "mr";
 	if (const char* env = std::getenv("RZB200_TRACE_SYNC")) ctx->trace_sync = std::atoi(env) != 0;
-	if (const char* env = std::getenv("RZB200_TRACE")) ctx->trace_refill = std::string(env) == "refill";
-	if (const char* env = std::getenv("RZB200_REFILL_THRESH")) ctx->refill_thresh = uint32_t(std::min(std::max(std::atoi(env), 1), 32));
-	if (const char* env = std::getenv("RZB200_REFILL_SLICE")) ctx->refill_slice = uint32_t(std::max(std::atoi(env), 1));
 	if (const char* env = std::getenv("RZB200_MR_BLOCKS")) ctx->mr_blocks = std::atoi(env);
 	if (const char* env = std::getenv("RZB200_SORT")) ctx->sort_enabled = std::atoi(env) != 0;
 	if (const char* env = std::getenv("RZB200_SORT_BITS")) ctx->sort_bits = uint32_t(std::min(std::max(std::atoi(env), 1), 6));
@@ -1031,11 +1026,6 @@ extern "C" int rzb_render(rzb_ctx* ctx, uint32_t passes)
 		{
 			const MrPathKernel kernel = reinterpret_cast<MrPathKernel>(const_cast<void*>(mrPathKernel(ctx->mr_k, ctx->mr_steps, count, fast)));
 			kernel<<<ctx->mr_grid[fast ? 1 : 0], kMrBlock, ctx->mr_smem, ctx->stream>>>(ctx->sc, f);
-		}
-		else if (ctx->trace_refill && !count)
-		{
-			if (fast) k_trace_paths_refill<true><<<ctx->trace_grid_fast, kTraceBlock, 0, ctx->stream>>>(ctx->sc, f, ctx->refill_thresh, ctx->refill_slice);
-			else k_trace_paths_refill<false><<<ctx->trace_grid, kTraceBlock, 0, ctx->stream>>>(ctx->sc, f, ctx->refill_thresh, ctx->refill_slice);
 		}
 		else if (ctx->trace_sync && !count) { if (fast) k_trace_paths<false, true, true><<<ctx->trace_grid_fast, kTraceBlock, 0, ctx->stream>>>(ctx->sc, f); else k_trace_paths<false, false, true><<<ctx->trace_grid, kTraceBlock, 0, ctx->stream>>>(ctx->sc, f); }
 		else if (count) { if (fast) k_trace_paths<true, true><<<ctx->trace_grid_fast, kTraceBlock, 0, ctx->stream>>>(ctx->sc, f); else k_trace_paths<true, false><<<ctx->trace_grid, kTraceBlock, 0, ctx->stream>>>(ctx->sc, f); }

@@ -320,91 +320,6 @@ namespace rzb
 		if (STATS) flush_counters(cnt, f.work);
 	}
 
-	// ---------------------------------------------------------------- closest hit with lane refill (experiment, RZB200_TRACE=refill)
-	// Whole-warp batches leave lanes idle while the longest ray of the batch finishes (bench.py batch_lane_utilisation:
-	// 0.59 on ordered rays). Here finished lanes wait only until `thresh` of them are idle; then they write their records and
-	// pull new rays together (one atomic, start-up code at >= thresh lanes). Between two such points every lane runs up to
-	// `slice` rounds on its own. Same per-ray operation sequence as k_trace_paths (records bit-exact).
-	template <bool FAST>
-	__global__ void __launch_bounds__(kTraceBlock, FAST ? 8 : 6) k_trace_paths_refill(DScene sc, DFrame f, uint32_t thresh, uint32_t slice)
-	{
-		__shared__ uint2 smem_stack[kSmemStack * kTraceBlock];
-		__shared__ ParkedRay smem_park[kTraceBlock];
-		Stack st = make_stack(smem_stack);
-		ParkedRay& park = smem_park[threadIdx.x];
-		TraceCounters cnt{0u, 0u, 0u, 0u};
-		const uint32_t lane = threadIdx.x & 31u;
-		const uint32_t n = f.slot_end - f.slot_begin;
-		Trav t;
-		t.alive = false;
-		bool have = false; // this lane holds a ray (alive or finished and not yet written)
-		uint32_t slot = 0u, flags = 0u;
-		float near_in = 0.0f, far_in = 0.0f;
-		bool work_left = true;
-		for (;;)
-		{
-			const uint32_t idle = __ballot_sync(0xFFFFFFFFu, !t.alive);
-			if (idle == 0xFFFFFFFFu || (work_left && uint32_t(__popc(idle)) >= thresh))
-			{
-				// finished rays: write the records
-				if (!t.alive && have)
-				{
-					RayResult r;
-					trav_end(t, true, near_in, far_in, park, r);
-					uint32_t tri_bits = flags | (r.external ? kHitExternalBit : 0u);
-					tri_bits |= (r.tri == kNoIndex) ? kHitTriMask : (r.tri & kHitTriMask);
-					f.hit_a[slot] = make_float4(r.t, r.b1, r.b2, __uint_as_float(tri_bits));
-					f.hit_inst[slot] = r.inst;
-					have = false;
-				}
-				if (!work_left && idle == 0xFFFFFFFFu) break;
-				if (work_left)
-				{
-					uint32_t base = 0u;
-					const uint32_t leader = __ffs(idle) - 1u;
-					if (lane == leader) base = atomicAdd(&f.counters[0], uint32_t(__popc(idle)));
-					base = __shfl_sync(0xFFFFFFFFu, base, leader);
-					if (base + uint32_t(__popc(idle)) >= n) work_left = false;
-					if (!t.alive)
-					{
-						uint32_t idx = base + __popc(idle & ((1u << lane) - 1u));
-						bool active = idx < n;
-						uint32_t x, y;
-						if (active)
-						{
-							// the ordered batches are handed out back to front (long walks first)
-							if (f.order != nullptr && f.order_reversed) idx = n - 1u - idx;
-							slot = f.order != nullptr ? f.order[idx] : f.slot_begin + idx;
-							active = slot_to_pixel(f, slot, x, y);
-						}
-						if (active)
-						{
-							const float4 so = f.st_o[slot], sd = f.st_d[slot];
-							const uint32_t bits = __float_as_uint(so.w);
-							const uint32_t depth = bits & 0xFFu, medium = bits >> kMediumShift;
-							near_in = 0.0f; far_in = kFltMax;
-							if (depth == 0u) { near_in = f.cam.near_; far_in = f.cam.far_; }
-							flags = 0u;
-							if (!(sc.flags & RZB_FLAG_CPU_SEMANTICS))
-							{
-								const float sigma = sc.materials[medium].scattering;
-								if (sigma > 1.0e-4f)
-								{
-									Rng rng(f.seed, slot, f.pass_index);
-									const float dist = (-__logf(rng.next() + 1.0e-4f)) / sigma;
-									if (dist < far_in) { far_in = dist; flags |= kHitScatterBit; }
-								}
-							}
-							trav_begin<false, false, FAST>(sc, t, true, v3(so.x, so.y, so.z), v3(sd.x, sd.y, sd.z), near_in, far_in, st, park, cnt);
-							have = true;
-						}
-					}
-				}
-			}
-			for (uint32_t r = 0; r < slice && t.alive; ++r) trav_round<false, false, FAST>(sc, t, st, park, cnt);
-		}
-	}
-
 	// ---------------------------------------------------------------- multi-ray-per-lane closest hit (rzb_traverse_mr.cuh)
 	// The warp loop shared by k_trace_paths_mr and k_trace_rays_mr. `Source` hands out work items and takes results:
 	//   uint32_t total() const; uint32_t* counter() const;

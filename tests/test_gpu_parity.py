@@ -746,8 +746,7 @@ def test_ray_ordering_does_not_change_the_result(monkeypatch):
             return c.read_accum()
 
     ordered = render()
-    for env in ({"RZB200_SORT": "0"}, {"RZB200_SORT_BITS": "3", "RZB200_SORT_DIRBITS": "0"}, {"RZB200_SORT_REVERSE": "0"},
-                {"RZB200_TRACE": "refill", "RZB200_REFILL_THRESH": "12", "RZB200_REFILL_SLICE": "4"}):
+    for env in ({"RZB200_SORT": "0"}, {"RZB200_SORT_BITS": "3", "RZB200_SORT_DIRBITS": "0"}, {"RZB200_SORT_REVERSE": "0"}):
         for k, v in env.items():
             monkeypatch.setenv(k, v)
         assert np.array_equal(ordered, render()), env
