@@ -6,6 +6,8 @@
 #include "rzb_kernels.cuh"
 #include "rzb_wide.hpp"
 
+#include <nvtx3/nvToolsExt.h> // header-only; ranges cost nothing unless a tool (nsys, ncu --nvtx) is attached
+
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
@@ -142,6 +144,13 @@ struct rzb_ctx
 
 namespace
 {
+	// NVTX range over one C-ABI call (the reference has wall-clock stage timers only)
+	struct NvtxRange
+	{
+		explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+		~NvtxRange() { nvtxRangePop(); }
+	};
+
 	int fail(rzb_ctx* ctx, int code, const std::string& msg)
 	{
 		if (ctx) ctx->error = msg;
@@ -539,6 +548,7 @@ namespace
 extern "C" int rzb_set_scene(rzb_ctx* ctx, const rzb_scene* s)
 {
 	if (!ctx || !s) return fail(ctx, RZB_ERR_INVALID, "rzb_set_scene: NULL argument");
+	NvtxRange nvtx("rzb_set_scene");
 	DeviceGuard guard(ctx->device);
 	RZB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
 	ctx->has_scene = false;
@@ -933,6 +943,7 @@ extern "C" int rzb_render(rzb_ctx* ctx, uint32_t passes)
 {
 	if (!ctx) return RZB_ERR_INVALID;
 	if (!ctx->has_scene || !ctx->has_camera) return fail(ctx, RZB_ERR_STATE, "rzb_render: scene and camera must be set first");
+	NvtxRange nvtx("rzb_render");
 	DeviceGuard guard(ctx->device);
 	if (!ctx->frame_ready)
 	{
@@ -1102,6 +1113,7 @@ namespace
 {
 	int tonemapAndCopy(rzb_ctx* ctx, const PeerList& peers, uint8_t* rgba8, float* depth, bool sync = true)
 	{
+		NvtxRange nvtx("rzb_resolve");
 		const uint32_t n = ctx->cam.width * ctx->cam.height;
 		if (rgba8)
 		{
