@@ -551,6 +551,12 @@ extern "C" int rzb_set_scene(rzb_ctx* ctx, const rzb_scene* s)
 	NvtxRange nvtx("rzb_set_scene");
 	DeviceGuard guard(ctx->device);
 	RZB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+	struct InFlight
+	{
+		rzb_ctx* ctx;
+		bool armed = false;
+		~InFlight() { if (armed) cudaStreamSynchronize(ctx->stream); }
+	} in_flight{ctx};
 	ctx->has_scene = false;
 	ctx->frame_ready = false;
 
@@ -573,9 +579,43 @@ extern "C" int rzb_set_scene(rzb_ctx* ctx, const rzb_scene* s)
 	if (s->instance_count != 0 && s->instance_node_count == 0)
 		return fail(ctx, RZB_ERR_INVALID, "rzb_set_scene: instances without an instance tree");
 
+	// (materials and maps first: the map pixels are the second largest upload and need only the checks below, so their
+	// copies run while the host walks the trees further down; `in_flight` waits for them on every way out)
+	// ---- materials (+ world material appended), maps
+	std::vector<rzb_material> mats(s->materials, s->materials + s->material_count);
+	mats.push_back(s->world_material);
+	for (const rzb_material& m : mats)
+	{
+		const uint32_t ids[5] = {m.texture, m.normal_map, m.metalness_map, m.roughness_map, m.emission_map};
+		for (uint32_t id : ids)
+			if (id != RZB_NO_INDEX && id >= s->map_count) return fail(ctx, RZB_ERR_INVALID, "rzb_set_scene: map id out of range");
+	}
+	if (ctx->map_pixel_buf.size() < s->map_count) ctx->map_pixel_buf.resize(s->map_count);
+	std::vector<DMap> maps(s->map_count);
+	int rc;
+	in_flight.armed = true;
+	for (uint32_t i = 0; i < s->map_count; ++i)
+	{
+		const rzb_map& m = s->maps[i];
+		if (!m.pixels || m.width == 0 || m.height == 0 || m.format > RZB_MAP_R32F)
+			return fail(ctx, RZB_ERR_INVALID, "rzb_set_scene: bad map");
+		const size_t texel = m.format == RZB_MAP_R8 ? 1 : 4;
+		const uint8_t* d_pixels = nullptr;
+		if ((rc = uploadTo(ctx, ctx->map_pixel_buf[i], static_cast<const uint8_t*>(m.pixels), size_t(m.width) * m.height * texel, &d_pixels))) return rc;
+		DMap d{};
+		d.pixels = d_pixels;
+		d.width = m.width; d.height = m.height;
+		d.format = m.format; d.filter = m.filter; d.address = m.address;
+		d.scale_x = m.scale[0]; d.scale_y = m.scale[1];
+		d.rot_sin = sinf(m.rotation); d.rot_cos = cosf(m.rotation);
+		d.trans_x = m.translation[0]; d.trans_y = m.translation[1];
+		maps[i] = d;
+	}
+
 	// ---- node placement: every tree is placed so that its root sits at an odd global index; sibling pairs (odd
 	// local index, next even) then start at even global indices = 64-byte aligned
 	std::vector<WideNode> wide_nodes; // RZB_SCENE_WIDE_TREES: the collapsed mesh trees of a full upload
+	const rzb_node* d_mesh_nodes_raw = nullptr;
 	std::vector<MeshEntry> table; // non-empty meshes only, ascending node_offset
 	std::vector<uint32_t> mesh_base(mesh_count, kNoIndex);
 	uint32_t top_base = 0;
@@ -619,6 +659,26 @@ extern "C" int rzb_set_scene(rzb_ctx* ctx, const rzb_scene* s)
 		cursor += top_capacity;
 		if (cursor >= (1u << 30)) return fail(ctx, RZB_ERR_INVALID, "rzb_set_scene: too many nodes");
 		total_nodes = cursor + 1;
+		// The triangles are the bulk of the upload (112 B each) and need no host-side check beyond the ranges above: start
+		// their copy and the device repack NOW, so that the DMA runs while the host walks the trees below. `in_flight`
+		// waits for the stream on every way out of this function (the caller may free its arrays after an error return).
+		{
+			int rc0;
+			const rzb_triangle* d_tri_raw = nullptr;
+			if ((rc0 = uploadTo(ctx, ctx->scene_buf[rzb_ctx::kBufTriRaw], s->triangles, s->triangle_count, &d_tri_raw))) return rc0;
+			in_flight.armed = true;
+			if ((rc0 = ensureBuf(ctx, ctx->scene_buf[rzb_ctx::kBufHot], size_t(s->triangle_count) * 48))) return rc0;
+			if ((rc0 = ensureBuf(ctx, ctx->scene_buf[rzb_ctx::kBufCold], size_t(s->triangle_count) * 80))) return rc0;
+			if (s->triangle_count)
+			{
+				k_pack_triangles<<<(s->triangle_count + 127) / 128, 128, 0, ctx->stream>>>(d_tri_raw, s->triangle_count,
+					static_cast<float4*>(ctx->scene_buf[rzb_ctx::kBufHot].ptr), static_cast<float4*>(ctx->scene_buf[rzb_ctx::kBufCold].ptr));
+				ctx->launches += 1;
+			}
+			if ((rc0 = uploadTo(ctx, ctx->scene_buf[rzb_ctx::kBufMeshNodesRaw], s->mesh_nodes, s->mesh_node_count, &d_mesh_nodes_raw))) return rc0;
+			if (s->tri_host_index &&
+				(rc0 = uploadTo(ctx, ctx->scene_buf[rzb_ctx::kBufTriHost], s->tri_host_index, s->triangle_count, static_cast<const uint32_t**>(nullptr)))) return rc0;
+		}
 		// every tree must BE a tree (each node reached once from the root: no cycles, no shared subtrees) and the deepest
 		// one bounds the traversal stack (rzb_device.cuh: Stack)
 		for (uint32_t m = 0; m < s->mesh_count; ++m)
@@ -701,36 +761,6 @@ extern "C" int rzb_set_scene(rzb_ctx* ctx, const rzb_scene* s)
 		inst_host[i] = h.host_index;
 	}
 
-	// ---- materials (+ world material appended), maps
-	std::vector<rzb_material> mats(s->materials, s->materials + s->material_count);
-	mats.push_back(s->world_material);
-	for (const rzb_material& m : mats)
-	{
-		const uint32_t ids[5] = {m.texture, m.normal_map, m.metalness_map, m.roughness_map, m.emission_map};
-		for (uint32_t id : ids)
-			if (id != RZB_NO_INDEX && id >= s->map_count) return fail(ctx, RZB_ERR_INVALID, "rzb_set_scene: map id out of range");
-	}
-	if (ctx->map_pixel_buf.size() < s->map_count) ctx->map_pixel_buf.resize(s->map_count);
-	std::vector<DMap> maps(s->map_count);
-	int rc;
-	for (uint32_t i = 0; i < s->map_count; ++i)
-	{
-		const rzb_map& m = s->maps[i];
-		if (!m.pixels || m.width == 0 || m.height == 0 || m.format > RZB_MAP_R32F)
-			return fail(ctx, RZB_ERR_INVALID, "rzb_set_scene: bad map");
-		const size_t texel = m.format == RZB_MAP_R8 ? 1 : 4;
-		const uint8_t* d_pixels = nullptr;
-		if ((rc = uploadTo(ctx, ctx->map_pixel_buf[i], static_cast<const uint8_t*>(m.pixels), size_t(m.width) * m.height * texel, &d_pixels))) return rc;
-		DMap d{};
-		d.pixels = d_pixels;
-		d.width = m.width; d.height = m.height;
-		d.format = m.format; d.filter = m.filter; d.address = m.address;
-		d.scale_x = m.scale[0]; d.scale_y = m.scale[1];
-		d.rot_sin = sinf(m.rotation); d.rot_cos = cosf(m.rotation);
-		d.trans_x = m.translation[0]; d.trans_y = m.translation[1];
-		maps[i] = d;
-	}
-
 	// ---- uploads straight from the caller's arrays, then device-side repacking into the traversal layout
 	DScene sc{};
 	DeviceBuffer* B = ctx->scene_buf;
@@ -743,15 +773,10 @@ extern "C" int rzb_set_scene(rzb_ctx* ctx, const rzb_scene* s)
 	}
 	else
 	{
-		const rzb_triangle* d_tri_raw = nullptr;
-		const rzb_node* d_mesh_nodes_raw = nullptr;
 		const MeshEntry* d_table = nullptr;
-		if ((rc = uploadTo(ctx, B[rzb_ctx::kBufTriRaw], s->triangles, s->triangle_count, &d_tri_raw))) return rc;
-		if ((rc = uploadTo(ctx, B[rzb_ctx::kBufMeshNodesRaw], s->mesh_nodes, s->mesh_node_count, &d_mesh_nodes_raw))) return rc;
+		// (triangles, raw mesh nodes and the triangle index map went first, before the host-side tree walk)
 		if ((rc = uploadTo(ctx, B[rzb_ctx::kBufMeshTable], table.data(), table.size(), &d_table))) return rc;
 		if ((rc = ensureBuf(ctx, B[rzb_ctx::kBufNodes], total_nodes * 32))) return rc;
-		if ((rc = ensureBuf(ctx, B[rzb_ctx::kBufHot], size_t(s->triangle_count) * 48))) return rc;
-		if ((rc = ensureBuf(ctx, B[rzb_ctx::kBufCold], size_t(s->triangle_count) * 80))) return rc;
 		d_nodes = static_cast<float4*>(B[rzb_ctx::kBufNodes].ptr);
 		RZB_CUDA(ctx, cudaMemsetAsync(d_nodes, 0, total_nodes * 32, ctx->stream));
 		if (s->mesh_node_count)
@@ -760,17 +785,7 @@ extern "C" int rzb_set_scene(rzb_ctx* ctx, const rzb_scene* s)
 				d_table, uint32_t(table.size()), d_nodes);
 			ctx->launches += 1;
 		}
-		if (s->triangle_count)
-		{
-			k_pack_triangles<<<(s->triangle_count + 127) / 128, 128, 0, ctx->stream>>>(d_tri_raw, s->triangle_count,
-				static_cast<float4*>(B[rzb_ctx::kBufHot].ptr), static_cast<float4*>(B[rzb_ctx::kBufCold].ptr));
-			ctx->launches += 1;
-		}
-		if (s->tri_host_index)
-		{
-			if ((rc = uploadTo(ctx, B[rzb_ctx::kBufTriHost], s->tri_host_index, s->triangle_count, static_cast<const uint32_t**>(nullptr)))) return rc;
-		}
-		else
+		if (!s->tri_host_index)
 		{
 			if ((rc = ensureBuf(ctx, B[rzb_ctx::kBufTriHost], size_t(s->triangle_count) * 4))) return rc;
 			if (s->triangle_count)

@@ -15,6 +15,13 @@ host = {k: np.ascontiguousarray(v) for k, v in flat.items()}
 bench.pin(list(host.values()))
 rgba = torch.empty((H, W, 4), dtype=torch.uint8, pin_memory=True).numpy()
 depth = torch.empty((H, W), dtype=torch.float32, pin_memory=True).numpy()
+# the floor of set_scene: one pinned host-to-device copy of the same number of bytes
+nbytes = sum(a.nbytes for a in host.values())
+src = torch.empty(nbytes, dtype=torch.uint8, pin_memory=True)
+dst = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
+for _ in range(2):
+    torch.cuda.synchronize(); t0 = time.perf_counter(); dst.copy_(src, non_blocking=True); torch.cuda.synchronize(); h2d_ms = (time.perf_counter() - t0) * 1e3
+print(json.dumps({"scene_bytes": nbytes, "plain_pinned_h2d_ms": h2d_ms, "GB_per_s": nbytes / h2d_ms / 1e6}))
 with capi.Context(0) as ctx:
     ctx.set_stream(torch.cuda.current_stream().cuda_stream)
     out = {}
