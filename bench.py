@@ -11,6 +11,9 @@ Before anything is timed the renderer runs 2 x max-depth untimed passes (pre-rol
 only coherent camera rays. One JSON line is printed by rank 0:
   value      Mrays/s, whole job, scene and path state resident in HBM, K passes timed on the device (CUDA events on
              the launching stream), barrier + synchronize on both sides, max over ranks
+  stage_ms_per_pass  exclusive device time per launch of the three kernels of a pass: the timed passes replayed with
+             RZB_FLAG_SERIAL_STAGES (in the headline region a pass's shadow kernel shares the GPU with the next pass's
+             closest-hit kernel on a second stream, which is worth ~2 %); the roofline figures use these times
   e2e        the same metric through the reference-facing boundary with HOST buffers: every e2e step is one
              Engine::renderWorld-equivalent frame = rzb_set_scene (host arrays -> device) + rzb_set_camera + rzb_reset
              + rzb_render(rpp passes) + rzb_resolve (tone map, RGBA8 + depth -> pinned host buffers)
@@ -345,6 +348,21 @@ def timed_passes(ctx, torch, stream, steps, warm):
     return a0.elapsed_time(a1), (float(st["last_trace_ms"]), float(st["last_shade_ms"]), float(st["last_shadow_ms"]))
 
 
+STAGE_NOTE = ("exclusive kernel times: replay of the same passes with every kernel in stream order (RZB_FLAG_SERIAL_STAGES); in the "
+              "headline region the shadow kernel of pass p runs on a second stream beside k_trace_paths of pass p + 1")
+
+
+def serial_stage_times(ctx, capi, torch, stream, steps, warm, seed):
+    """Per-kernel device time per launch. The headline region overlaps a pass's shadow kernel with the next pass's closest-hit
+    kernel, so a stage's events there bracket two kernels sharing the GPU; the same passes (counter-based RNG: same rays) are
+    therefore replayed with RZB_FLAG_SERIAL_STAGES and the CUDA events around every stage of (up to 256 of) them are read.
+    Returns (ms of the serial replay, (trace, shade, shadow) ms per launch)."""
+    ctx.set_config(1, 1, MAX_DEPTH, capi.FLAG_SERIAL_STAGES, seed)
+    out = timed_passes(ctx, torch, stream, steps, warm)
+    ctx.set_config(1, 1, MAX_DEPTH, capi.FLAG_NONE, seed)
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -472,9 +490,7 @@ def main():
     barrier()
     clocks = sampler.stop()
     ms = ev0.elapsed_time(ev1)
-    # per-kernel device time per launch: CUDA events recorded around each stage of (up to 256 of) the timed passes
     st = ctx.render_stats()
-    stage_ms = (float(st["last_trace_ms"]), float(st["last_shade_ms"]), float(st["last_shadow_ms"]))
     launches = int(st["kernel_launches"]) - launches0
     if resolver is not None:
         resolver.wait()
@@ -488,6 +504,9 @@ def main():
         ms_max, spp_sum, rays_sum = float(t_max[0].item()), float(t_all[1].item()), float(t_all[2].item())
     value = rays_sum / (ms_max * 1e-3) / 1e6
     spp_per_s = spp_sum / (ms_max * 1e-3)  # completed camera paths per pixel per second, whole job
+
+    # ---- per-kernel device time per launch (serial replay of the timed passes, see serial_stage_times)
+    serial_ms, stage_ms = serial_stage_times(ctx, capi, torch, stream, args.steps, warm, seed)
 
     # ---- both roofs of the dominant kernel (replay of the same passes with the counting kernels)
     roofline = work_and_roofline(ctx, capi, args.steps, warm, seed, n_px, stage_ms,
@@ -551,7 +570,8 @@ def main():
                 f2 = w2.flatten()
                 ctx.set_scene(f2)
                 ctx.set_camera(w2.camera_struct())
-                ms2, stage2 = timed_passes(ctx, torch, stream, n2, warm)
+                ms2, _ = timed_passes(ctx, torch, stream, n2, warm)
+                _, stage2 = serial_stage_times(ctx, capi, torch, stream, n2, warm, seed)
                 aux[secondary] = {"triangles": int(f2["triangles"].shape[0]), "instances": int(f2["instances"].shape[0]),
                                   "value": n2 * n_px / (ms2 * 1e-3) / 1e6, "unit": "Mrays/s", "steps": n2,
                                   "stage_ms_per_pass": {"k_trace_paths": stage2[0], "k_shade": stage2[1], "k_trace_shadow": stage2[2]},
@@ -567,7 +587,8 @@ def main():
                         w3 = build_world(wl)
                         ctx.set_scene(w3.flatten())
                         ctx.set_camera(w3.camera_struct())
-                        ms3, stage3 = timed_passes(ctx, torch, stream, n2, warm)
+                        ms3, _ = timed_passes(ctx, torch, stream, n2, warm)
+                        _, stage3 = serial_stage_times(ctx, capi, torch, stream, n2, warm, seed)
                         own[wl] = {"value": n2 * n_px / (ms3 * 1e-3) / 1e6, "unit": "Mrays/s", "steps": n2,
                                    "stage_ms_per_pass": {"k_trace_paths": stage3[0], "k_shade": stage3[1], "k_trace_shadow": stage3[2]}}
                 except Exception as e:
@@ -601,7 +622,8 @@ def main():
                     "frames": e2e_frames},
             "e2e_dropin": dropin,
             "gpu_launches": launches,
-            "stage_ms_per_pass": {"k_trace_paths": stage_ms[0], "k_shade": stage_ms[1], "k_trace_shadow": stage_ms[2]},
+            "stage_ms_per_pass": {"k_trace_paths": stage_ms[0], "k_shade": stage_ms[1], "k_trace_shadow": stage_ms[2],
+                                  "serial_ms_per_step": serial_ms / args.steps, "note": STAGE_NOTE},
             "roofline": roofline,
             "cpu_baseline": cpu, "aux": aux,
         })

@@ -211,6 +211,11 @@ enum
 	                               no medium scattering / Beer-Lambert, opaque shadows, texture replaces colour */
 	RZB_FLAG_COUNT_WORK = 2,    /* rzb_render counts box tests / triangle tests / shadow rays (rzb_work_counters);
 	                               measurement aid, slower kernels */
+	RZB_FLAG_SERIAL_STAGES = 8, /* rzb_render launches every kernel of a pass in stream order. Without it (default) the
+	                               shadow kernel of pass p runs on a second stream beside the closest-hit kernel of pass
+	                               p + 1 (it only adds to the accumulator, which nothing reads before the next shading
+	                               kernel; about 2 % faster). With it the per-stage times of rzb_render_stats are exclusive
+	                               kernel times: measurement aid */
 	RZB_FLAG_TEMPORAL_REPROJECTION = 4 /* Camera::reproject + spacialReprojection (cuda_camera.cuh:390-426,
 	                               cuda_postprocess_kernel.cu:5-16): when accumulation restarts (rzb_reset after at least one
 	                               rendered pass at the same resolution), the first pass projects every pixel's hit point

@@ -22,6 +22,7 @@ FLAG_NONE = 0
 FLAG_CPU_SEMANTICS = 1
 FLAG_COUNT_WORK = 2
 FLAG_TEMPORAL_REPROJECTION = 4
+FLAG_SERIAL_STAGES = 8  # every kernel of a pass in stream order: exclusive per-stage times (rzb200.h)
 SCENE_REFERENCE_TREES, SCENE_OWN_TREES, SCENE_KEEP_GEOMETRY, SCENE_WIDE_TREES = 0, 1, 2, 4
 MAP_RGBA8, MAP_R8, MAP_R32F = 0, 1, 2
 FILTER_POINT, FILTER_LINEAR = 0, 1

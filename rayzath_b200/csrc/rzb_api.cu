@@ -132,11 +132,19 @@ struct rzb_ctx
 	float sort_min[3] = {0.0f, 0.0f, 0.0f}, sort_extent = 0.0f;
 	float last_sort_ms = 0.0f;
 	uint32_t x_flags = 0;          // internal DScene::flags bits (kFlag*)
+	// The shadow kernel of pass p runs on `stream2` beside the closest-hit kernel of pass p + 1 (it only adds to the
+	// accumulator, which nothing touches before the next k_shade); the two passes use alternating counter sets. Measured
+	// +2.4 % / +2.0 % (1M-triangle / materials scene): one kernel tail per pass is filled. RZB200_OVERLAP=0 or
+	// RZB_FLAG_SERIAL_STAGES put it back in stream order (exclusive per-stage times).
+	bool overlap = true;
+	cudaStream_t stream2 = nullptr;
+	cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+	bool shadow_pending = false;
 	// closest-hit kernel flavour: one ray per lane (default) or several rays per lane with phase voting
 	// (rzb_traverse_mr.cuh, RZB200_TRACE=mr: measured slower on B200, DESIGN.md section 4 -- kept as the measured
 	// alternative; RZB200_MR_RAYS = rays per lane, RZB200_MR_BLOCKS caps its resident blocks per SM)
 	bool trace_mr = false;
-	bool trace_sync = false;       // RZB200_TRACE_SYNC=1: warp-synchronised rounds in the closest-hit kernel (experiment)
+	int trace_mode = 0;            // RZB200_TRACE_MODE: 0 free-running lanes, 1 warp-synchronised rounds (also RZB200_TRACE_SYNC=1)
 	int mr_blocks = 0, mr_k = 2, mr_steps = 2;
 	int mr_grid[2] = {0, 0};       // [FAST]
 	size_t mr_smem = 0;
@@ -375,6 +383,9 @@ extern "C" int rzb_create(int device, rzb_ctx** out)
 	ctx->sm_count = prop.multiProcessorCount;
 	if ((e = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking)) != cudaSuccess) { delete ctx; return cudaFail(nullptr, e, "cudaStreamCreate"); }
 	ctx->stream = ctx->own_stream;
+	if ((e = cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking)) != cudaSuccess) { delete ctx; return cudaFail(nullptr, e, "cudaStreamCreate"); }
+	cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming);
+	cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming);
 	cudaEventCreate(&ctx->ev_begin);
 	cudaEventCreate(&ctx->ev_end);
 	cudaEventCreateWithFlags(&ctx->ev_resolve[0], cudaEventDisableTiming);
@@ -389,7 +400,7 @@ extern "C" int rzb_create(int device, rzb_ctx** out)
 	ctx->debug_sync = std::getenv("RZB200_DEBUG_SYNC") != nullptr;
 	if (const char* env = std::getenv("RZB200_CARVEOUT")) ctx->set_carveout = std::atoi(env) != 0;
 	if (const char* env = std::getenv("RZB200_TRACE")) ctx->trace_mr = std::string(env) == "mr";
-	if (const char* env = std::getenv("RZB200_TRACE_SYNC")) ctx->trace_sync = std::atoi(env) != 0;
+	if (const char* env = std::getenv("RZB200_TRACE_SYNC")) ctx->trace_mode = std::atoi(env) != 0 ? 1 : 0;
 	if (const char* env = std::getenv("RZB200_MR_BLOCKS")) ctx->mr_blocks = std::atoi(env);
 	if (const char* env = std::getenv("RZB200_SORT")) ctx->sort_enabled = std::atoi(env) != 0;
 	if (const char* env = std::getenv("RZB200_SORT_BITS")) ctx->sort_bits = uint32_t(std::min(std::max(std::atoi(env), 1), 6));
@@ -402,6 +413,10 @@ extern "C" int rzb_create(int device, rzb_ctx** out)
 	// 1M-triangle scene, 0.677 -> 0.670 on the materials scene; the result does not depend on the order)
 	ctx->x_flags |= kFlagAnyHitNearFirst;
 	if (const char* env = std::getenv("RZB200_ANYHIT_ORDER")) { if (std::atoi(env) == 0) ctx->x_flags &= ~kFlagAnyHitNearFirst; }
+	// RZB200_OVERLAP=0: a pass's shadow kernel in stream order instead of on a second stream beside the next pass's closest-hit
+	// kernel
+	if (const char* env = std::getenv("RZB200_OVERLAP")) ctx->overlap = std::atoi(env) != 0;
+	if (const char* env = std::getenv("RZB200_TRACE_MODE")) ctx->trace_mode = std::atoi(env) == 1 ? 1 : 0;
 	ctx->trace_grid = gridFor(ctx, reinterpret_cast<const void*>(&k_trace_paths<false, false>), kTraceBlock);
 	ctx->shadow_grid = gridFor(ctx, reinterpret_cast<const void*>(&k_trace_shadow<false>), kTraceBlock);
 	ctx->trace_grid_fast = gridFor(ctx, reinterpret_cast<const void*>(&k_trace_paths<false, true>), kTraceBlock);
@@ -470,6 +485,9 @@ extern "C" void rzb_destroy(rzb_ctx* ctx)
 	if (ctx->h_pick) cudaFreeHost(ctx->h_pick);
 	for (auto& ev : ctx->ev_stage) cudaEventDestroy(ev);
 	cudaStreamDestroy(ctx->own_stream);
+	if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
+	if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+	if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
 	delete ctx;
 }
 
@@ -1040,7 +1058,9 @@ extern "C" int rzb_render(rzb_ctx* ctx, uint32_t passes)
 		f.pass_index = uint32_t(ctx->passes);
 		const bool timed = (p % stride) == 0u;
 		cudaEvent_t* ev = timed ? &ctx->ev_stage[size_t(ctx->sampled_passes) * 5] : nullptr;
-		RZB_CUDA(ctx, cudaMemsetAsync(ctx->d_counters, 0, 12, ctx->stream));
+		// (overlap: the shadow kernel of the previous pass may still be reading its counters -- alternate between two sets)
+		f.counters = ctx->d_counters + ((ctx->overlap && (ctx->passes & 1u)) ? 20 : 0);
+		RZB_CUDA(ctx, cudaMemsetAsync(f.counters, 0, 12, ctx->stream));
 		f.order = (ctx->sort_enabled && ctx->order_valid) ? static_cast<const uint32_t*>(ctx->sort_buf[rzb_ctx::kSortOrder].ptr) : nullptr;
 		if (timed) cudaEventRecord(ev[0], ctx->stream);
 		if (fast && ctx->geom_wide)
@@ -1053,13 +1073,19 @@ extern "C" int rzb_render(rzb_ctx* ctx, uint32_t passes)
 			const MrPathKernel kernel = reinterpret_cast<MrPathKernel>(const_cast<void*>(mrPathKernel(ctx->mr_k, ctx->mr_steps, count, fast)));
 			kernel<<<ctx->mr_grid[fast ? 1 : 0], kMrBlock, ctx->mr_smem, ctx->stream>>>(ctx->sc, f);
 		}
-		else if (ctx->trace_sync && !count) { if (fast) k_trace_paths<false, true, true><<<ctx->trace_grid_fast, kTraceBlock, 0, ctx->stream>>>(ctx->sc, f); else k_trace_paths<false, false, true><<<ctx->trace_grid, kTraceBlock, 0, ctx->stream>>>(ctx->sc, f); }
+		else if (ctx->trace_mode == 1 && !count) { if (fast) k_trace_paths<false, true, 1><<<ctx->trace_grid_fast, kTraceBlock, 0, ctx->stream>>>(ctx->sc, f); else k_trace_paths<false, false, 1><<<ctx->trace_grid, kTraceBlock, 0, ctx->stream>>>(ctx->sc, f); }
 		else if (count) { if (fast) k_trace_paths<true, true><<<ctx->trace_grid_fast, kTraceBlock, 0, ctx->stream>>>(ctx->sc, f); else k_trace_paths<true, false><<<ctx->trace_grid, kTraceBlock, 0, ctx->stream>>>(ctx->sc, f); }
 		else { if (fast) k_trace_paths<false, true><<<ctx->trace_grid_fast, kTraceBlock, 0, ctx->stream>>>(ctx->sc, f); else k_trace_paths<false, false><<<ctx->trace_grid, kTraceBlock, 0, ctx->stream>>>(ctx->sc, f); }
 		if (ctx->debug_sync)
 		{
 			const cudaError_t e = cudaStreamSynchronize(ctx->stream);
 			if (e != cudaSuccess) return cudaFail(ctx, e, ("k_trace_paths, pass " + std::to_string(ctx->passes)).c_str());
+		}
+		if (ctx->shadow_pending)
+		{
+			// the previous pass's shadow kernel adds to the accumulator and reads the shadow queue k_shade refills
+			RZB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));
+			ctx->shadow_pending = false;
 		}
 		if (f.pass_index == 0u && f.reproject_blend > 0.0f)
 		{
@@ -1094,8 +1120,21 @@ extern "C" int rzb_render(rzb_ctx* ctx, uint32_t passes)
 		{
 			// (wide trees: the any-hit walk stays on the binary trees, which are on the device too -- measured faster there:
 			// 64 registers / 8 blocks per SM against 72 / 7, and an any-hit walk gains nothing from nearest-of-four ordering)
-			if (count) k_trace_shadow<true><<<ctx->shadow_grid, kTraceBlock, 0, ctx->stream>>>(ctx->sc, f);
-			else k_trace_shadow<false><<<ctx->shadow_grid, kTraceBlock, 0, ctx->stream>>>(ctx->sc, f);
+			const bool side = ctx->overlap && !count && !ctx->debug_sync && !(ctx->cfg.flags & RZB_FLAG_SERIAL_STAGES);
+			cudaStream_t sh_stream = side ? ctx->stream2 : ctx->stream;
+			if (side)
+			{
+				RZB_CUDA(ctx, cudaEventRecord(ctx->ev_fork, ctx->stream));
+				RZB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream2, ctx->ev_fork, 0));
+			}
+			if (count) k_trace_shadow<true><<<ctx->shadow_grid, kTraceBlock, 0, sh_stream>>>(ctx->sc, f);
+			else k_trace_shadow<false><<<ctx->shadow_grid, kTraceBlock, 0, sh_stream>>>(ctx->sc, f);
+			if (side)
+			{
+				if (timed) cudaEventRecord(ev[3], ctx->stream2);
+				RZB_CUDA(ctx, cudaEventRecord(ctx->ev_join, ctx->stream2));
+				ctx->shadow_pending = true;
+			}
 			ctx->launches += 1;
 			if (ctx->debug_sync)
 			{
@@ -1105,11 +1144,16 @@ extern "C" int rzb_render(rzb_ctx* ctx, uint32_t passes)
 		}
 		if (timed)
 		{
-			cudaEventRecord(ev[3], ctx->stream);
+			if (!ctx->shadow_pending) cudaEventRecord(ev[3], ctx->stream);
 			ctx->sampled_passes += 1;
 		}
 		ctx->passes += 1;
 		if (count) ctx->counted_segments += bandPixels(ctx);
+	}
+	if (ctx->shadow_pending)
+	{
+		RZB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));
+		ctx->shadow_pending = false;
 	}
 	RZB_CUDA(ctx, cudaEventRecord(ctx->ev_end, ctx->stream));
 	RZB_CUDA(ctx, cudaGetLastError());
@@ -1319,9 +1363,9 @@ extern "C" int rzb_get_render_stats(rzb_ctx* ctx, rzb_render_stats* out)
 		}
 		cudaGetLastError();
 	}
-	uint32_t counters[16] = {};
-	RZB_CUDA(ctx, cudaMemcpy(counters, ctx->d_counters, 64, cudaMemcpyDeviceToHost));
-	out->shadow_rays = counters[1]; // of the last pass
+	uint32_t counters[32] = {};
+	RZB_CUDA(ctx, cudaMemcpy(counters, ctx->d_counters, 128, cudaMemcpyDeviceToHost));
+	out->shadow_rays = counters[(ctx->overlap && ctx->passes && ((ctx->passes - 1u) & 1u)) ? 21 : 1]; // of the last pass
 	out->last_render_ms = ctx->last_render_ms;
 	out->last_trace_ms = ctx->last_trace_ms;
 	out->last_shade_ms = ctx->last_shade_ms;

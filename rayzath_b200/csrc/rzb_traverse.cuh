@@ -215,14 +215,13 @@ namespace rzb
 		}
 	}
 
-	// One round: descend from the current node to a leaf, intersect it, pop until a node with a passed box is current
-	// (or the ray is finished). Invariant: an alive lane has a current node whose box test has passed.
+	// The three pieces of a round. Invariant: an alive lane has a current node whose box test has passed.
+	// ---- descend through inner nodes; returns false when neither child was hit (nothing is current: pop next)
 	template <bool ANY, bool STATS, bool FAST, bool WIDE = false>
-	__device__ __forceinline__ void trav_round(const DScene& sc, Trav& t, Stack& st, ParkedRay& park, TraceCounters& cnt)
+	__device__ __forceinline__ bool trav_descend(const DScene& sc, Trav& t, Stack& st, TraceCounters& cnt)
 	{
 		const float4* __restrict__ nodes = sc.nodes;
 		bool have_cur = t.alive;
-		// ---- descend through inner nodes
 		if (t.alive)
 		{
 			while ((t.cur_tc & 0x3FFFFFFFu) == 0u)
@@ -317,8 +316,13 @@ namespace rzb
 				}
 			}
 		}
-		// ---- leaf
-		if (have_cur)
+		return have_cur;
+	}
+
+	// ---- the current node is a leaf: instance-tree leaf = a range of instances to enter one by one; mesh leaf = triangles
+	template <bool ANY, bool STATS, bool FAST, bool WIDE = false>
+	__device__ __forceinline__ void trav_leaf(const DScene& sc, Trav& t, Stack& st, TraceCounters& cnt)
+	{
 		{
 			const uint32_t count = t.cur_tc & 0x3FFFFFFFu;
 			if (!t.in_mesh) st.push(kEntryInstRange | t.cur_begin, t.cur_begin + count);
@@ -356,7 +360,13 @@ namespace rzb
 				}
 			}
 		}
-		// ---- pop until a node with a passed box is current (or the ray is finished)
+	}
+
+	// ---- pop until a node with a passed box is current (or the ray is finished)
+	template <bool ANY, bool STATS, bool FAST, bool WIDE = false>
+	__device__ __forceinline__ void trav_pop(const DScene& sc, Trav& t, Stack& st, ParkedRay& park, TraceCounters& cnt)
+	{
+		const float4* __restrict__ nodes = sc.nodes;
 		while (t.alive)
 		{
 			const bool have = st.sp != 0;
@@ -373,13 +383,17 @@ namespace rzb
 					park.near_ = fdiv(t.near_, t.len);
 					park.far_ = fdiv(t.far_, t.len);
 				}
-				t.o = v3(park.ox, park.oy, park.oz);
-				t.d = v3(park.dx, park.dy, park.dz);
-				t.rcp = reciprocal_rn(t.d);
-				t.margin = margin_for(t.d);
-				t.sbits = ANY ? 0u : sign_bits(t.d);
-				t.near_ = park.near_; t.far_ = park.far_;
-				t.len = 1.0f;
+				// (nothing left on the stack: the walk is over and the world ray is not needed again)
+				if (have)
+				{
+					t.o = v3(park.ox, park.oy, park.oz);
+					t.d = v3(park.dx, park.dy, park.dz);
+					t.rcp = reciprocal_rn(t.d);
+					t.margin = margin_for(t.d);
+					t.sbits = ANY ? 0u : sign_bits(t.d);
+					t.near_ = park.near_; t.far_ = park.far_;
+					t.len = 1.0f;
+				}
 				t.in_mesh = false;
 			}
 			if (!have)
@@ -453,6 +467,16 @@ namespace rzb
 		}
 	}
 
+	// One round: descend from the current node to a leaf, intersect it, pop until a node with a passed box is current
+	// (or the ray is finished).
+	template <bool ANY, bool STATS, bool FAST, bool WIDE = false>
+	__device__ __forceinline__ void trav_round(const DScene& sc, Trav& t, Stack& st, ParkedRay& park, TraceCounters& cnt)
+	{
+		const bool have_cur = trav_descend<ANY, STATS, FAST, WIDE>(sc, t, st, cnt);
+		if (have_cur) trav_leaf<ANY, STATS, FAST, WIDE>(sc, t, st, cnt);
+		trav_pop<ANY, STATS, FAST, WIDE>(sc, t, st, park, cnt);
+	}
+
 	__device__ __forceinline__ void trav_end(const Trav& t, const bool active, const float near_in, const float far_in,
 		const ParkedRay& park, RayResult& res)
 	{
@@ -476,13 +500,19 @@ namespace rzb
 	// with the conservative test (64 registers, 8 blocks per SM): 0.25 free-running vs 0.35 synchronised -- every
 	// render kernel now instantiates SYNC = false, only the one-warp k_raycast keeps SYNC = true.
 	// FAST = true selects the conservative box test (slab_hit) and nearer-entry-first child order.
-	template <bool ANY, bool STATS, bool SYNC = ANY, bool FAST = false, bool WIDE = false>
+	// MODE: 0 = free-running lanes, 1 = warp-synchronised rounds.
+	// Measured and dropped in round 2 ("while-while" rounds): a lane keeps popping and descending until a MESH leaf is current,
+	// then the warp's lanes intersect their leaves together (in trav_round a lane whose descent ends without a leaf sits out
+	// the leaf phase: triangle tests run at 6.8 of 32 lanes on the 1M-triangle scene). Same records, but 1.44 instead of
+	// 0.94 ms per pass (materials scene 0.95 / 0.66; shadow kernel 0.32 / 0.21): every point where lanes wait for each other
+	// costs more than the lanes it fills -- like the synchronised rounds and the multi-ray kernels before.
+	template <bool ANY, bool STATS, int MODE = (ANY ? 1 : 0), bool FAST = false, bool WIDE = false>
 	__device__ __forceinline__ void trace_ray(const DScene& sc, const bool active, const V3 origin, const V3 direction,
 		const float near_in, const float far_in, Stack& st, ParkedRay& park, TraceCounters& cnt, RayResult& res)
 	{
 		Trav t;
 		trav_begin<ANY, STATS, FAST>(sc, t, active, origin, direction, near_in, far_in, st, park, cnt);
-		while (SYNC ? __any_sync(0xFFFFFFFFu, t.alive) != 0 : t.alive)
+		while (MODE == 1 ? __any_sync(0xFFFFFFFFu, t.alive) != 0 : t.alive)
 			trav_round<ANY, STATS, FAST, WIDE>(sc, t, st, park, cnt);
 		trav_end(t, active, near_in, far_in, park, res);
 	}

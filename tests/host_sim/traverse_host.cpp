@@ -217,7 +217,7 @@ static int trav_host_run_impl(const rzb_scene* s, const float* origins, const fl
 		}
 		else
 		{
-			if (mr == 2) trace_ray<false, true, false, true, true>(sc, true, o, d, near_far[2 * i], near_far[2 * i + 1], st, park, cnt, r);
+			if (mr == 2) trace_ray<false, true, 0, true, true>(sc, true, o, d, near_far[2 * i], near_far[2 * i + 1], st, park, cnt, r);
 			else trace_ray<false, true>(sc, true, o, d, near_far[2 * i], near_far[2 * i + 1], st, park, cnt, r);
 			rzb_hit h{};
 			h.instance = RZB_NO_INDEX; h.triangle = RZB_NO_INDEX;
