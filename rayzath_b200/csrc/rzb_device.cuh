@@ -143,25 +143,58 @@ namespace rzb
 
 	struct Stack
 	{
-		uint2* smem; // &smem_stack[0][threadIdx.x], stride blockDim.x
+		// Shared-memory part: &smem_stack[threadIdx.x], stride kTraceBlock entries. On the device it is kept as a 32-bit
+		// shared-window address and accessed with st.shared / ld.shared: as a generic pointer inside this struct the compiler
+		// emitted generic ST.E.64 / LD.E.64 with 64-bit address arithmetic (two registers for the base) for every push and pop.
+#ifdef __CUDA_ARCH__
+		uint32_t smem;
+#else
+		uint2* smem;
+#endif
 		uint2 local[kLocalStack];
 		int sp;
 		static __device__ __forceinline__ int clamp_local(int i) { return i < kLocalStack ? i : kLocalStack - 1; }
+		__device__ __forceinline__ void set_smem(uint2* base_for_thread)
+		{
+#ifdef __CUDA_ARCH__
+			smem = static_cast<uint32_t>(__cvta_generic_to_shared(base_for_thread));
+#else
+			smem = base_for_thread;
+#endif
+		}
+		__device__ __forceinline__ void smem_store(const int i, const uint32_t a, const uint32_t b)
+		{
+#ifdef __CUDA_ARCH__
+			asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(smem + uint32_t(i) * uint32_t(kTraceBlock * 8)), "r"(a), "r"(b) : "memory");
+#else
+			smem[i * kTraceBlock] = make_uint2(a, b);
+#endif
+		}
+		__device__ __forceinline__ uint2 smem_load(const int i) const
+		{
+#ifdef __CUDA_ARCH__
+			uint2 r;
+			asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(r.x), "=r"(r.y) : "r"(smem + uint32_t(i) * uint32_t(kTraceBlock * 8)) : "memory");
+			return r;
+#else
+			return smem[i * kTraceBlock];
+#endif
+		}
 		__device__ __forceinline__ void push(uint32_t a, uint32_t b)
 		{
-			if (sp < kSmemStack) smem[sp * kTraceBlock] = make_uint2(a, b);
+			if (sp < kSmemStack) smem_store(sp, a, b);
 			else local[clamp_local(sp - kSmemStack)] = make_uint2(a, b);
 			++sp;
 		}
 		__device__ __forceinline__ uint2 pop()
 		{
 			--sp;
-			if (sp < kSmemStack) return smem[sp * kTraceBlock];
+			if (sp < kSmemStack) return smem_load(sp);
 			return local[clamp_local(sp - kSmemStack)];
 		}
 		__device__ __forceinline__ uint2 peek() const
 		{
-			if (sp - 1 < kSmemStack) return smem[(sp - 1) * kTraceBlock];
+			if (sp - 1 < kSmemStack) return smem_load(sp - 1);
 			return local[clamp_local(sp - 1 - kSmemStack)];
 		}
 	};

@@ -152,7 +152,7 @@ namespace rzb
 	__device__ __forceinline__ Stack make_stack(uint2* smem_base)
 	{
 		Stack st;
-		st.smem = smem_base + threadIdx.x;
+		st.set_smem(smem_base + threadIdx.x);
 		st.sp = 0;
 		return st;
 	}
@@ -277,9 +277,12 @@ namespace rzb
 		}
 	}
 
+#ifndef RZB_TRACE_BLOCKS
+#define RZB_TRACE_BLOCKS 7
+#endif
 	// MODE: 0 = free-running lanes (default), 1 = warp-synchronised rounds (rzb_traverse.cuh: trace_ray)
 	template <bool STATS, bool FAST, int MODE = 0, bool WIDE = false>
-	__global__ void __launch_bounds__(kTraceBlock, (FAST && !WIDE) ? 8 : 6) k_trace_paths(DScene sc, DFrame f)
+	__global__ void __launch_bounds__(kTraceBlock, (FAST && !WIDE) ? 8 : RZB_TRACE_BLOCKS) k_trace_paths(DScene sc, DFrame f)
 	{
 		__shared__ uint2 smem_stack[kSmemStack * kTraceBlock];
 		__shared__ ParkedRay smem_park[kTraceBlock];
@@ -507,7 +510,11 @@ namespace rzb
 	}
 
 	// ---------------------------------------------------------------- k_shade
-	__global__ void __launch_bounds__(128) k_shade(DScene sc, DFrame f)
+#ifndef RZB_SHADE_BLOCKS
+#define RZB_SHADE_BLOCKS 6
+#endif
+	constexpr int kShadeBlocks = RZB_SHADE_BLOCKS; // resident blocks per SM the register allocation aims at
+	__global__ void __launch_bounds__(128, kShadeBlocks) k_shade(DScene sc, DFrame f)
 	{
 		const uint32_t slot = f.slot_begin + blockIdx.x * blockDim.x + threadIdx.x;
 		uint32_t x = 0, y = 0;

@@ -199,7 +199,7 @@ static int trav_host_run_impl(const rzb_scene* s, const float* origins, const fl
 	}
 	std::vector<uint2> smem(size_t(kSmemStack) * kTraceBlock);
 	Stack st;
-	st.smem = smem.data();
+	st.set_smem(smem.data());
 	st.sp = 0;
 	TraceCounters cnt{0u, 0u, 0u, 0u};
 	uint64_t total[4] = {0, 0, 0, 0};
