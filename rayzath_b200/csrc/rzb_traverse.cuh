@@ -57,12 +57,16 @@ namespace rzb
 	__device__ __forceinline__ V3 reciprocal_rn(const V3& d) { return v3(fdiv(1.0f, d.x), fdiv(1.0f, d.y), fdiv(1.0f, d.z)); }
 	// relative margin of the fast slab test for a ray direction: kSlabMargin, or infinity (= always take the exact
 	// path) when a component is so small that its reciprocal overflows while quotients may not
-	__device__ __forceinline__ float margin_for(const V3& d)
+	__device__ __forceinline__ bool tiny_component(const V3& d)
 	{
 		const float ax = fabsf(d.x), ay = fabsf(d.y), az = fabsf(d.z);
-		const bool tiny = (ax != 0.0f && ax < 1.0e-30f) || (ay != 0.0f && ay < 1.0e-30f) || (az != 0.0f && az < 1.0e-30f);
-		return tiny ? kInf : kSlabMargin;
+		return (ax != 0.0f && ax < 1.0e-30f) || (ay != 0.0f && ay < 1.0e-30f) || (az != 0.0f && az < 1.0e-30f);
 	}
+	__device__ __forceinline__ float margin_for(const V3& d) { return tiny_component(d) ? kInf : kSlabMargin; }
+	// Trav::sbits = sign bits of the direction (bits 0-2) | kSbitsTiny: the margin is kept as this one bit, not as a register
+	constexpr uint32_t kSbitsTiny = 16u; // (bit 3 stays 0: a node of split type 3 never flips)
+	__device__ __forceinline__ uint32_t level_bits(const V3& d) { return sign_bits(d) | (tiny_component(d) ? kSbitsTiny : 0u); }
+	__device__ __forceinline__ float margin_of(const uint32_t sbits) { return (sbits & kSbitsTiny) ? kInf : kSlabMargin; }
 
 	// Fast slab predicate. Returns true when the box is hit AND its entry distance is within the range; tmin_out is
 	// the (approximate, or exact after the fallback) entry distance.
@@ -95,7 +99,10 @@ namespace rzb
 		tmin_out = tmin;
 		if (gap <= bound)
 		{
-			const uint32_t r = slab_exact(n0, n1, o, d, near_, far_, tmin_out);
+			// (through a temporary: a variable whose address goes to the out-of-line function lives in local memory)
+			float te;
+			const uint32_t r = slab_exact(n0, n1, o, d, near_, far_, te);
+			tmin_out = te;
 			return r == 3u;
 		}
 		return !(tmax < near_ || tmin > tmax || tmin > far_);
@@ -126,8 +133,12 @@ namespace rzb
 		tma = tmin[0]; tmb = tmin[1];
 		if (gap <= bound)
 		{
-			ha = slab_exact(a0, a1, o, d, near_, far_, tma) == 3u;
-			hb = slab_exact(b0, b1, o, d, near_, far_, tmb) == 3u;
+			// (through temporaries: handing tma / tmb themselves to the out-of-line function put them into local memory -- one
+			// STL.64 per pair step and two LDL per deferred child in the profile)
+			float ta, tb;
+			ha = slab_exact(a0, a1, o, d, near_, far_, ta) == 3u;
+			hb = slab_exact(b0, b1, o, d, near_, far_, tb) == 3u;
+			tma = ta; tmb = tb;
 			return;
 		}
 		ha = !(tmax[0] < near_ || tmin[0] > tmax[0] || tmin[0] > far_);
@@ -167,7 +178,7 @@ namespace rzb
 	struct Trav
 	{
 		V3 o, d, rcp;               // current level (world first)
-		float margin, near_, far_, len;
+		float near_, far_, len;
 		uint32_t sbits;
 		bool in_mesh, mesh_hit, lext, committed_ext, alive;
 		uint32_t cur_inst, ltri;
@@ -188,9 +199,8 @@ namespace rzb
 		if (ANY && sc.instance_count == 0u && (sc.flags & RZB_FLAG_CPU_SEMANTICS)) t.mask = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
 		t.o = origin; t.d = direction;
 		t.rcp = reciprocal_rn(direction);
-		t.margin = margin_for(direction);
 		t.near_ = near_in; t.far_ = far_in; t.len = 1.0f;
-		t.sbits = ANY ? 0u : sign_bits(direction);
+		t.sbits = ANY ? 0u : level_bits(direction);
 		t.in_mesh = false; t.mesh_hit = false; t.lext = true;
 		t.cur_inst = kNoIndex; t.ltri = kNoIndex;
 		t.lb1 = 0.0f; t.lb2 = 0.0f;
@@ -209,7 +219,7 @@ namespace rzb
 			const float4 n1 = __ldg(sc.nodes + 2 * size_t(sc.top_root) + 1);
 			if (STATS) cnt.top_nodes++;
 			float tmin;
-			t.alive = slab_hit<FAST>(n0, n1, t.o, t.d, t.rcp, t.near_, t.far_, t.margin, tmin);
+			t.alive = slab_hit<FAST>(n0, n1, t.o, t.d, t.rcp, t.near_, t.far_, margin_of(t.sbits), tmin);
 			t.cur_begin = __float_as_uint(n1.z);
 			t.cur_tc = __float_as_uint(n1.w);
 		}
@@ -285,35 +295,30 @@ namespace rzb
 				bool h0, h1;
 				if (FAST)
 				{
-					h0 = slab_hit<true>(p0, p1, t.o, t.d, t.rcp, t.near_, t.far_, t.margin, tm0);
-					h1 = slab_hit<true>(p2, p3, t.o, t.d, t.rcp, t.near_, t.far_, t.margin, tm1);
+					h0 = slab_hit<true>(p0, p1, t.o, t.d, t.rcp, t.near_, t.far_, 0.0f, tm0);
+					h1 = slab_hit<true>(p2, p3, t.o, t.d, t.rcp, t.near_, t.far_, 0.0f, tm1);
 				}
-				else slab_pair_exact(p0, p1, p2, p3, t.o, t.d, t.rcp, t.near_, t.far_, t.margin, h0, h1, tm0, tm1);
+				else slab_pair_exact(p0, p1, p2, p3, t.o, t.d, t.rcp, t.near_, t.far_, margin_of(t.sbits), h0, h1, tm0, tm1);
 				// near child first: `flip` = the second child is the near one
 				// own trees (FAST): nearer entry first; reference trees: by ray sign on the split axis, as the reference does
 				// any hit: the result does not depend on the order; RZB_FLAG_X_ANYHIT_NEAR_FIRST (experiment switch, set by the
 				// context from RZB200_ANYHIT_ORDER) visits the nearer entry first instead of the first child
 				const bool flip = ANY ? ((sc.flags & kFlagAnyHitNearFirst) != 0u && h0 && h1 && tm1 < tm0)
 					: (FAST ? (h0 && h1 && tm1 < tm0) : ((t.sbits >> (t.cur_tc >> 30)) & 1u) != 0u);
-				const bool hit_a = flip ? h1 : h0, hit_b = flip ? h0 : h1;
-				if (hit_a)
-				{
-					// B is deferred with its entry distance: it is range-tested again when popped, i.e. after A's subtree
-					if (hit_b) st.push((t.in_mesh ? kEntryMeshNode : kEntryTopNode) | (t.cur_begin + (flip ? 0u : 1u)),
-						__float_as_uint(flip ? tm0 : tm1));
-					t.cur_tc = __float_as_uint(flip ? p3.w : p1.w);
-					t.cur_begin = __float_as_uint(flip ? p3.z : p1.z);
-				}
-				else if (hit_b)
-				{
-					t.cur_tc = __float_as_uint(flip ? p1.w : p3.w);
-					t.cur_begin = __float_as_uint(flip ? p1.z : p3.z);
-				}
-				else
+				// one straight-line selection for "both hit" (near child first, the other deferred) and "one hit" -- as two
+				// branches the lanes of a warp ran them one after the other
+				if (!(h0 || h1))
 				{
 					have_cur = false;
 					break;
 				}
+				const bool take_b = h1 && (!h0 || flip); // continue with the second child of the pair
+				// the other child is deferred with its entry distance: it is range-tested again when popped, i.e. after the
+				// near subtree has been searched
+				if (h0 && h1) st.push((t.in_mesh ? kEntryMeshNode : kEntryTopNode) | (t.cur_begin + (take_b ? 0u : 1u)),
+					__float_as_uint(take_b ? tm0 : tm1));
+				t.cur_tc = __float_as_uint(take_b ? p3.w : p1.w);
+				t.cur_begin = __float_as_uint(take_b ? p3.z : p1.z);
 			}
 		}
 		return have_cur;
@@ -389,8 +394,7 @@ namespace rzb
 					t.o = v3(park.ox, park.oy, park.oz);
 					t.d = v3(park.dx, park.dy, park.dz);
 					t.rcp = reciprocal_rn(t.d);
-					t.margin = margin_for(t.d);
-					t.sbits = ANY ? 0u : sign_bits(t.d);
+					t.sbits = ANY ? 0u : level_bits(t.d);
 					t.near_ = park.near_; t.far_ = park.far_;
 					t.len = 1.0f;
 				}
@@ -412,23 +416,23 @@ namespace rzb
 				const float4 n0 = make_float4(in.bminx, in.bminy, in.bminz, in.bmaxx);
 				const float4 n1 = make_float4(in.bmaxy, in.bmaxz, 0.0f, 0.0f);
 				float tmin;
-				if (!slab_hit<FAST>(n0, n1, t.o, t.d, t.rcp, t.near_, t.far_, t.margin, tmin)) continue;
+				if (!slab_hit<FAST>(n0, n1, t.o, t.d, t.rcp, t.near_, t.far_, margin_of(t.sbits), tmin)) continue;
 				if (in.mesh_root == kNoIndex) continue;
 				V3 lo, ld;
 				float l;
 				ray_to_local(in, t.o, t.d, lo, ld, l);
 				const float lnear = fmul(t.near_, l), lfar = fmul(t.far_, l);
 				const V3 lrcp = reciprocal_rn(ld);
-				const float lmargin = margin_for(ld);
+				const uint32_t lbits = ANY ? 0u : level_bits(ld);
 				const float4 r0 = __ldg(nodes + 2 * size_t(in.mesh_root));
 				const float4 r1 = __ldg(nodes + 2 * size_t(in.mesh_root) + 1);
 				if (STATS) cnt.mesh_nodes++;
-				if (!slab_hit<FAST>(r0, r1, lo, ld, lrcp, lnear, lfar, lmargin, tmin)) continue;
+				if (!slab_hit<FAST>(r0, r1, lo, ld, lrcp, lnear, lfar, margin_of(lbits), tmin)) continue;
 				t.in_mesh = true; t.mesh_hit = false;
 				t.cur_inst = idx;
 				t.mat_offset = in.mat_offset; t.mat_count = in.mat_count;
-				t.o = lo; t.d = ld; t.rcp = lrcp; t.margin = lmargin; t.len = l;
-				t.sbits = ANY ? 0u : sign_bits(ld);
+				t.o = lo; t.d = ld; t.rcp = lrcp; t.len = l;
+				t.sbits = lbits;
 				t.near_ = lnear; t.far_ = lfar;
 				t.cur_begin = __float_as_uint(r1.z);
 				t.cur_tc = __float_as_uint(r1.w);
@@ -444,7 +448,7 @@ namespace rzb
 			{
 				// late range test (the reference tests the far child after the near subtree has been searched)
 				const float tmin = __uint_as_float(e.y);
-				const float bound = t.margin * fmaxf(fminf(fabsf(tmin), 1.0e30f), 1.0e-30f);
+				const float bound = margin_of(t.sbits) * fmaxf(fminf(fabsf(tmin), 1.0e30f), 1.0e-30f);
 				if (tmin > t.far_ + bound) continue;
 				if (!(tmin < t.far_ - bound))
 				{
