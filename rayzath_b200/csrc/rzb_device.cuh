@@ -128,7 +128,10 @@ namespace rzb
 	// at 1080p, entries in shared memory 20 / 12 / 8 / 4 / 2 -> materials scene 1058 / 1100 / 1108 / 1103 / 1088 Mrays/s,
 	// 1M triangles 1140 / 1159 / 1161 / 1153 / 1135 (at 8 blocks per SM the 20-entry stack left the shadow kernel
 	// almost no L1).
-	constexpr int kSmemStack = 8;
+#ifndef RZB_SMEM_STACK
+#define RZB_SMEM_STACK 8
+#endif
+	constexpr int kSmemStack = RZB_SMEM_STACK;
 	constexpr int kLocalStack = 64;
 	constexpr int kTraceBlock = 128;
 

@@ -773,6 +773,37 @@ def test_ray_ordering_does_not_change_the_result(monkeypatch):
     assert np.allclose(a, b, rtol=1e-4, atol=1e-5)
 
 
+def test_overlapped_shadow_kernel_gives_the_serial_result():
+    """By default the shadow kernel of pass p runs on a second stream beside the closest-hit kernel of pass p + 1 (it only
+    adds to the accumulator, which nothing reads before the next shading kernel). RZB_FLAG_SERIAL_STAGES puts every kernel
+    in stream order. Per pixel the same additions happen in the same order either way: on the heightfield scene (one light:
+    at most one shadow ray per pixel and pass) the accumulators are bit-identical, on the materials scene (two lights: two
+    atomic adds may swap) they agree up to float summation order; stage times are reported in both modes."""
+    for name, exact in (("heightfield", True), ("materials", False)):
+        w = GOLDEN_SCENES[name]()
+        flat, cam = w.flatten(), w.camera_struct()
+        out = {}
+        for flags in (capi.FLAG_NONE, capi.FLAG_SERIAL_STAGES):
+            with capi.Context(0) as c:
+                c.set_scene(flat)
+                c.set_camera(cam)
+                c.set_config(max_depth=8, flags=flags, seed=23)
+                c.reset()
+                c.render(1)   # a call that ends right after its first pass
+                c.render(30)
+                c.render(2)
+                out[flags] = c.read_accum()
+                st = c.render_stats()
+                assert st["passes"] == 33 and st["shadow_rays"] > 0
+                assert st["last_trace_ms"] > 0 and st["last_shade_ms"] > 0 and st["last_shadow_ms"] > 0
+        a, b = out[capi.FLAG_NONE], out[capi.FLAG_SERIAL_STAGES]
+        assert np.array_equal(a[..., 3], b[..., 3])
+        if exact:
+            assert np.array_equal(a, b), name
+        else:
+            assert np.allclose(a, b, rtol=1e-4, atol=1e-5), name
+
+
 def test_mean_samples_is_the_mean_alpha(contexts):
     c = contexts["materials"]
     c.set_config(max_depth=6, seed=2)
