@@ -277,6 +277,9 @@ namespace rzb
 		}
 	}
 
+#ifndef RZB_SHADOW_BLOCKS
+#define RZB_SHADOW_BLOCKS 8
+#endif
 #ifndef RZB_TRACE_BLOCKS
 #define RZB_TRACE_BLOCKS 7
 #endif
@@ -789,7 +792,7 @@ namespace rzb
 	// Dropped: giving finished lanes new rays between synchronised rounds (threshold 1..24 idle lanes) raised the
 	// share of busy lane-rounds from 0.44 to 0.70-0.88 but not the speed (1.28..1.41 ms).
 	template <bool STATS, bool WIDE = false>
-	__global__ void __launch_bounds__(kTraceBlock, WIDE ? 6 : 8) k_trace_shadow(DScene sc, DFrame f)
+	__global__ void __launch_bounds__(kTraceBlock, WIDE ? 6 : RZB_SHADOW_BLOCKS) k_trace_shadow(DScene sc, DFrame f)
 	{
 		__shared__ uint2 smem_stack[kSmemStack * kTraceBlock];
 		__shared__ ParkedRay smem_park[kTraceBlock];

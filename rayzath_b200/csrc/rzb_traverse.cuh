@@ -113,7 +113,7 @@ namespace rzb
 	// largest magnitude -- more cautious than checking each box on its own (a few more exact fallbacks, never a wrong
 	// decision), and 4 instructions per pair cheaper (ncu: the per-box check was 11 % of k_trace_paths' instructions).
 	__device__ __forceinline__ void slab_pair_exact(const float4 a0, const float4 a1, const float4 b0, const float4 b1, const V3& o,
-		const V3& d, const V3& rcp, const float near_, const float far_, const float margin, bool& ha, bool& hb, float& tma, float& tmb)
+		const V3& d, const V3& rcp, const float near_, const float far_, const bool tiny, bool& ha, bool& hb, float& tma, float& tmb)
 	{
 		float tmin[2], tmax[2];
 #pragma unroll
@@ -129,9 +129,12 @@ namespace rzb
 		const float gap = fminf(fminf(fminf(fabsf(tmax[0] - near_), fabsf(tmin[0] - tmax[0])), fabsf(tmin[0] - far_)),
 			fminf(fminf(fabsf(tmax[1] - near_), fabsf(tmin[1] - tmax[1])), fabsf(tmin[1] - far_)));
 		const float mag = fmaxf(fmaxf(fabsf(tmin[0]), fabsf(tmax[0])), fmaxf(fabsf(tmin[1]), fabsf(tmax[1])));
-		const float bound = margin * fmaxf(fminf(mag, 1.0e30f), 1.0e-30f);
+		// `tiny` (a direction component whose reciprocal overflows, margin_for): always the exact path. The floor keeps the
+		// bound above the spacing of denormal products; an infinite magnitude gives an infinite bound (exact path: correct, and
+		// only rays with a zero direction component get there).
+		const float bound = kSlabMargin * fmaxf(mag, 1.0e-30f);
 		tma = tmin[0]; tmb = tmin[1];
-		if (gap <= bound)
+		if (tiny || gap <= bound)
 		{
 			// (through temporaries: handing tma / tmb themselves to the out-of-line function put them into local memory -- one
 			// STL.64 per pair step and two LDL per deferred child in the profile)
@@ -298,7 +301,7 @@ namespace rzb
 					h0 = slab_hit<true>(p0, p1, t.o, t.d, t.rcp, t.near_, t.far_, 0.0f, tm0);
 					h1 = slab_hit<true>(p2, p3, t.o, t.d, t.rcp, t.near_, t.far_, 0.0f, tm1);
 				}
-				else slab_pair_exact(p0, p1, p2, p3, t.o, t.d, t.rcp, t.near_, t.far_, margin_of(t.sbits), h0, h1, tm0, tm1);
+				else slab_pair_exact(p0, p1, p2, p3, t.o, t.d, t.rcp, t.near_, t.far_, (t.sbits & kSbitsTiny) != 0u, h0, h1, tm0, tm1);
 				// near child first: `flip` = the second child is the near one
 				// own trees (FAST): nearer entry first; reference trees: by ray sign on the split axis, as the reference does
 				// any hit: the result does not depend on the order; RZB_FLAG_X_ANYHIT_NEAR_FIRST (experiment switch, set by the
