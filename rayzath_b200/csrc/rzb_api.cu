@@ -131,7 +131,6 @@ struct rzb_ctx
 	DeviceBuffer sort_buf[kSortBufCount];
 	float sort_min[3] = {0.0f, 0.0f, 0.0f}, sort_extent = 0.0f;
 	float last_sort_ms = 0.0f;
-	uint32_t x_flags = 0;          // internal DScene::flags bits (kFlag*)
 	// The shadow kernel of pass p runs on `stream2` beside the closest-hit kernel of pass p + 1 (it only adds to the
 	// accumulator, which nothing touches before the next k_shade); the two passes use alternating counter sets. Measured
 	// +2.4 % / +2.0 % (1M-triangle / materials scene): one kernel tail per pass is filled. RZB200_OVERLAP=0 or
@@ -411,8 +410,6 @@ extern "C" int rzb_create(int device, rzb_ctx** out)
 	if (const char* env = std::getenv("RZB200_SORT_REVERSE")) ctx->order_reversed = std::atoi(env) != 0;
 	// any-hit walks visit the nearer-entry child first (measured: shadow kernel 0.240 -> 0.220 ms per pass on the
 	// 1M-triangle scene, 0.677 -> 0.670 on the materials scene; the result does not depend on the order)
-	ctx->x_flags |= kFlagAnyHitNearFirst;
-	if (const char* env = std::getenv("RZB200_ANYHIT_ORDER")) { if (std::atoi(env) == 0) ctx->x_flags &= ~kFlagAnyHitNearFirst; }
 	// RZB200_OVERLAP=0: a pass's shadow kernel in stream order instead of on a second stream beside the next pass's closest-hit
 	// kernel
 	if (const char* env = std::getenv("RZB200_OVERLAP")) ctx->overlap = std::atoi(env) != 0;
@@ -846,7 +843,7 @@ extern "C" int rzb_set_scene(rzb_ctx* ctx, const rzb_scene* s)
 	sc.default_material = s->default_material;
 	sc.direct_light_count = s->direct_light_count;
 	sc.spot_light_count = s->spot_light_count;
-	sc.flags = ctx->cfg.flags | ctx->x_flags;
+	sc.flags = ctx->cfg.flags;
 	RZB_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); // host staging vectors die at return; the caller may reuse its arrays
 	ctx->sc = sc;
 	if (!keep_geometry)
@@ -923,7 +920,7 @@ extern "C" int rzb_set_config(rzb_ctx* ctx, const rzb_config* config)
 	if (!ctx || !config) return fail(ctx, RZB_ERR_INVALID, "rzb_set_config: NULL argument");
 	if (config->max_depth == 0 || config->max_depth > 255) return fail(ctx, RZB_ERR_INVALID, "rzb_set_config: max_depth must be 1..255");
 	ctx->cfg = *config;
-	ctx->sc.flags = config->flags | ctx->x_flags;
+	ctx->sc.flags = config->flags;
 	return RZB_OK;
 }
 

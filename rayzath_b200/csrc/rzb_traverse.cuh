@@ -43,8 +43,6 @@ namespace rzb
 		cur_tc = leaf ? (ref >> 25) & 15u : 0u;
 		cur_begin = leaf ? ref & 0x1FFFFFFu : ref;
 	}
-	// internal bits of DScene::flags (above the public RZB_FLAG_* bits)
-	constexpr uint32_t kFlagAnyHitNearFirst = 1u << 16;
 
 	// exact predicate (the reference's arithmetic); bit 0 = box, bit 1 = range; tmin returned through the reference
 	__device__ __noinline__ uint32_t slab_exact(const float4 n0, const float4 n1, const V3 o, const V3 d,
@@ -303,11 +301,9 @@ namespace rzb
 				}
 				else slab_pair_exact(p0, p1, p2, p3, t.o, t.d, t.rcp, t.near_, t.far_, (t.sbits & kSbitsTiny) != 0u, h0, h1, tm0, tm1);
 				// near child first: `flip` = the second child is the near one
-				// own trees (FAST): nearer entry first; reference trees: by ray sign on the split axis, as the reference does
-				// any hit: the result does not depend on the order; RZB_FLAG_X_ANYHIT_NEAR_FIRST (experiment switch, set by the
-				// context from RZB200_ANYHIT_ORDER) visits the nearer entry first instead of the first child
-				const bool flip = ANY ? ((sc.flags & kFlagAnyHitNearFirst) != 0u && h0 && h1 && tm1 < tm0)
-					: (FAST ? (h0 && h1 && tm1 < tm0) : ((t.sbits >> (t.cur_tc >> 30)) & 1u) != 0u);
+				// own trees (FAST) and any hit (its result does not depend on the order; measured: an occluder is found sooner than
+				// with the first child first): nearer entry first; reference trees: by ray sign on the split axis, as the reference
+				const bool flip = (ANY || FAST) ? (h0 && h1 && tm1 < tm0) : ((t.sbits >> (t.cur_tc >> 30)) & 1u) != 0u;
 				// one straight-line selection for "both hit" (near child first, the other deferred) and "one hit" -- as two
 				// branches the lanes of a warp ran them one after the other
 				if (!(h0 || h1))

@@ -1,6 +1,6 @@
 #!/usr/bin/env python3
 """Developer probe (GPU): stage times of the render passes under the experiment switches the context reads from the
-environment at creation (RZB200_SORT, RZB200_SORT_BITS, RZB200_ANYHIT_ORDER, RZB200_TRACE ...). One JSON line per
+environment at creation (RZB200_SORT, RZB200_SORT_BITS, RZB200_OVERLAP, RZB200_TRACE ...). One JSON line per
 (workload, variant). Usage: gpu_variants.py [--workloads a,b] [--variants name:K=V;K=V,...] [--passes N]"""
 import argparse
 import json
@@ -14,7 +14,7 @@ import torch
 import bench
 from rayzath_b200 import capi
 
-DEFAULT_VARIANTS = "base:;anyhit1:RZB200_ANYHIT_ORDER=1;sort6:RZB200_SORT=1,RZB200_SORT_BITS=6"
+DEFAULT_VARIANTS = "base:;serial:RZB200_OVERLAP=0;sort6:RZB200_SORT=1,RZB200_SORT_BITS=6"
 
 
 def main():
