@@ -29,6 +29,21 @@ def test_binding_covers_header():
     assert sorted(capi.SYMBOLS) == declared_symbols()
 
 
+def test_flag_constants_match_the_header():
+    """The Python binding's FLAG_* / SCENE_* constants are the header's enumerators."""
+    text = open(os.path.join(ROOT, "include", "rzb200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    enums = {name: int(value, 0) for name, value in re.findall(r"\b(RZB_[A-Z_0-9]+)\s*=\s*(0x[0-9a-fA-F]+|\d+)", text)}
+    checked = 0
+    for py_name, value in vars(capi).items():
+        if py_name.startswith("FLAG_") or py_name.startswith("SCENE_"):
+            c_name = "RZB_" + py_name
+            assert c_name in enums, c_name
+            assert enums[c_name] == value, (c_name, enums[c_name], value)
+            checked += 1
+    assert checked >= 5 and enums["RZB_FLAG_SERIAL_STAGES"] == 8
+
+
 def test_abi_version():
     assert capi.lib().rzb_abi_version() == 3
 
