@@ -17,12 +17,17 @@
 //     kernel showed 38 % of all issued instructions inside division sequences (profiles/);
 //   * the far child is deferred on a short stack (shared memory, interleaved by lane) together with its entry
 //     distance, so the reference's late range test is a compare at pop time instead of a second box test;
-//   * one flat while-while loop serves both levels; the world ray and the committed hit live in shared memory while a
-//     mesh is being walked (they are only touched at instance transitions), which keeps the loop at <= 80 registers.
+//   * one flat loop of rounds (trav_descend / trav_leaf / trav_pop) serves both levels; the world ray and the committed hit
+//     live in shared memory while a mesh is being walked (they are only touched at instance transitions), which keeps the
+//     exact closest-hit kernel at 72 registers (7 blocks per SM) and the conservative ones at 64 (8 blocks);
+//   * the kernels are bound by instruction issue at low SIMT efficiency, so what few lanes execute is kept short: one
+//     straight-line child selection, no out-parameter that forces a value into local memory, the stack addressed as
+//     shared memory, no world-ray restore when a walk is over (profiles/r02_final2_phase_lines.txt).
 // Scenes with own trees (RZB_SCENE_OWN_TREES) and all shadow queries use a conservative box test instead (FAST).
 // What was measured and dropped (B200, 1M-triangle scene): per-lane ray refill (startup = root test +
-// instance transform is too expensive to run for single lanes), warp-private work chunks, vote-scheduled phases and a
-// camera-ray / bounce-ray queue split -- none beat whole-warp batches of 32 neighbouring slots.
+// instance transform is too expensive to run for single lanes), warp-private work chunks, vote-scheduled phases, a
+// camera-ray / bounce-ray queue split, warp-synchronised and while-while rounds, several rays per lane, cache hints --
+// none beat free-running lanes on whole-warp batches of 32 rays that the order pass put next to each other.
 #pragma once
 
 #include "rzb_device.cuh"
