@@ -528,6 +528,8 @@ namespace rzb
 		uint32_t hinst = kNoIndex;
 		if (valid)
 		{
+			// the pixel's accumulator is read-modified-written at the very end: start bringing it in now
+			asm volatile("prefetch.global.L2 [%0];" ::"l"(f.accum + (size_t(y) * f.cam.width + x)));
 			so = ld_s(f.st_o + slot); sd = ld_s(f.st_d + slot); scol = ld_s(f.st_c + slot);
 			ha = ld_s(f.hit_a + slot); hinst = ld_s(f.hit_inst + slot);
 		}
