@@ -472,14 +472,21 @@ def main():
     # ---- pre-roll + warm-up (untimed), then the timed region: K passes (+ the exchange step), device-timed on the
     # launching stream. The pre-roll (2 x max depth passes) puts paths of every depth in flight: the first passes after
     # a reset trace only coherent camera rays and would flatter the number.
+    # The W warm-up steps run IMMEDIATELY in front of the timed region: whatever leaves the GPU idle for milliseconds (NVML
+    # set-up of the clock sampler, reading an accumulator back) happens before them, and the completed-paths figure in front
+    # of the timed region comes from the device-side reduction (rzb_mean_samples, 8 bytes back). With the driver's 20-step
+    # window (24 ms) an idle gap in front of it cost 4 % (1694 against 1765 Mrays/s for 512 steps).
     warm = PREROLL + args.warmup
-    ctx.render(warm)
+    ctx.render(PREROLL)
     combine()
     barrier()
-    alpha0 = float(ctx.read_accum()[..., 3].mean())
-    launches0 = int(ctx.render_stats()["kernel_launches"])
     sampler = ClockSampler(local_rank)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    frame_share = float(n_px) / float(W * H)  # this rank's pixels / frame pixels (1 unless the frame is split into bands)
+    ctx.render(args.warmup)
+    combine()
+    alpha0 = ctx.mean_samples() * frame_share
+    launches0 = int(ctx.render_stats()["kernel_launches"])
     barrier()
     sampler.start()
     ev0.record(stream)
@@ -494,7 +501,7 @@ def main():
     launches = int(st["kernel_launches"]) - launches0
     if resolver is not None:
         resolver.wait()
-    t_all = torch.tensor([ms, (float(ctx.read_accum()[..., 3].mean()) - alpha0), float(args.steps) * n_px],
+    t_all = torch.tensor([ms, (ctx.mean_samples() * frame_share - alpha0), float(args.steps) * n_px],
                          dtype=torch.float64, device="cuda")
     ms_max, spp_sum, rays_sum = float(t_all[0].item()), float(t_all[1].item()), float(t_all[2].item())
     if dist is not None:

@@ -135,6 +135,7 @@ struct rzb_ctx
 	// accumulator, which nothing touches before the next k_shade); the two passes use alternating counter sets. Measured
 	// +2.4 % / +2.0 % (1M-triangle / materials scene): one kernel tail per pass is filled. RZB200_OVERLAP=0 or
 	// RZB_FLAG_SERIAL_STAGES put it back in stream order (exclusive per-stage times).
+	uint32_t stage_stride = 0;     // RZB200_STAGE_STRIDE: 0 = automatic (see rzb_render)
 	bool overlap = true;
 	cudaStream_t stream2 = nullptr;
 	cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
@@ -411,6 +412,7 @@ extern "C" int rzb_create(int device, rzb_ctx** out)
 	// RZB200_OVERLAP=0: a pass's shadow kernel in stream order instead of on a second stream beside the next pass's closest-hit
 	// kernel
 	if (const char* env = std::getenv("RZB200_OVERLAP")) ctx->overlap = std::atoi(env) != 0;
+	if (const char* env = std::getenv("RZB200_STAGE_STRIDE")) ctx->stage_stride = uint32_t(std::max(std::atoi(env), 1));
 	if (const char* env = std::getenv("RZB200_TRACE_MODE")) ctx->trace_mode = std::atoi(env) == 1 ? 1 : 0;
 	ctx->trace_grid = gridFor(ctx, reinterpret_cast<const void*>(&k_trace_paths<false, false>), kTraceBlock);
 	ctx->shadow_grid = gridFor(ctx, reinterpret_cast<const void*>(&k_trace_shadow<false>), kTraceBlock);
@@ -998,7 +1000,12 @@ extern "C" int rzb_render(rzb_ctx* ctx, uint32_t passes)
 	f.prev_cam = makeDeviceCamera(ctx->prev_cam);
 	f.reproject_blend = ctx->has_prev ? ctx->cam.temporal_blend : 0.0f;
 	// per-stage device timing: up to 256 passes of this call are bracketed by events (4 per sampled pass)
-	const uint32_t stride = (passes + 255u) / 256u;
+	// With the shadow kernel overlapped (default) a stage's events bracket kernels that share the GPU, so the figures are
+	// indicative only: every 8th pass is sampled there (five event records per sampled pass cost 13 us of a 1.2 ms pass:
+	// 1.216 -> 1.203 ms per pass in a 20-pass call). In stream order (RZB_FLAG_SERIAL_STAGES, counting kernels,
+	// RZB200_OVERLAP=0) every pass is sampled. RZB200_STAGE_STRIDE overrides the stride.
+	const bool overlapped = ctx->overlap && lights && !count && !ctx->debug_sync && !(ctx->cfg.flags & RZB_FLAG_SERIAL_STAGES);
+	const uint32_t stride = std::max((passes + 255u) / 256u, ctx->stage_stride ? ctx->stage_stride : (overlapped ? 8u : 1u));
 	const uint32_t n_sampled = passes ? (passes + stride - 1u) / stride : 0u;
 	const uint32_t n_slots = f.slot_end - f.slot_begin;
 	// ---- ray ordering set-up: bin tables = [camera groups | bounce bins | 1 bin for slots without a pixel | shadow bins]
